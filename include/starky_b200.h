@@ -1,0 +1,172 @@
+/*
+ * starky_b200.h -- C ABI of libstarkyb200.so, the B200-native (sm_100a) replacement for the
+ * data-parallel core of starky::prover::prove as called by Electron-Labs/starky_bls12_381.
+ *
+ * Drop-in boundary.  The reference has no FFI today; the entry points below are
+ * what a Rust `extern "C"` block in a `starky-gpu` crate would bind so that
+ *     starky::prover::prove::<F, C, S, 2>(stark, &config, trace_poly_values, &public_inputs, &mut timing)
+ * (/root/reference/src/aggregate_proof.rs:59,105,138,169,212 and ecc_aggregate.rs:545) can be served by
+ * sb_prove() for F = GoldilocksField, C = PoseidonGoldilocksConfig, D = 2 and S one of the five starks.
+ * The Rust shim is in rust/starky_gpu/ (source only: no cargo in the build image); INTEGRATION.md shows it.
+ *
+ * All field elements are canonical Goldilocks values (uint64_t in [0, 2^64 - 2^32 + 1)).
+ * Extension elements F_p[X]/(X^2-7) are two consecutive uint64_t (c0, c1).
+ * No function aborts across the boundary: every failure is a negative return code + sb_last_error().
+ */
+#ifndef STARKY_B200_H
+#define STARKY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (reference behaviour: Err(anyhow) / panic, aggregate_proof.rs:65,67) ---- */
+#define SB_OK 0
+#define SB_EINVAL (-1)                  /* bad argument / shape mismatch with the constraint program      */
+#define SB_ECUDA (-2)                   /* CUDA runtime failure (message in sb_last_error)                 */
+#define SB_ENCCL (-3)                   /* reserved: collective failure                                    */
+#define SB_EQUOTIENT_NOT_DIVISIBLE (-4) /* reference: panic "Quotient has failed, the vanishing polynomial is not divisible by Z_H" */
+#define SB_EZETA_IN_SUBGROUP (-5)       /* reference: Err("Opening point is in the subgroup.")             */
+#define SB_EPOW (-6)                    /* reference: expect("Proof of work failed...")                    */
+#define SB_ENOMEM (-7)
+#define SB_EAIR (-8)                    /* constraint program missing / malformed                          */
+
+/* ---- stark identity: selects the constraint program (the C side cannot call eval_packed_generic) ---- */
+enum sb_stark_id {
+  SB_STARK_FP12_MUL = 0,        /* fp12_mul.rs:31            60285 cols, degree 3 */
+  SB_STARK_PAIRING_PRECOMP = 1, /* calc_pairing_precomp.rs:135 29376 cols, degree 4 */
+  SB_STARK_MILLER_LOOP = 2,     /* miller_loop.rs:81         97330 cols, degree 3 */
+  SB_STARK_FINAL_EXP = 3,       /* final_exponentiate.rs:131 73527 cols, degree 5 */
+  SB_STARK_ECC_AGG = 4,         /* ecc_aggregate.rs:23        3339 cols, degree 4 */
+  SB_STARK_CUSTOM = 100         /* any AIR loaded with sb_air_load (tests)        */
+};
+
+/* ---- trace layouts accepted by sb_prove / sb_lde_commit ---- */
+enum sb_trace_layout {
+  SB_TRACE_COLMAJOR_U64 = 0, /* one [n_cols][n] block; column c at trace + c*n            (Vec<PolynomialValues<F>> flattened) */
+  SB_TRACE_COLS_U64_PTRS = 1, /* const uint64_t* const* : n_cols pointers to n values each (Vec<PolynomialValues<F>> as is, aggregate_proof.rs:57) */
+  SB_TRACE_ROWMAJOR_U64 = 2, /* [n][n_cols], the Vec<[F; COLUMNS]> that generate_trace returns (skips trace_rows_to_poly_values) */
+  SB_TRACE_ROWMAJOR_U32 = 3, /* [n][n_cols] uint32_t: every cell the reference writes is < 2^32 (utils.rs:7-19) */
+  SB_TRACE_DEVICE_COLMAJOR_U64 = 4 /* as COLMAJOR_U64 but `trace` is a device pointer on the ctx's GPU */
+};
+
+/* ---- flags ---- */
+#define SB_FLAG_ALLOW_INVALID_TRACE 1u /* benchmarking on random traces: drop (instead of rejecting) non-zero high quotient coefficients */
+#define SB_FLAG_FIXED_POW_WITNESS 2u   /* use params.fixed_pow_witness instead of grinding (transcript-exact replay of an oracle/reference run) */
+#define SB_FLAG_OBSERVE_PUBLIC_INPUTS 4u /* observe PIs before the trace cap (off = the pinned plonky2 era) */
+#define SB_FLAG_FRI_MUL_BY_X 8u        /* older plonky2 multiplied the FRI final polynomial by X (off by default) */
+
+/* Mirrors starky::config::StarkConfig + the per-stark constants (aggregate_proof.rs:32-33,76,122,155-156,186-187). */
+typedef struct sb_params {
+  uint32_t stark_id;          /* enum sb_stark_id                                              */
+  uint32_t log_n;             /* trace rows n = 2^log_n                                        */
+  uint32_t n_cols;            /* S::COLUMNS                                                    */
+  uint32_t n_public_inputs;   /* S::PUBLIC_INPUTS                                              */
+  uint32_t constraint_degree; /* Stark::constraint_degree()                                    */
+  uint32_t rate_bits;         /* config.fri_config.rate_bits (1, or 2 for PP/FE/ECC)           */
+  uint32_t cap_height;        /* 4                                                             */
+  uint32_t num_challenges;    /* 2                                                             */
+  uint32_t pow_bits;          /* 16                                                            */
+  uint32_t num_query_rounds;  /* 84                                                            */
+  uint32_t fri_arity_bits;    /* ConstantArityBits(4, 5): arity bits                           */
+  uint32_t fri_final_poly_bits; /* ... and final poly bits                                     */
+  uint32_t flags;
+  uint32_t reserved;
+  uint64_t fixed_pow_witness;
+} sb_params;
+
+/* StarkConfig::standard_fast_config() with the per-stark rate_bits override; fills everything but log_n/flags. */
+int sb_params_standard(uint32_t stark_id, uint32_t log_n, sb_params* out);
+
+/* ---- proof object: a flat uint64_t buffer (POD) with the field order of
+ *      starky::proof::StarkProofWithPublicInputs<F, C, 2> (SURVEY 8b "Proof object to fill") ---- */
+typedef struct sb_proof_layout {
+  uint32_t log_n, log_lde, n_cols, n_quotient_polys, n_public_inputs, cap_len, n_fri_rounds, final_poly_len;
+  uint32_t n_queries, arity_bits, trace_path_len, reserved;
+  uint64_t off_trace_cap;      /* [cap_len][4]                                                    */
+  uint64_t off_quotient_cap;   /* [cap_len][4]                                                    */
+  uint64_t off_local_values;   /* openings.local_values   [n_cols][2]                            */
+  uint64_t off_next_values;    /* openings.next_values    [n_cols][2]                            */
+  uint64_t off_quotient_polys; /* openings.quotient_polys [nq][2]                                */
+  uint64_t off_fri_caps;       /* commit_phase_merkle_caps [n_fri_rounds][cap_len][4]            */
+  uint64_t off_final_poly;     /* final_poly [final_poly_len][2]                                 */
+  uint64_t off_pow_witness;    /* 1                                                               */
+  uint64_t off_queries;        /* n_queries records of query_stride words                        */
+  uint64_t query_stride;
+  /* inside one query record: */
+  uint64_t q_off_trace_leaf;   /* [n_cols]                                                        */
+  uint64_t q_off_trace_path;   /* [trace_path_len][4]                                             */
+  uint64_t q_off_quot_leaf;    /* [nq]                                                            */
+  uint64_t q_off_quot_path;    /* [trace_path_len][4]                                             */
+  uint64_t q_off_steps;        /* round r: evals [2^arity][2] then path [step_path_len(r)][4], packed */
+  uint64_t off_public_inputs;  /* [n_public_inputs]                                               */
+  uint64_t total_words;
+} sb_proof_layout;
+
+/* Computes the layout for the given parameters (pure host arithmetic). */
+int sb_proof_layout_for(const sb_params* p, sb_proof_layout* out);
+/* Merkle path length of FRI round r's tree in that layout. */
+uint32_t sb_fri_step_path_len(const sb_proof_layout* l, uint32_t round);
+/* Word offset, inside one query record, of FRI round r's step. */
+uint64_t sb_fri_step_offset(const sb_proof_layout* l, uint32_t round);
+
+typedef struct sb_ctx sb_ctx;
+typedef struct sb_proof {
+  sb_proof_layout layout;
+  uint64_t* words; /* layout.total_words canonical u64, owned by the library */
+  /* stage timings of this proof, milliseconds, CUDA events (TimingTree scopes of starky::prover::prove) */
+  float ms_h2d, ms_trace_commit, ms_quotient, ms_quotient_commit, ms_openings, ms_fri, ms_d2h, ms_total;
+} sb_proof;
+
+/* ---- lifecycle ---- */
+int sb_init(const int* devices, int n_devices, sb_ctx** out); /* devices == NULL: current device */
+void sb_destroy(sb_ctx* ctx);
+const char* sb_last_error(sb_ctx* ctx); /* ctx may be NULL: last error of this thread */
+
+/* ---- constraint programs ("AIR") ---- */
+/* Load a compiled constraint program (tools/airgen output) and bind it to a stark id on this ctx.
+ * The five standard ids are auto-loaded from $SB_AIR_DIR (default: <library dir>/../air) on first use. */
+int sb_air_load(sb_ctx* ctx, uint32_t stark_id, const char* path);
+
+/* ---- the hot path: replaces starky::prover::prove ---- */
+int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout,
+             const uint64_t* public_inputs, sb_proof** out);
+void sb_proof_free(sb_proof* proof);
+
+/* ---- stage-level entry points (parity tests and benchmarks; SURVEY 8b "Stage-level exports") ----
+ * Device buffers stay resident in the ctx between stage calls of one proof. */
+
+/* PolynomialBatch::from_values: iNTT, coset LDE (shift 7), Poseidon Merkle tree to the cap.
+ * lde_out (optional, host): [n_cols][N] values in LEAF order (index = bitrev(natural LDE index)),
+ * digests_out (optional, host): [N][4] leaf digests, cap_out (optional, host): [2^cap_height][4]. */
+int sb_lde_commit(sb_ctx* ctx, const sb_params* p, const void* trace, int layout,
+                  uint64_t* lde_out, uint64_t* digests_out, uint64_t* cap_out);
+/* compute_quotient_polys up to (excluding) coset_ifft: q_j(x_i) for both challenges.
+ * Needs a preceding sb_lde_commit on this ctx.  out (host): [num_challenges][N] in NATURAL LDE index order. */
+int sb_quotient_values(sb_ctx* ctx, const sb_params* p, const uint64_t* public_inputs,
+                       const uint64_t* alphas, uint64_t* out);
+/* Batched forward/inverse NTT of `count` length-2^log_n vectors (natural order in and out). */
+int sb_ntt_batch(sb_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t count, int inverse);
+/* `count` Poseidon-12 permutations on host states [count][12]. */
+int sb_poseidon_permute_batch(sb_ctx* ctx, uint64_t* states, uint32_t count);
+/* hash_or_noop of `count` leaves of `leaf_len` elements: leaves given column-major [leaf_len][count]. */
+int sb_hash_leaves(sb_ctx* ctx, const uint64_t* cols, uint32_t leaf_len, uint32_t count, uint64_t* digests_out);
+
+/* ---- device-resident benchmarking hooks (bench.py `value` leg: inputs already in HBM) ---- */
+/* Upload a trace once; subsequent sb_prove(..., trace=NULL, layout=SB_TRACE_DEVICE_COLMAJOR_U64) re-uses it. */
+int sb_trace_upload(sb_ctx* ctx, const sb_params* p, const void* trace, int layout);
+/* Number of kernels this ctx has launched so far (bench.py gpu_launches). */
+uint64_t sb_kernel_launches(sb_ctx* ctx);
+/* Milliseconds (CUDA events, on the ctx stream) of named stages of the last sb_prove / stage call:
+ * "lde", "leaf_hash", "merkle", "quotient", ... returns <0 if unknown. */
+float sb_stage_ms(sb_ctx* ctx, const char* stage);
+/* dependent-free u32 multiply-add throughput microbenchmark (Gop/s), the IMAD roofline denominator. */
+int sb_measure_imad_peak(sb_ctx* ctx, double* gops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARKY_B200_H */
