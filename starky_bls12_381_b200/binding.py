@@ -1,0 +1,226 @@
+"""ctypes binding of libstarkyb200.so -- one Python name per C entry point of include/starky_b200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class SbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libstarkyb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class StarkId:
+    FP12_MUL, PAIRING_PRECOMP, MILLER_LOOP, FINAL_EXP, ECC_AGG, CUSTOM = 0, 1, 2, 3, 4, 100
+
+
+class TraceLayout:
+    COLMAJOR_U64, COLS_U64_PTRS, ROWMAJOR_U64, ROWMAJOR_U32, DEVICE_COLMAJOR_U64 = 0, 1, 2, 3, 4
+
+
+class Flags:
+    ALLOW_INVALID_TRACE, FIXED_POW_WITNESS, OBSERVE_PUBLIC_INPUTS, FRI_MUL_BY_X = 1, 2, 4, 8
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "stark_id", "log_n", "n_cols", "n_public_inputs", "constraint_degree", "rate_bits", "cap_height",
+        "num_challenges", "pow_bits", "num_query_rounds", "fri_arity_bits", "fri_final_poly_bits", "flags",
+        "reserved")] + [("fixed_pow_witness", C.c_uint64)]
+
+    def copy(self):
+        q = Params()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(Params))
+        return q
+
+
+class ProofLayout(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "log_n", "log_lde", "n_cols", "n_quotient_polys", "n_public_inputs", "cap_len", "n_fri_rounds",
+        "final_poly_len", "n_queries", "arity_bits", "trace_path_len", "reserved")] + [(n, C.c_uint64) for n in (
+        "off_trace_cap", "off_quotient_cap", "off_local_values", "off_next_values", "off_quotient_polys",
+        "off_fri_caps", "off_final_poly", "off_pow_witness", "off_queries", "query_stride", "q_off_trace_leaf",
+        "q_off_trace_path", "q_off_quot_leaf", "q_off_quot_path", "q_off_steps", "off_public_inputs",
+        "total_words")]
+
+
+class _CProof(C.Structure):
+    _fields_ = [("layout", ProofLayout), ("words", C.POINTER(C.c_uint64))] + [(n, C.c_float) for n in (
+        "ms_h2d", "ms_trace_commit", "ms_quotient", "ms_quotient_commit", "ms_openings", "ms_fri", "ms_d2h",
+        "ms_total")]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libstarkyb200.so")
+
+
+def lib():
+    """Load the CUDA library.  There is no CPU fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C starky_bls12_381_b200/csrc); there is no CPU fallback" % path)
+        L = C.CDLL(path)
+        L.sb_last_error.restype = C.c_char_p
+        L.sb_last_error.argtypes = [C.c_void_p]
+        L.sb_init.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.sb_destroy.argtypes = [C.c_void_p]
+        L.sb_params_standard.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(Params)]
+        L.sb_proof_layout_for.argtypes = [C.POINTER(Params), C.POINTER(ProofLayout)]
+        L.sb_fri_step_path_len.argtypes = [C.POINTER(ProofLayout), C.c_uint32]
+        L.sb_fri_step_path_len.restype = C.c_uint32
+        L.sb_fri_step_offset.argtypes = [C.POINTER(ProofLayout), C.c_uint32]
+        L.sb_fri_step_offset.restype = C.c_uint64
+        L.sb_air_load.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p]
+        L.sb_prove.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p,
+                               C.POINTER(C.POINTER(_CProof))]
+        L.sb_proof_free.argtypes = [C.POINTER(_CProof)]
+        L.sb_lde_commit.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]
+        L.sb_coeffs_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.sb_quotient_values.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sb_ntt_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.sb_poseidon_permute_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.sb_hash_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.sb_trace_upload.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int]
+        L.sb_kernel_launches.argtypes = [C.c_void_p]
+        L.sb_kernel_launches.restype = C.c_uint64
+        L.sb_stage_ms.argtypes = [C.c_void_p, C.c_char_p]
+        L.sb_stage_ms.restype = C.c_float
+        L.sb_measure_imad_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        _LIB = L
+    return _LIB
+
+
+def standard_params(stark_id, log_n, flags=0):
+    p = Params()
+    rc = lib().sb_params_standard(stark_id, log_n, C.byref(p))
+    if rc:
+        raise SbError(rc, "sb_params_standard")
+    p.flags = flags
+    return p
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Proof:
+    """Owns one sb_proof; `words` is a numpy view of the flat POD (copied out on construction)."""
+
+    def __init__(self, cproof):
+        c = cproof.contents
+        self.layout = ProofLayout()
+        C.memmove(C.byref(self.layout), C.byref(c.layout), C.sizeof(ProofLayout))
+        n = self.layout.total_words
+        self.words = np.ctypeslib.as_array(c.words, shape=(n,)).copy()
+        self.timings = {k: getattr(c, k) for k in ("ms_h2d", "ms_trace_commit", "ms_quotient", "ms_quotient_commit",
+                                                   "ms_openings", "ms_fri", "ms_d2h", "ms_total")}
+        lib().sb_proof_free(cproof)
+
+    def field(self, name, count):
+        off = getattr(self.layout, name)
+        return self.words[off:off + count]
+
+
+class Context:
+    """One sb_ctx: one GPU, one stream, resident device buffers reused across proofs.  Not re-entrant."""
+
+    def __init__(self, device=None):
+        self._h = C.c_void_p()
+        if device is None:
+            rc = lib().sb_init(None, 0, C.byref(self._h))
+        else:
+            arr = (C.c_int * 1)(int(device))
+            rc = lib().sb_init(arr, 1, C.byref(self._h))
+        if rc:
+            raise SbError(rc, lib().sb_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            lib().sb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise SbError(rc, lib().sb_last_error(self._h).decode())
+
+    def air_load(self, stark_id, path):
+        self._check(lib().sb_air_load(self._h, stark_id, os.fsencode(path)))
+
+    def trace_upload(self, p, trace, layout=TraceLayout.COLMAJOR_U64):
+        self._check(lib().sb_trace_upload(self._h, C.byref(p), _ptr(trace), layout))
+
+    def lde_commit(self, p, trace, layout=TraceLayout.COLMAJOR_U64, want_lde=True, want_digests=True):
+        N = 1 << (p.log_n + p.rate_bits)
+        lde = np.empty((p.n_cols, N), np.uint64) if want_lde else None
+        dig = np.empty((N, 4), np.uint64) if want_digests else None
+        cap = np.empty((1 << p.cap_height, 4), np.uint64)
+        self._check(lib().sb_lde_commit(self._h, C.byref(p), _ptr(trace), layout, _ptr(lde), _ptr(dig), _ptr(cap)))
+        return dict(lde=lde, digests=dig, cap=cap)
+
+    def coeffs(self, p):
+        out = np.empty((p.n_cols, 1 << p.log_n), np.uint64)
+        self._check(lib().sb_coeffs_download(self._h, _ptr(out)))
+        return out
+
+    def quotient_values(self, p, public_inputs, alphas):
+        N = 1 << (p.log_n + p.rate_bits)
+        out = np.empty((p.num_challenges, N), np.uint64)
+        pis, al = _u64(public_inputs), _u64(alphas)
+        self._check(lib().sb_quotient_values(self._h, C.byref(p), _ptr(pis), _ptr(al), _ptr(out)))
+        return out
+
+    def ntt_batch(self, data, inverse=False):
+        d = _u64(data).copy()
+        count, n = d.shape
+        self._check(lib().sb_ntt_batch(self._h, _ptr(d), int(n).bit_length() - 1, count, int(inverse)))
+        return d
+
+    def poseidon_permute_batch(self, states):
+        s = _u64(states).copy()
+        self._check(lib().sb_poseidon_permute_batch(self._h, _ptr(s), s.shape[0]))
+        return s
+
+    def hash_leaves(self, cols):
+        c = _u64(cols)
+        out = np.empty((c.shape[1], 4), np.uint64)
+        self._check(lib().sb_hash_leaves(self._h, _ptr(c), c.shape[0], c.shape[1], _ptr(out)))
+        return out
+
+    def prove(self, p, trace, public_inputs, layout=TraceLayout.COLMAJOR_U64):
+        out = C.POINTER(_CProof)()
+        pis = _u64(public_inputs)
+        self._check(lib().sb_prove(self._h, C.byref(p), _ptr(trace), layout, _ptr(pis), C.byref(out)))
+        return Proof(out)
+
+    def kernel_launches(self):
+        return int(lib().sb_kernel_launches(self._h))
+
+    def stage_ms(self, name):
+        return float(lib().sb_stage_ms(self._h, name.encode()))
+
+    def measure_imad_peak(self):
+        out = (C.c_double * 2)()
+        self._check(lib().sb_measure_imad_peak(self._h, out))
+        return {"mad_lo_u32_gops": out[0], "mad_wide_u32_gops": out[1]}

@@ -1,0 +1,105 @@
+// K2 / K3: Poseidon-12 Merkle commitment of an LDE batch for sm_100a.
+// Replaces plonky2::hash::merkle_tree::MerkleTree::new(leaves, cap_height) with PoseidonHash::hash_or_noop leaves
+// and two_to_one inner nodes, as called from PolynomialBatch::from_values / from_coeffs
+// inside starky::prover::prove (reference call sites /root/reference/src/aggregate_proof.rs:59,105,138,169,212).
+//
+// The LDE is never transposed into plonky2's Vec<Vec<F>> leaves: a leaf is "all columns at one position" of the
+// column-major [C][N] batch, so the thread(s) owning a position stream down the columns (coalesced across positions)
+// through the rate-8 overwrite sponge and scatter only the 32-byte digest to plonky2's leaf index.
+//
+// Tree storage: one buffer of 4-word digests, level 0 (N leaf digests, plonky2 leaf order) first, then N/2, ...
+// down to the cap (2^cap_height digests).  Level l starts at digest offset 2N - (2N >> l).
+#include "common.cuh"
+#include "poseidon.cuh"
+
+// position (coset-major, see ntt.cu) -> plonky2 leaf index:  J*n + k  ->  J*n + bitrev_n(k)
+__device__ __forceinline__ uint32_t leaf_index_of(uint32_t pos, unsigned log_block) {
+  uint32_t mask = (1u << log_block) - 1;
+  return (pos & ~mask) | bitrev32(pos & mask, log_block);
+}
+
+// One thread per leaf.  cols: [leaf_len][n_leaves].
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                        uint32_t n_leaves, unsigned log_block,
+                                                        u64* __restrict__ digests) {
+  uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_leaves) return;
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  const u64* p = cols + pos;
+  if (leaf_len <= 4) {  // hash_or_noop: short leaves are copied, not hashed
+#pragma unroll
+    for (int i = 0; i < 4; i++) if ((uint32_t)i < leaf_len) s[i] = p[(size_t)i * n_leaves];
+  } else {
+    uint32_t full = leaf_len / 8, rem = leaf_len % 8;
+    u64 nx[8];
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) nx[i] = p[(size_t)i * n_leaves];
+    }
+    for (uint32_t c = 0; c < full; c++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = nx[i];
+      if (c + 1 < full) {  // prefetch the next 8 columns under the permutation
+        const u64* q = p + (size_t)(c + 1) * 8 * n_leaves;
+#pragma unroll
+        for (int i = 0; i < 8; i++) nx[i] = q[(size_t)i * n_leaves];
+      }
+      poseidon_permute(s);
+    }
+    if (rem) {
+      const u64* q = p + (size_t)full * 8 * n_leaves;
+#pragma unroll
+      for (int i = 0; i < 8; i++) if ((uint32_t)i < rem) s[i] = q[(size_t)i * n_leaves];
+      poseidon_permute(s);
+    }
+  }
+  u64* d = digests + 4ull * leaf_index_of(pos, log_block);
+  d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+
+void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, uint32_t n_leaves, unsigned log_block,
+                           u64* d_digests) {
+  unsigned block = n_leaves >= 128 * (unsigned)ctx->sm_count ? 128 : (n_leaves >= 64 * (unsigned)ctx->sm_count ? 64 : 32);
+  LAUNCH(ctx, leaf_hash_kernel, (n_leaves + block - 1) / block, block, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+}
+
+// one level: out[i] = two_to_one(in[2i], in[2i+1])
+__global__ void merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, uint32_t n_out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const ulonglong2* src = (const ulonglong2*)(in + 8ull * i);
+  ulonglong2 a = src[0], b = src[1], c = src[2], d = src[3];
+  u64 l[4] = {a.x, a.y, b.x, b.y}, r[4] = {c.x, c.y, d.x, d.y}, o[4];
+  poseidon_two_to_one(l, r, o);
+  ulonglong2* dst = (ulonglong2*)(out + 4ull * i);
+  dst[0] = make_ulonglong2(o[0], o[1]);
+  dst[1] = make_ulonglong2(o[2], o[3]);
+}
+
+void sb_merkle_levels(sb_ctx* ctx, u64* d_tree, uint32_t n_leaves, unsigned cap_height) {
+  uint32_t cap = 1u << cap_height;
+  u64* in = d_tree;
+  for (uint32_t cnt = n_leaves; cnt > cap; cnt >>= 1) {
+    u64* out = in + 4ull * cnt;
+    uint32_t n_out = cnt >> 1;
+    unsigned block = n_out >= 4096 ? 64 : 32;
+    LAUNCH(ctx, merkle_level_kernel, (n_out + block - 1) / block, block, 0, in, out, n_out);
+    in = out;
+  }
+}
+
+__global__ void permute_kernel(u64* states, uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 s[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) s[k] = states[12ull * i + k];
+  poseidon_permute(s);
+#pragma unroll
+  for (int k = 0; k < 12; k++) states[12ull * i + k] = s[k];
+}
+void sb_poseidon_permute_device(sb_ctx* ctx, u64* d_states, uint32_t count) {
+  LAUNCH(ctx, permute_kernel, (count + 63) / 64, 64, 0, d_states, count);
+}

@@ -1,0 +1,298 @@
+// K1 / K5: column-batched Goldilocks NTTs for sm_100a.
+// Replaces PolynomialValues::ifft, PolynomialCoeffs::lde + coset_fft(7) and the transpose +
+// reverse_index_bits of PolynomialBatch::from_values / from_coeffs (plonky2; reached from
+// starky::prover::prove, reference call sites /root/reference/src/aggregate_proof.rs:59,105,138,169,212).
+//
+// Data layout (DESIGN.md "HBM layout"):
+//   values [C][n]  column-major, natural order           (what Vec<PolynomialValues<F>> holds)
+//   coeffs [C][n]  position p holds coefficient c_{bitrev(p)}  ("bit-reversed coefficient order")
+//   lde    [C][N]  position J*n + k holds P(7 * w_N^(j + 2^r k)), j = bitrev_r(J)   ("coset-major order")
+// With that choice a column needs NO permutation pass: a decimation-in-frequency inverse transform takes natural
+// values to bit-reversed coefficients, and per coset a decimation-in-time forward transform takes bit-reversed
+// (scaled) coefficients to natural-order coset values.  plonky2's leaf index of position (J,k) is J*n + bitrev_n(k);
+// only the 32-byte digests are scattered to it (merkle.cu), the 8*C*N bytes of LDE never are.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// twiddles and coset scale tables (computed once per size, cached in the ctx)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void twiddle_kernel(u64* fwd, u64* inv, u64 w, u64 w_inv, uint32_t half) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= half) return;
+  fwd[k] = gl_pow(w, k);
+  inv[k] = gl_pow(w_inv, k);
+}
+
+const Twiddles& sb_twiddles(sb_ctx* ctx, unsigned log_size) {
+  auto it = ctx->tw.find(log_size);
+  if (it != ctx->tw.end()) return it->second;
+  Twiddles& t = ctx->tw[log_size];
+  t.log_size = log_size;
+  uint32_t half = log_size ? (1u << (log_size - 1)) : 1;
+  t.fwd.ensure(8ull * half);
+  t.inv.ensure(8ull * half);
+  u64 w = gl_root(log_size), wi = gl_inv(w);
+  LAUNCH(ctx, twiddle_kernel, (half + 255) / 256, 256, 0, t.fwd.as<u64>(), t.inv.as<u64>(), w, wi, half);
+  return t;
+}
+
+// scale[J][p] = n^-1 * (7 * w_N^j)^{bitrev_n(p)},  j = bitrev_r(J)
+__global__ void coset_scale_kernel(u64* scale, unsigned log_n, unsigned rate_bits, u64 w_N, u64 n_inv) {
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t n = 1u << log_n;
+  if (idx >= (n << rate_bits)) return;
+  uint32_t J = idx >> log_n, p = idx & (n - 1);
+  uint32_t j = bitrev32(J, rate_bits), k = bitrev32(p, log_n);
+  u64 base = gl_mul(7, gl_pow(w_N, j));
+  scale[idx] = gl_mul(n_inv, gl_pow(base, k));
+}
+
+static const u64* coset_scale(sb_ctx* ctx, unsigned log_n, unsigned rate_bits) {
+  uint64_t key = ((uint64_t)log_n << 8) | rate_bits;
+  auto it = ctx->coset_scale.find(key);
+  if (it != ctx->coset_scale.end()) return it->second.as<u64>();
+  DevBuf& b = ctx->coset_scale[key];
+  uint32_t total = 1u << (log_n + rate_bits);
+  b.ensure(8ull * total);
+  LAUNCH(ctx, coset_scale_kernel, (total + 255) / 256, 256, 0, b.as<u64>(), log_n, rate_bits,
+         gl_root(log_n + rate_bits), gl_inv(1ull << log_n));
+  return b.as<u64>();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// shared-memory butterflies.  `buf` holds `cpb` vectors of n = 2^log_n elements; tw is the table of the
+// enclosing transform of size 2^log_tw (tw[k] = w^k), so stage `half` uses tw[j << (log_tw - 1 - log2(half))].
+// ---------------------------------------------------------------------------------------------------------
+template <int EPT>
+__device__ __forceinline__ void dif_stages(u64* buf, unsigned log_n, unsigned log_tw, const u64* __restrict__ tw,
+                                           unsigned T) {
+  // decimation in frequency: natural order in -> bit-reversed order out
+  const unsigned half_n = 1u << (log_n - 1);
+  for (int s = (int)log_n - 1; s >= 0; s--) {
+    const unsigned half = 1u << s;
+#pragma unroll
+    for (int m = 0; m < EPT / 2; m++) {
+      unsigned w = threadIdx.x + m * T;
+      unsigned col = w >> (log_n - 1), b = w & (half_n - 1);
+      unsigned j = b & (half - 1);
+      unsigned i0 = ((b >> s) << (s + 1)) + j + (col << log_n);
+      u64 u = buf[i0], v = buf[i0 + half];
+      buf[i0] = gl_add(u, v);
+      buf[i0 + half] = gl_mul(gl_sub(u, v), __ldg(tw + ((size_t)j << (log_tw - 1 - s))));
+    }
+    __syncthreads();
+  }
+}
+template <int EPT>
+__device__ __forceinline__ void dit_stages(u64* buf, unsigned log_n, unsigned log_tw, const u64* __restrict__ tw,
+                                           unsigned T) {
+  // decimation in time: bit-reversed order in -> natural order out
+  const unsigned half_n = 1u << (log_n - 1);
+  for (unsigned s = 0; s < log_n; s++) {
+    const unsigned half = 1u << s;
+#pragma unroll
+    for (int m = 0; m < EPT / 2; m++) {
+      unsigned w = threadIdx.x + m * T;
+      unsigned col = w >> (log_n - 1), b = w & (half_n - 1);
+      unsigned j = b & (half - 1);
+      unsigned i0 = ((b >> s) << (s + 1)) + j + (col << log_n);
+      u64 u = buf[i0], t = gl_mul(buf[i0 + half], __ldg(tw + ((size_t)j << (log_tw - 1 - s))));
+      buf[i0] = gl_add(u, t);
+      buf[i0 + half] = gl_sub(u, t);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: fused iNTT -> (n^-1, coset shift) scaling -> 2^r coset NTTs, one pass over the trace.
+// Algorithmic HBM bytes per column: 8n read + 8n (coefficients, kept for openings/FRI) + 8N written.
+// ---------------------------------------------------------------------------------------------------------
+template <int EPT>
+__global__ void lde_kernel(const u64* __restrict__ values, u64* __restrict__ coeffs, u64* __restrict__ lde,
+                           uint32_t n_cols, unsigned log_n, unsigned rate_bits, unsigned cpb,
+                           const u64* __restrict__ tw_fwd, const u64* __restrict__ tw_inv,
+                           const u64* __restrict__ scale, u64 n_inv) {
+  extern __shared__ u64 buf[];
+  const unsigned T = blockDim.x;
+  const uint32_t n = 1u << log_n;
+  const size_t N = (size_t)n << rate_bits;
+  const uint32_t col0 = blockIdx.x * cpb;
+  u64 c[EPT];
+#pragma unroll
+  for (int m = 0; m < EPT; m++) {
+    unsigned e = threadIdx.x + m * T;
+    uint32_t col = col0 + (e >> log_n);
+    buf[e] = col < n_cols ? values[(size_t)col * n + (e & (n - 1))] : 0;
+  }
+  __syncthreads();
+  dif_stages<EPT>(buf, log_n, log_n, tw_inv, T);
+  // buf[p] = n * c_{bitrev(p)}; the 1/n is folded into the coset scale table
+#pragma unroll
+  for (int m = 0; m < EPT; m++) c[m] = buf[threadIdx.x + m * T];
+  for (unsigned J = 0; J < (1u << rate_bits); J++) {
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < EPT; m++) {
+      unsigned e = threadIdx.x + m * T;
+      buf[e] = gl_mul(c[m], __ldg(scale + ((size_t)J << log_n) + (e & (n - 1))));
+    }
+    __syncthreads();
+    dit_stages<EPT>(buf, log_n, log_n, tw_fwd, T);
+#pragma unroll
+    for (int m = 0; m < EPT; m++) {
+      unsigned e = threadIdx.x + m * T;
+      uint32_t col = col0 + (e >> log_n);
+      if (col < n_cols) lde[(size_t)col * N + ((size_t)J << log_n) + (e & (n - 1))] = buf[e];
+    }
+  }
+  if (coeffs) {
+    const u64 ninv = n_inv;
+#pragma unroll
+    for (int m = 0; m < EPT; m++) {
+      unsigned e = threadIdx.x + m * T;
+      uint32_t col = col0 + (e >> log_n);
+      if (col < n_cols) coeffs[(size_t)col * n + (e & (n - 1))] = gl_mul(c[m], ninv);
+    }
+  }
+}
+
+void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, uint32_t n_cols, unsigned log_n,
+                  unsigned rate_bits) {
+  if (log_n < 1 || log_n > 13) SB_THROW(SB_EINVAL, "trace height 2^%u unsupported (1 <= log_n <= 13)", log_n);
+  const Twiddles& tw = sb_twiddles(ctx, log_n);
+  const u64* scale = coset_scale(ctx, log_n, rate_bits);
+  const uint32_t n = 1u << log_n;
+  // block shape: EPT elements per thread, cpb columns per block so that a block has >= 128 threads
+  int ept = n >= 8192 ? 8 : 4;
+  unsigned cpb = 1;
+  while (cpb * n / ept < 128) cpb *= 2;
+  unsigned T = cpb * n / ept;
+  size_t smem = 8ull * cpb * n;
+  uint32_t grid = (n_cols + cpb - 1) / cpb;
+  if (ept == 8) {
+    CUDA_CHECK(cudaFuncSetAttribute(lde_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, lde_kernel<8>, grid, T, smem, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits, cpb,
+           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n));
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(lde_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, lde_kernel<4>, grid, T, smem, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits, cpb,
+           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Generic batched transform of `count` vectors of size 2^log_size (quotient polys, FRI polynomials, tests).
+//   dif = true : natural in  -> bit-reversed out      dif = false: bit-reversed in -> natural out
+//   inverse    : use w^-1 and scale by size^-1
+// Stages with half >= 2^LOG_BLOCK run as one global pass each; the rest run in shared memory per 2^LOG_BLOCK block.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void ntt_global_stage_kernel(u64* data, unsigned log_size, unsigned s, const u64* __restrict__ tw,
+                                        bool dif, uint64_t total_butterflies) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= total_butterflies) return;
+  const uint64_t half_size = 1ull << (log_size - 1);
+  uint64_t vec = w >> (log_size - 1), b = w & (half_size - 1);
+  uint64_t half = 1ull << s, j = b & (half - 1);
+  u64* d = data + (vec << log_size);
+  uint64_t i0 = ((b >> s) << (s + 1)) + j;
+  u64 t = __ldg(tw + (j << (log_size - 1 - s)));
+  u64 u = d[i0], v = d[i0 + half];
+  if (dif) {
+    d[i0] = gl_add(u, v);
+    d[i0 + half] = gl_mul(gl_sub(u, v), t);
+  } else {
+    v = gl_mul(v, t);
+    d[i0] = gl_add(u, v);
+    d[i0 + half] = gl_sub(u, v);
+  }
+}
+
+template <int EPT>
+__global__ void ntt_block_kernel(u64* data, unsigned log_size, unsigned log_block, const u64* __restrict__ tw,
+                                 bool dif, u64 post_scale) {
+  extern __shared__ u64 buf[];
+  const unsigned T = blockDim.x;
+  u64* d = data + ((size_t)blockIdx.x << log_block);
+#pragma unroll
+  for (int m = 0; m < EPT; m++) buf[threadIdx.x + m * T] = d[threadIdx.x + m * T];
+  __syncthreads();
+  if (dif) dif_stages<EPT>(buf, log_block, log_size, tw, T);
+  else dit_stages<EPT>(buf, log_block, log_size, tw, T);
+#pragma unroll
+  for (int m = 0; m < EPT; m++) {
+    u64 v = buf[threadIdx.x + m * T];
+    d[threadIdx.x + m * T] = post_scale == 1 ? v : gl_mul(v, post_scale);
+  }
+}
+
+__global__ void scale_kernel(u64* d, uint64_t n, u64 s) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = gl_mul(d[i], s);
+}
+void sb_scale_device(sb_ctx* ctx, u64* d, uint64_t n, u64 s) {
+  LAUNCH(ctx, scale_kernel, (unsigned)((n + 255) / 256), 256, 0, d, n, s);
+}
+
+void sb_ntt_device(sb_ctx* ctx, u64* d_data, unsigned log_size, uint32_t count, bool inverse, bool dif) {
+  if (log_size == 0 || count == 0) return;
+  const Twiddles& tw = sb_twiddles(ctx, log_size);
+  const u64* t = inverse ? tw.inv.as<u64>() : tw.fwd.as<u64>();
+  unsigned log_block = log_size < 12 ? log_size : 12;
+  u64 post = inverse ? gl_inv(1ull << log_size) : 1;
+  uint64_t total_bf = (uint64_t)count << (log_size - 1);
+  auto global_stages = [&](bool descending) {
+    if (descending) for (int s = (int)log_size - 1; s >= (int)log_block; s--)
+      LAUNCH(ctx, ntt_global_stage_kernel, (unsigned)((total_bf + 255) / 256), 256, 0, d_data, log_size, (unsigned)s, t, true, total_bf);
+    else for (unsigned s = log_block; s < log_size; s++)
+      LAUNCH(ctx, ntt_global_stage_kernel, (unsigned)((total_bf + 255) / 256), 256, 0, d_data, log_size, s, t, false, total_bf);
+  };
+  auto block_pass = [&](u64 scale) {
+    uint32_t blocks = count << (log_size - log_block);
+    uint32_t nb = 1u << log_block;
+    size_t smem = 8ull * nb;
+    if (nb >= 1024) {
+      unsigned T = nb / 4;
+      LAUNCH(ctx, ntt_block_kernel<4>, blocks, T, smem, d_data, log_size, log_block, t, dif, scale);
+    } else if (nb >= 64) {
+      unsigned T = nb / 2;
+      LAUNCH(ctx, ntt_block_kernel<2>, blocks, T, smem, d_data, log_size, log_block, t, dif, scale);
+    } else {
+      // tiny transforms: one thread per butterfly, at least one
+      unsigned T = nb / 2;
+      LAUNCH(ctx, ntt_block_kernel<2>, blocks, T, smem, d_data, log_size, log_block, t, dif, scale);
+    }
+  };
+  if (dif) { global_stages(true); block_pass(post); }
+  else {
+    if (log_block == log_size) block_pass(post);
+    else {
+      block_pass(1); global_stages(false);
+      if (post != 1) sb_scale_device(ctx, d_data, (uint64_t)count << log_size, post);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// row-major [n][C] (u64 or u32) -> column-major [C][n] u64: the device replacement of
+// starky::util::trace_rows_to_poly_values (aggregate_proof.rs:57,104,137,168,211).  32x32 smem tiles.
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void transpose_kernel(const T* __restrict__ rows, u64* __restrict__ cols, uint32_t n_rows, uint32_t n_cols) {
+  __shared__ u64 tile[32][33];
+  uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    uint32_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < n_rows && c < n_cols) ? (u64)rows[(size_t)r * n_cols + c] : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    uint32_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < n_rows && c < n_cols) cols[(size_t)c * n_rows + r] = tile[threadIdx.x][i];
+  }
+}
+void sb_transpose_rows_to_cols(sb_ctx* ctx, const void* d_rows, u64* d_cols, uint32_t n_rows, uint32_t n_cols, bool is_u32) {
+  dim3 grid((n_cols + 31) / 32, (n_rows + 31) / 32), block(32, 8);
+  if (is_u32) { LAUNCH(ctx, transpose_kernel<uint32_t>, grid, block, 0, (const uint32_t*)d_rows, d_cols, n_rows, n_cols); }
+  else { LAUNCH(ctx, transpose_kernel<u64>, grid, block, 0, (const u64*)d_rows, d_cols, n_rows, n_cols); }
+}

@@ -1,0 +1,22 @@
+// Internal declarations shared by capi.cu / prover.cu / quotient.cu / fri.cu.
+#pragma once
+#include "common.cuh"
+
+// proof layout (include/starky_b200.h sb_proof_layout)
+sb_proof_layout proof_layout(const sb_params& p);
+uint32_t fri_step_path_len(const sb_proof_layout& l, uint32_t round);
+uint64_t fri_step_offset(const sb_proof_layout& l, uint32_t round);
+std::vector<unsigned> fri_arities(const sb_params& p);
+static inline unsigned quotient_degree_factor(const sb_params& p) { return p.constraint_degree > 1 ? p.constraint_degree - 1 : 1; }
+
+// capi.cu
+int sb_fail(sb_ctx* ctx, const SbError& e);
+const u64* ingest_trace(sb_ctx* ctx, const sb_params* p, const void* trace, int layout);
+void commit_trace(sb_ctx* ctx, const sb_params* p, const u64* d_values);
+const u64* tree_cap_ptr(const u64* d_tree, size_t n_leaves, unsigned cap_height);
+
+// quotient.cu
+void air_release_all(sb_ctx* ctx);
+
+// fri.cu
+void sb_bitrev_permute_device(sb_ctx* ctx, const u64* d_in, u64* d_out, unsigned log_size, uint32_t count);

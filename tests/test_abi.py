@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol include/starky_b200.h declares,
+and the pure-host helpers (standard params, proof layout) agree with the oracle's restatement."""
+import ctypes as C
+import os
+import re
+
+import oracle_lib as O
+import starky_bls12_381_b200 as sb
+from helpers import to_oracle_params
+
+ROOT = O.ROOT
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "starky_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = sb.lib()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(L, name), "libstarkyb200.so does not export %s" % name
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    import starky_bls12_381_b200.binding as B
+    monkeypatch.setattr(B, "_LIB", None)
+    monkeypatch.setattr(B, "lib_path", lambda: "/nonexistent/libstarkyb200.so")
+    try:
+        B.lib()
+        assert False, "expected ImportError"
+    except ImportError as e:
+        assert "no CPU fallback" in str(e)
+
+
+def test_standard_params_match_reference_configs():
+    # columns / public inputs / degree / rate bits per stark
+    want = {0: (60285, 432, 3, 1), 1: (29376, 4968, 4, 2), 2: (97330, 5064, 3, 1), 3: (73527, 288, 5, 2),
+            4: (3339, 12824, 4, 2)}
+    for sid, (c, pi, deg, r) in want.items():
+        p = sb.standard_params(sid, 10)
+        assert (p.n_cols, p.n_public_inputs, p.constraint_degree, p.rate_bits) == (c, pi, deg, r)
+        assert (p.cap_height, p.num_challenges, p.pow_bits, p.num_query_rounds) == (4, 2, 16, 84)
+    for info in sb.STARKS.values():
+        p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1)
+        assert (p.n_cols, p.n_public_inputs, p.constraint_degree, p.rate_bits) == (
+            info.columns, info.public_inputs, info.constraint_degree, info.rate_bits)
+
+
+def test_proof_layout_matches_oracle_and_survey():
+    # FRI arity bits / final poly length per stark: FP12 [] / 16, PP [4,4] / 4, ML [4] / 64,
+    # FE [4,4] / 32, ECC [4,4] / 32
+    want = {"fp12_mul": (0, 16), "pairing_precomp": (2, 4), "miller_loop": (1, 64), "final_exp": (2, 32),
+            "ecc_agg": (2, 32)}
+    for name, info in sb.STARKS.items():
+        p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1)
+        l = sb.ProofLayout()
+        assert sb.lib().sb_proof_layout_for(C.byref(p), C.byref(l)) == 0
+        assert (l.n_fri_rounds, l.final_poly_len) == want[name]
+        ol = O.layout(to_oracle_params(p))
+        assert bytes(l) == bytes(ol)
+        for r in range(l.n_fri_rounds):
+            assert sb.lib().sb_fri_step_path_len(C.byref(l), r) == l.log_lde - 4 * (r + 1) - 4
