@@ -109,7 +109,7 @@ __device__ __forceinline__ void dit_stages(u64* buf, unsigned log_n, unsigned lo
 // Algorithmic HBM bytes per column: 8n read + 8n (coefficients, kept for openings/FRI) + 8N written.
 // ---------------------------------------------------------------------------------------------------------
 template <int EPT>
-__global__ void lde_kernel(const u64* __restrict__ values, u64* __restrict__ coeffs, u64* __restrict__ lde,
+__global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* __restrict__ values, u64* __restrict__ coeffs, u64* __restrict__ lde,
                            uint32_t n_cols, unsigned log_n, unsigned rate_bits, unsigned cpb,
                            const u64* __restrict__ tw_fwd, const u64* __restrict__ tw_inv,
                            const u64* __restrict__ scale, u64 n_inv) {
@@ -164,7 +164,7 @@ void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, u
   const u64* scale = coset_scale(ctx, log_n, rate_bits);
   const uint32_t n = 1u << log_n;
   // block shape: EPT elements per thread, cpb columns per block so that a block has >= 128 threads
-  int ept = n >= 8192 ? 8 : 4;
+  int ept = n >= 4096 ? 8 : 4;
   unsigned cpb = 1;
   while (cpb * n / ept < 128) cpb *= 2;
   unsigned T = cpb * n / ept;
@@ -209,7 +209,7 @@ __global__ void ntt_global_stage_kernel(u64* data, unsigned log_size, unsigned s
 }
 
 template <int EPT>
-__global__ void ntt_block_kernel(u64* data, unsigned log_size, unsigned log_block, const u64* __restrict__ tw,
+__global__ void __launch_bounds__(1024) ntt_block_kernel(u64* data, unsigned log_size, unsigned log_block, const u64* __restrict__ tw,
                                  bool dif, u64 post_scale) {
   extern __shared__ u64 buf[];
   const unsigned T = blockDim.x;
