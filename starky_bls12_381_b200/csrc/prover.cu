@@ -1,7 +1,37 @@
 // Host orchestration of one proof: the device replacement of starky::prover::prove
-// (/root/reference/src/aggregate_proof.rs:59,105,138,169,212).
+// (/root/reference/src/aggregate_proof.rs:59,105,138,169,212).  The Fiat-Shamir transcript
+// (plonky2 Challenger, ~10^2 permutations) runs on the host between kernels; only caps, openings, the two combined
+// polynomials and the final proof cross PCIe.
+#include <string.h>
+
+#include <algorithm>
+
+#include "poseidon.cuh"
 #include "prover.cuh"
 
+// ---- stage functions from the other translation units ----
+struct AirProgram;
+AirProgram* air_get(sb_ctx* ctx, const sb_params* p);
+void sb_quotient_device(sb_ctx* ctx, const sb_params* p, const u64* d_pis, const u64* alphas, u64* d_out);
+void sb_openings_device(sb_ctx* ctx, const u64* d_coeffs, unsigned log_n, uint32_t n_polys, e2_t za, const e2_t* zb,
+                        e2_t* d_tab_a, e2_t* d_tab_b, e2_t* d_out_a, e2_t* d_out_b);
+void sb_combine_device(sb_ctx* ctx, const u64* d_coeffs, unsigned log_n, uint32_t n_polys, e2_t alpha, uint32_t j0,
+                       e2_t* d_apow, e2_t* d_partial, size_t partial_capacity_elems, e2_t* d_out);
+void sb_fri_leaf_hash_device(sb_ctx* ctx, const u64* d_re, const u64* d_im, uint32_t n_leaves, unsigned arity_bits, u64* d_digests);
+u64 sb_pow_device(sb_ctx* ctx, const u64 state[12], int pos, unsigned bits, unsigned long long* d_best);
+void sb_gather_leaf_device(sb_ctx* ctx, u64* dst, uint64_t stride, uint64_t off, const u64* cols, uint32_t N, uint32_t n_cols,
+                           const uint32_t* d_positions, uint32_t n_queries);
+void sb_gather_path_device(sb_ctx* ctx, u64* dst, uint64_t stride, uint64_t off, const u64* tree, uint32_t n_leaves,
+                           uint32_t path_len, const uint32_t* d_leaf_idx, unsigned shift, uint32_t n_queries);
+void sb_gather_fri_evals_device(sb_ctx* ctx, u64* dst, uint64_t stride, uint64_t off, const u64* re, const u64* im,
+                                unsigned arity_bits, const uint32_t* d_leaf_idx, unsigned shift, uint32_t n_queries);
+void sb_coset_to_bitrev_device(sb_ctx* ctx, const u64* d_in, u64* d_out, unsigned log_n, unsigned log_N, uint32_t count);
+void sb_coset_shift_device(sb_ctx* ctx, u64* d, unsigned log_size, uint32_t count, u64 s);
+void sb_tail_nonzero_device(sb_ctx* ctx, const u64* d, unsigned log_size, uint32_t count, uint32_t keep, int* d_flag);
+
+// ---------------------------------------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------------------------------------
 std::vector<unsigned> fri_arities(const sb_params& p) {
   // FriReductionStrategy::ConstantArityBits(arity_bits, final_poly_bits)
   std::vector<unsigned> r;
@@ -12,7 +42,6 @@ std::vector<unsigned> fri_arities(const sb_params& p) {
   }
   return r;
 }
-
 uint32_t fri_step_path_len(const sb_proof_layout& l, uint32_t round) {
   unsigned log_leaves = l.log_lde - l.arity_bits * (round + 1);
   return log_leaves - ilog2(l.cap_len);
@@ -22,7 +51,6 @@ uint64_t fri_step_offset(const sb_proof_layout& l, uint32_t round) {
   for (uint32_t r = 0; r < round; r++) o += (uint64_t(2) << l.arity_bits) + 4ull * fri_step_path_len(l, r);
   return o;
 }
-
 sb_proof_layout proof_layout(const sb_params& p) {
   if (p.fri_arity_bits == 0) SB_THROW(SB_EINVAL, "fri_arity_bits is 0");
   sb_proof_layout l = {};
@@ -57,24 +85,307 @@ sb_proof_layout proof_layout(const sb_params& p) {
   return l;
 }
 
-// ---- temporary stubs (filled in by quotient.cu / fri.cu as those stages land) ----
-void air_release_all(sb_ctx*) {}
+// ---------------------------------------------------------------------------------------------------------
+// plonky2 Challenger (duplex sponge over Poseidon-12), host side
+// ---------------------------------------------------------------------------------------------------------
+struct HostChallenger {
+  u64 state[12];
+  u64 in_buf[8]; int n_in = 0;
+  u64 out_buf[8]; int n_out = 0;
+  HostChallenger() { memset(state, 0, sizeof(state)); }
+  void duplexing() {
+    for (int i = 0; i < n_in; i++) state[i] = in_buf[i];
+    n_in = 0;
+    poseidon_permute(state);
+    memcpy(out_buf, state, 64);
+    n_out = 8;
+  }
+  void observe(u64 x) { n_out = 0; in_buf[n_in++] = x; if (n_in == 8) duplexing(); }
+  void observe_many(const u64* x, size_t n) { for (size_t i = 0; i < n; i++) observe(x[i]); }
+  u64 challenge() { if (n_in > 0 || n_out == 0) duplexing(); return out_buf[--n_out]; }
+  e2_t ext_challenge() { u64 a = challenge(); u64 b = challenge(); return e2_make(a, b); }
+};
 
-__global__ void bitrev_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, unsigned log_size, uint64_t total) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  uint64_t vec = i >> log_size;
-  uint32_t k = (uint32_t)(i & ((1ull << log_size) - 1));
-  out[(vec << log_size) + bitrev32(k, log_size)] = in[i];
-}
-void sb_bitrev_permute_device(sb_ctx* ctx, const u64* d_in, u64* d_out, unsigned log_size, uint32_t count) {
-  uint64_t total = (uint64_t)count << log_size;
-  LAUNCH(ctx, bitrev_permute_kernel, (unsigned)((total + 255) / 256), 256, 0, d_in, d_out, log_size, total);
+struct Arena {
+  char* base; size_t off = 0, cap;
+  Arena(void* b, size_t c) : base((char*)b), cap(c) {}
+  template <class T> T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* r = (T*)(base + off);
+    off += sizeof(T) * count;
+    if (off > cap) SB_THROW(SB_ENOMEM, "internal: work arena overflow");
+    return r;
+  }
+};
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, const uint64_t* public_inputs,
+                       sb_proof* proof) {
+  const unsigned log_n = p->log_n, r = p->rate_bits, log_N = log_n + r, qdf = quotient_degree_factor(*p);
+  const uint32_t n = 1u << log_n, N = 1u << log_N, C = p->n_cols;
+  const sb_proof_layout L = proof_layout(*p);
+  const uint32_t nq = L.n_quotient_polys;
+  if (p->n_public_inputs && !public_inputs) SB_THROW(SB_EINVAL, "public_inputs is NULL");
+  if (p->num_challenges != 2) SB_THROW(SB_EINVAL, "num_challenges must be 2");
+  air_get(ctx, p);  // validates the shape against the constraint program before any work
+  u64* W = proof->words;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t ev[8];
+  for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 8; i++) cudaEventDestroy(e[i]); } } guard{ev};
+
+  // ---- 0. ingest, 1. trace commitment ----
+  CUDA_CHECK(cudaEventRecord(ev[0], st));
+  const u64* d_values = ingest_trace(ctx, p, trace, layout);
+  CUDA_CHECK(cudaEventRecord(ev[1], st));
+  commit_trace(ctx, p, d_values);
+  CUDA_CHECK(cudaMemcpyAsync(W + L.off_trace_cap, tree_cap_ptr(ctx->tree.as<u64>(), N, p->cap_height), 32ull * L.cap_len,
+                             cudaMemcpyDeviceToHost, st));
+  ctx->pis.ensure(8ull * (p->n_public_inputs + 1));
+  if (p->n_public_inputs)
+    CUDA_CHECK(cudaMemcpyAsync(ctx->pis.p, public_inputs, 8ull * p->n_public_inputs, cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaEventRecord(ev[2], st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+
+  HostChallenger ch;
+  if (p->flags & SB_FLAG_OBSERVE_PUBLIC_INPUTS) ch.observe_many(public_inputs, p->n_public_inputs);
+  ch.observe_many(W + L.off_trace_cap, 4ull * L.cap_len);
+  u64 alphas[2] = {ch.challenge(), ch.challenge()};
+
+  // ---- work arena ----
+  const size_t partial_elems = (size_t)(ctx->sm_count * 16 + 8) * 128 + 2 * (size_t)n;
+  size_t need = 16ull * N * 2 + 8ull * nq * n * 2 + 16ull * n * 2 + 16ull * (2ull * C + nq + 8) + 16ull * (C + nq + 8) +
+                16ull * partial_elems + 16ull * n * 2 + 8ull * L.query_stride * L.n_queries + 16ull * N * 2 + 64ull * N +
+                (1 << 16);
+  ctx->scratch2.ensure(need);
+  Arena ar(ctx->scratch2.p, ctx->scratch2.cap);
+
+  // ---- 3. quotient values, K5: quotient polynomials and their commitment ----
+  ctx->qvals.ensure(16ull * N);
+  u64* d_q = ctx->qvals.as<u64>();
+  stage_begin(ctx, "quotient");
+  sb_quotient_device(ctx, p, ctx->pis.as<u64>(), alphas, d_q);
+  stage_end(ctx, "quotient");
+  CUDA_CHECK(cudaEventRecord(ev[3], st));
+  u64* d_qtmp = ar.take<u64>(2ull * N);
+  int* d_flag = ar.take<int>(4);
+  sb_coset_to_bitrev_device(ctx, d_q, d_qtmp, log_n, log_N, 2);          // values in bit-reversed natural order
+  sb_ntt_device(ctx, d_qtmp, log_N, 2, /*inverse=*/true, /*dif=*/false);  // -> natural-order coefficients of q(7X)
+  sb_coset_shift_device(ctx, d_qtmp, log_N, 2, gl_inv(7));                // coset_ifft(7)
+  CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  sb_tail_nonzero_device(ctx, d_qtmp, log_N, 2, qdf * n, d_flag);
+  int h_flag = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  // chunk polys [nq][n], natural coefficient order -> values on H -> the same LDE + Merkle path as the trace
+  u64* d_qc_nat = ar.take<u64>((size_t)nq * n);
+  u64* d_qc_br = ar.take<u64>((size_t)nq * n);
+  for (unsigned j = 0; j < 2; j++)
+    CUDA_CHECK(cudaMemcpyAsync(d_qc_nat + (size_t)j * qdf * n, d_qtmp + (size_t)j * N, 8ull * qdf * n, cudaMemcpyDeviceToDevice, st));
+  sb_bitrev_permute_device(ctx, d_qc_nat, d_qc_br, log_n, nq);
+  sb_ntt_device(ctx, d_qc_br, log_n, nq, false, /*dif=*/false);          // bit-reversed coefficients -> natural values
+  ctx->qcoeffs.ensure(8ull * nq * n);
+  ctx->qlde.ensure(8ull * nq * N);
+  ctx->qtree.ensure(64ull * N);
+  sb_lde_trace(ctx, d_qc_br, ctx->qcoeffs.as<u64>(), ctx->qlde.as<u64>(), nq, log_n, r);
+  sb_hash_leaves_device(ctx, ctx->qlde.as<u64>(), nq, N, log_n, ctx->qtree.as<u64>());
+  sb_merkle_levels(ctx, ctx->qtree.as<u64>(), N, p->cap_height);
+  CUDA_CHECK(cudaMemcpyAsync(W + L.off_quotient_cap, tree_cap_ptr(ctx->qtree.as<u64>(), N, p->cap_height), 32ull * L.cap_len,
+                             cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaEventRecord(ev[4], st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_flag && !(p->flags & SB_FLAG_ALLOW_INVALID_TRACE))
+    SB_THROW(SB_EQUOTIENT_NOT_DIVISIBLE, "Quotient has failed, the vanishing polynomial is not divisible by Z_H");
+  ch.observe_many(W + L.off_quotient_cap, 4ull * L.cap_len);
+
+  // ---- 4. zeta, 5. openings ----
+  const e2_t zeta = ch.ext_challenge();
+  {
+    e2_t t = zeta;
+    for (unsigned i = 0; i < log_n; i++) t = e2_mul(t, t);
+    if (e2_eq(t, e2_make(1, 0))) SB_THROW(SB_EZETA_IN_SUBGROUP, "Opening point is in the subgroup.");
+  }
+  const u64 g = gl_root(log_n);
+  const e2_t zeta_next = e2_scale(zeta, g);
+  e2_t* d_tab_a = ar.take<e2_t>(n);
+  e2_t* d_tab_b = ar.take<e2_t>(n);
+  e2_t* d_open = ar.take<e2_t>(2ull * C + nq);
+  sb_openings_device(ctx, ctx->coeffs.as<u64>(), log_n, C, zeta, &zeta_next, d_tab_a, d_tab_b, d_open, d_open + C);
+  sb_openings_device(ctx, ctx->qcoeffs.as<u64>(), log_n, nq, zeta, nullptr, d_tab_a, d_tab_b, d_open + 2ull * C, nullptr);
+  CUDA_CHECK(cudaMemcpyAsync(W + L.off_local_values, d_open, 16ull * C, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(W + L.off_next_values, d_open + C, 16ull * C, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(W + L.off_quotient_polys, d_open + 2ull * C, 16ull * nq, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaEventRecord(ev[5], st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  ch.observe_many(W + L.off_local_values, 2ull * C);        // batch 0 = local_values ++ quotient_polys
+  ch.observe_many(W + L.off_quotient_polys, 2ull * nq);
+  ch.observe_many(W + L.off_next_values, 2ull * C);         // batch 1 = next_values
+
+  // ---- 6. prove_openings: batch combine on the device, the two synthetic divisions on the host ----
+  const e2_t alpha = ch.ext_challenge();
+  e2_t* d_apow = ar.take<e2_t>((size_t)C + nq);
+  e2_t* d_partial = ar.take<e2_t>(partial_elems);
+  e2_t* d_F = ar.take<e2_t>(2ull * n);
+  sb_combine_device(ctx, ctx->coeffs.as<u64>(), log_n, C, alpha, 0, d_apow, d_partial, partial_elems, d_F);
+  sb_combine_device(ctx, ctx->qcoeffs.as<u64>(), log_n, nq, alpha, C, d_apow, d_partial, partial_elems, d_F + n);
+  std::vector<e2_t> hF(2ull * n);
+  CUDA_CHECK(cudaMemcpyAsync(hF.data(), d_F, 32ull * n, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<e2_t> coeffs(n);
+  {
+    std::vector<e2_t> ft(n), fz(n);
+    for (uint32_t k = 0; k < n; k++) {                       // bit-reversed coefficient order -> natural
+      uint32_t pp = bitrev32(k, log_n);
+      ft[k] = hF[pp];
+      fz[k] = e2_add(hF[pp], hF[n + pp]);
+    }
+    // Q_z = (F - F(z)) / (X - z), padded back to n coefficients; final = alpha^C * Q_zeta + Q_{g zeta}
+    const e2_t shift = e2_pow(alpha, C);
+    e2_t a0 = e2_make(0, 0), a1 = e2_make(0, 0);
+    coeffs[n - 1] = e2_make(0, 0);
+    for (uint32_t k = n; k-- > 1;) {
+      a0 = e2_add(e2_mul(a0, zeta), fz[k]);
+      a1 = e2_add(e2_mul(a1, zeta_next), ft[k]);
+      coeffs[k - 1] = e2_add(e2_mul(a0, shift), a1);
+    }
+    if (p->flags & SB_FLAG_FRI_MUL_BY_X) { coeffs.insert(coeffs.begin(), e2_make(0, 0)); coeffs.pop_back(); }
+  }
+
+  // ---- FRI commit phase ----
+  const std::vector<unsigned> arities = fri_arities(*p);
+  struct Round { u64* re; u64* im; u64* tree; uint32_t n_leaves; unsigned log_size; };
+  std::vector<Round> rounds;
+  u64 shift = 7;
+  unsigned cur_log = log_N;
+  std::vector<u64> stage_re, stage_im;
+  for (size_t round = 0; round < arities.size(); round++) {
+    const unsigned ab = arities[round];
+    const size_t size = size_t(1) << cur_log;
+    // coset_fft(shift): c_m * shift^m, zero-padded to the LDE size, forward transform to bit-reversed order
+    u64* d_vals = ar.take<u64>(2 * size);
+    std::vector<u64> host(2 * size, 0);
+    u64 s = 1;
+    for (size_t m = 0; m < coeffs.size(); m++) {
+      host[m] = gl_mul(coeffs[m].a, s);
+      host[size + m] = gl_mul(coeffs[m].b, s);
+      s = gl_mul(s, shift);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d_vals, host.data(), 16ull * size, cudaMemcpyHostToDevice, st));
+    sb_ntt_device(ctx, d_vals, cur_log, 2, false, /*dif=*/true);
+    Round R;
+    R.re = d_vals; R.im = d_vals + size; R.log_size = cur_log; R.n_leaves = (uint32_t)(size >> ab);
+    R.tree = ar.take<u64>(8ull * R.n_leaves + 64);
+    sb_fri_leaf_hash_device(ctx, R.re, R.im, R.n_leaves, ab, R.tree);
+    sb_merkle_levels(ctx, R.tree, R.n_leaves, p->cap_height);
+    u64* cap_dst = W + L.off_fri_caps + round * 4ull * L.cap_len;
+    CUDA_CHECK(cudaMemcpyAsync(cap_dst, tree_cap_ptr(R.tree, R.n_leaves, p->cap_height), 32ull * L.cap_len, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));   // also keeps `host` alive until the upload is done
+    rounds.push_back(R);
+    ch.observe_many(cap_dst, 4ull * L.cap_len);
+    const e2_t beta = ch.ext_challenge();
+    const size_t arity = size_t(1) << ab;
+    std::vector<e2_t> folded(coeffs.size() / arity);
+    for (size_t m = 0; m < folded.size(); m++) {
+      e2_t acc = e2_make(0, 0);
+      for (size_t i = arity; i-- > 0;) acc = e2_add(e2_mul(acc, beta), coeffs[arity * m + i]);
+      folded[m] = acc;
+    }
+    coeffs.swap(folded);
+    shift = gl_pow(shift, arity);
+    cur_log -= ab;
+  }
+  if (coeffs.size() != L.final_poly_len) SB_THROW(SB_EINVAL, "internal: final polynomial length %zu != %u", coeffs.size(), L.final_poly_len);
+  for (size_t i = 0; i < coeffs.size(); i++) { W[L.off_final_poly + 2 * i] = coeffs[i].a; W[L.off_final_poly + 2 * i + 1] = coeffs[i].b; }
+  ch.observe_many(W + L.off_final_poly, 2ull * coeffs.size());
+
+  // ---- proof of work ----
+  u64 witness;
+  if (p->flags & SB_FLAG_FIXED_POW_WITNESS) witness = p->fixed_pow_witness;
+  else {
+    u64 inter[12];
+    memcpy(inter, ch.state, sizeof(inter));
+    for (int i = 0; i < ch.n_in; i++) inter[i] = ch.in_buf[i];
+    witness = sb_pow_device(ctx, inter, ch.n_in, p->pow_bits, ar.take<unsigned long long>(2));
+  }
+  ch.observe(witness);
+  const u64 response = ch.challenge();
+  if (p->pow_bits && (response >> (64 - p->pow_bits)) != 0) SB_THROW(SB_EPOW, "proof-of-work witness does not satisfy %u bits", p->pow_bits);
+  W[L.off_pow_witness] = witness;
+
+  // ---- query rounds ----
+  const uint32_t nQ = L.n_queries;
+  std::vector<uint32_t> h_idx(2ull * nQ);
+  for (uint32_t q = 0; q < nQ; q++) {
+    uint32_t x = (uint32_t)(ch.challenge() % N);
+    h_idx[q] = x;                                                             // plonky2 leaf index
+    h_idx[nQ + q] = (x & ~(n - 1)) | bitrev32(x & (n - 1), log_n);            // device LDE position of that leaf
+  }
+  uint32_t* d_idx = ar.take<uint32_t>(2ull * nQ);
+  u64* d_queries = ar.take<u64>(L.query_stride * nQ);
+  CUDA_CHECK(cudaMemcpyAsync(d_idx, h_idx.data(), 8ull * nQ, cudaMemcpyHostToDevice, st));
+  sb_gather_leaf_device(ctx, d_queries, L.query_stride, L.q_off_trace_leaf, ctx->lde.as<u64>(), N, C, d_idx + nQ, nQ);
+  sb_gather_path_device(ctx, d_queries, L.query_stride, L.q_off_trace_path, ctx->tree.as<u64>(), N, L.trace_path_len, d_idx, 0, nQ);
+  sb_gather_leaf_device(ctx, d_queries, L.query_stride, L.q_off_quot_leaf, ctx->qlde.as<u64>(), N, nq, d_idx + nQ, nQ);
+  sb_gather_path_device(ctx, d_queries, L.query_stride, L.q_off_quot_path, ctx->qtree.as<u64>(), N, L.trace_path_len, d_idx, 0, nQ);
+  unsigned sh = 0;
+  for (size_t round = 0; round < rounds.size(); round++) {
+    const unsigned ab = arities[round];
+    sh += ab;
+    const uint64_t off = fri_step_offset(L, (uint32_t)round);
+    sb_gather_fri_evals_device(ctx, d_queries, L.query_stride, off, rounds[round].re, rounds[round].im, ab, d_idx, sh, nQ);
+    sb_gather_path_device(ctx, d_queries, L.query_stride, off + (uint64_t(2) << ab), rounds[round].tree, rounds[round].n_leaves,
+                          fri_step_path_len(L, (uint32_t)round), d_idx, sh, nQ);
+  }
+  CUDA_CHECK(cudaEventRecord(ev[6], st));
+  CUDA_CHECK(cudaMemcpyAsync(W + L.off_queries, d_queries, 8ull * L.query_stride * nQ, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaEventRecord(ev[7], st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (p->n_public_inputs) memcpy(W + L.off_public_inputs, public_inputs, 8ull * p->n_public_inputs);
+
+  proof->ms_h2d = ev_ms(ev[0], ev[1]);
+  proof->ms_trace_commit = ev_ms(ev[1], ev[2]);
+  proof->ms_quotient = ev_ms(ev[2], ev[3]);
+  proof->ms_quotient_commit = ev_ms(ev[3], ev[4]);
+  proof->ms_openings = ev_ms(ev[4], ev[5]);
+  proof->ms_fri = ev_ms(ev[5], ev[6]);
+  proof->ms_d2h = ev_ms(ev[6], ev[7]);
+  proof->ms_total = ev_ms(ev[0], ev[7]);
+  stage_collect(ctx);
 }
 
 extern "C" {
-int sb_air_load(sb_ctx* ctx, uint32_t, const char*) { return sb_fail(ctx, SbError{SB_EAIR, "sb_air_load: not built yet"}); }
-int sb_prove(sb_ctx* ctx, const sb_params*, const void*, int, const uint64_t*, sb_proof**) { return sb_fail(ctx, SbError{SB_EINVAL, "sb_prove: not built yet"}); }
-void sb_proof_free(sb_proof* p) { if (p) { delete[] p->words; delete p; } }
-int sb_quotient_values(sb_ctx* ctx, const sb_params*, const uint64_t*, const uint64_t*, uint64_t*) { return sb_fail(ctx, SbError{SB_EINVAL, "sb_quotient_values: not built yet"}); }
+
+int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, const uint64_t* public_inputs, sb_proof** out) {
+  if (!ctx || !p || !out) return SB_EINVAL;
+  sb_proof* proof = nullptr;
+  try {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (p->n_cols == 0 || p->log_n < 1 || p->log_n > 13 || p->rate_bits < 1 || p->rate_bits > 4 ||
+        p->cap_height > p->log_n + p->rate_bits)
+      SB_THROW(SB_EINVAL, "bad parameters (n_cols %u, log_n %u, rate_bits %u, cap_height %u)", p->n_cols, p->log_n, p->rate_bits, p->cap_height);
+    proof = new sb_proof();
+    memset(proof, 0, sizeof(*proof));
+    proof->layout = proof_layout(*p);
+    cudaError_t e = cudaMallocHost((void**)&proof->words, 8ull * proof->layout.total_words);
+    if (e != cudaSuccess) { proof->words = nullptr; SB_THROW(SB_ENOMEM, "cudaMallocHost(proof, %llu words): %s", (unsigned long long)proof->layout.total_words, cudaGetErrorString(e)); }
+    prove_impl(ctx, p, trace, layout, public_inputs, proof);
+    *out = proof;
+    return SB_OK;
+  } catch (const SbError& e) {
+    cudaStreamSynchronize(ctx->stream);
+    sb_proof_free(proof);
+    return sb_fail(ctx, e);
+  } catch (const std::exception& e) {
+    cudaStreamSynchronize(ctx->stream);
+    sb_proof_free(proof);
+    return sb_fail(ctx, SbError{SB_EINVAL, e.what()});
+  }
 }
+
+void sb_proof_free(sb_proof* proof) {
+  if (!proof) return;
+  if (proof->words) cudaFreeHost(proof->words);
+  delete proof;
+}
+
+}  // extern "C"
