@@ -1,0 +1,253 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: starky prove ms/STARK on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--stark pairing_precomp] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full proof (sb_prove: trace LDE -> Poseidon Merkle -> quotient -> FRI -> proof in host memory) of one
+synthetic trace of the workload stark.  At N GPUs every rank proves its own trace (the reference's seven proofs are
+independent, SURVEY 8e "proof-level parallelism"), so scaling is weak and `value` = wall ms per step / N.
+  value : trace already resident in HBM when the timed region starts (layout DEVICE_COLMAJOR_U64)
+  e2e   : through the plugin call with the trace in pinned HOST memory (H2D of the trace and D2H of the proof inside)
+  --impl reference : the CPU restatement of the reference's prover (oracle/, all host threads) on the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+U32_MACS_PER_PERM = 6400          # algorithmic u32 multiply-adds per Poseidon-12 permutation
+U32_MACS_PER_CONSTRAINT = 10      # algorithmic u32 multiply-adds per constraint evaluation
+WORKLOADS = {
+    "fp12_mul": "FP12MulStark 60285 cols x 16 rows, rate_bits 1 (BASELINE configs[0])",
+    "pairing_precomp": "PairingPrecompStark 29376 cols x 1024 rows, rate_bits 2 (BASELINE configs[1])",
+    "miller_loop": "MillerLoopStark 97330 cols x 1024 rows, rate_bits 1 (BASELINE configs[2])",
+    "final_exp": "FinalExponentiateStark 73527 cols x 8192 rows, rate_bits 2 (BASELINE configs[3])",
+    "ecc_agg": "ECCAggStark 3339 cols x 8192 rows, rate_bits 2 (BASELINE configs[4] member)",
+}
+K_CONSTRAINTS = {"fp12_mul": 82560, "pairing_precomp": 113634, "miller_loop": 145574, "final_exp": 360800, "ecc_agg": 20013}
+
+
+def synthetic(info, seed):
+    """SURVEY 8d distribution A: every trace cell and public input uniform in [0, 2^32) (real traces are u32 limbs/bits)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    trace = rng.integers(0, 1 << 32, (info.columns, info.num_rows), dtype=np.uint64)
+    pis = rng.integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
+    return trace, pis
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [c for c in sm if mx and c > 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, info, rank, world):
+    """CPU arm: the oracle restatement of starky::prover::prove, all host threads, same stark and shape."""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    from starky_bls12_381_b200 import airfiles
+    O.build()
+    flat = airfiles.air_path(args.stark, "air")
+    trace, pis = synthetic(info, 0xB2000000 + info.stark_id)
+    p = O.make_params(stark_id=info.stark_id, log_n=info.num_rows.bit_length() - 1, n_cols=info.columns,
+                      n_pis=info.public_inputs, degree=info.constraint_degree, rate_bits=info.rate_bits, flags=1)
+    cores = O.lib().orc_num_threads()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rc, _ = O.prove(flat, p, trace, pis)
+        assert rc == 0, O.err()
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    line = {"impl": "reference", "metric": "starky_prove_ms_per_stark", "value": ms, "unit": "ms", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.stark], "trace": "uniform u32 cells, seeded PCG64",
+                       "note": "CPU restatement of the reference algorithm (oracle/), not the Rust binary: no cargo in the image"},
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": "one full proof per step"},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--stark", default="pairing_precomp", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import starky_bls12_381_b200 as sb
+    info = sb.STARKS[args.stark]
+    if args.impl == "reference":
+        return run_reference(args, info, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from starky_bls12_381_b200 import airfiles
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    airfiles.air_path(args.stark, "airbin")
+    ctx = sb.Context(local_rank)
+    p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+    trace, pis = synthetic(info, 0xB2000000 + info.stark_id + 1000 * rank)
+    # pinned host copy for the end-to-end leg; resident device copy for the kernel leg
+    host = torch.from_numpy(trace.view(np.int64)).pin_memory()
+    host_ptr = host.data_ptr()
+    ctx.trace_upload(p, host_ptr)
+    C, n, N = info.columns, info.num_rows, info.num_rows << info.rate_bits
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        out = [fn() for _ in range(steps)]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, out
+
+    resident = lambda: ctx.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64)
+    e2e_fn = lambda: ctx.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
+    for _ in range(args.warmup):
+        resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.kernel_launches()
+    dt, proofs = timed(resident, args.steps)
+    launches = ctx.kernel_launches() - l0
+    stage = {k: float(np.mean([pr.timings[k] for pr in proofs])) for k in proofs[0].timings}
+    kern = {k: ctx.stage_ms(k) for k in ("lde", "leaf_hash", "merkle", "quotient")}
+    e2e_fn()
+    dt_e2e, proofs_e2e = timed(e2e_fn, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = 1e3 * dt / args.steps
+    ms_e2e = 1e3 * dt_e2e / args.steps
+    proof_bytes = int(proofs[0].layout.total_words) * 8
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        imad = ctx.measure_imad_peak()
+        perms = -(-C // 8) * N + (N - 16)
+        t_hash = (kern["leaf_hash"] + kern["merkle"]) * 1e-3
+        t_lde = kern["lde"] * 1e-3
+        t_q = kern["quotient"] * 1e-3
+        lde_bytes = 8.0 * C * (n + n + N)           # trace read + coefficients kept + LDE written
+        roof = {
+            # dominant kernel of the step: the Poseidon leaf sponge (integer-pipe bound)
+            "kernel": "leaf_hash_kernel+merkle_level_kernel", "bound": "imad",
+            "achieved": perms * U32_MACS_PER_PERM / t_hash / 1e9, "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
+            "frac": perms * U32_MACS_PER_PERM / t_hash / 1e9 / imad["mad_lo_u32_gops"], "traffic": None,
+            "peak_source": "sb_measure_imad_peak: dependent-free mad.lo.u32, measured in this run",
+            "share_of_step": (kern["leaf_hash"] + kern["merkle"]) / ms_step,
+            "stages": {
+                "lde": {"bound": "hbm", "achieved": lde_bytes / t_lde / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": lde_bytes / t_lde / 1e9 / hbm_peak, "ms": kern["lde"], "peak_source": peak_src},
+                "merkle_hbm_view": {"bound": "hbm", "achieved": 8.0 * C * N / t_hash / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": 8.0 * C * N / t_hash / 1e9 / hbm_peak, "ms": kern["leaf_hash"] + kern["merkle"]},
+                "quotient": {"bound": "imad", "achieved": K_CONSTRAINTS[args.stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9,
+                             "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
+                             "frac": K_CONSTRAINTS[args.stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9 / imad["mad_lo_u32_gops"],
+                             "ms": kern["quotient"]},
+            },
+        }
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            import oracle_lib as O
+            O.build()
+            flat = airfiles.air_path(args.stark, "air")
+            op = O.Params.from_buffer_copy(bytes(p))
+            t0 = time.perf_counter()
+            rc, words = O.prove(flat, op, trace, pis)
+            cpu_ms = 1e3 * (time.perf_counter() - t0)
+            same = bool(rc == 0 and np.array_equal(words, proofs[0].words))
+            cpu = {"value": cpu_ms, "unit": "ms", "cores": int(O.lib().orc_num_threads()), "kind": "port",
+                   "sample": "one full proof of the same trace", "proof_bit_identical_to_gpu": same}
+        line = {
+            "metric": "starky_prove_ms_per_stark", "value": ms_step / world, "unit": "ms", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.stark], "trace": "uniform u32 cells, seeded PCG64, one trace per rank",
+                       "parallelism": "replicas: one independent proof per GPU, no data-path collective",
+                       "l2": "inputs larger than L2 (trace %.0f MB, LDE %.0f MB)" % (8e-6 * C * n, 8e-6 * C * N),
+                       "lde_merkle_gbs": 8.0 * C * N / ((kern["lde"] + kern["leaf_hash"] + kern["merkle"]) * 1e-3) / 1e9},
+            "e2e": {"value": ms_e2e / world, "unit": "ms", "h2d_bytes_per_step": 8 * C * n + 8 * info.public_inputs,
+                    "d2h_bytes_per_step": proof_bytes},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "stage_ms": stage, "kernel_ms": kern,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,7 @@
 #include "poseidon_rc.h"
 
 #if defined(__CUDACC__)
-__constant__ u64 c_poseidon_rc[POSEIDON_RC_COUNT] = POSEIDON_RC_TABLE;
+static __constant__ u64 c_poseidon_rc[POSEIDON_RC_COUNT] = POSEIDON_RC_TABLE;
 #endif
 static const u64 h_poseidon_rc[POSEIDON_RC_COUNT] = POSEIDON_RC_TABLE;
 

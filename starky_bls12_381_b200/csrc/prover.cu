@@ -88,6 +88,8 @@ sb_proof_layout proof_layout(const sb_params& p) {
 // ---------------------------------------------------------------------------------------------------------
 // plonky2 Challenger (duplex sponge over Poseidon-12), host side
 // ---------------------------------------------------------------------------------------------------------
+void sb_host_poseidon_permute(u64 s[12]);   // host_poseidon.cpp
+
 struct HostChallenger {
   u64 state[12];
   u64 in_buf[8]; int n_in = 0;
@@ -96,7 +98,7 @@ struct HostChallenger {
   void duplexing() {
     for (int i = 0; i < n_in; i++) state[i] = in_buf[i];
     n_in = 0;
-    poseidon_permute(state);
+    sb_host_poseidon_permute(state);
     memcpy(out_buf, state, 64);
     n_out = 8;
   }
@@ -353,6 +355,32 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
   stage_collect(ctx);
 }
 
+// Pinned host buffers for proofs are expensive to create (cudaMallocHost of tens of MB); sb_proof_free parks them
+// here and the next sb_prove of a fitting size takes one back.
+#include <mutex>
+static std::mutex g_pool_mu;
+static std::vector<std::pair<size_t, void*>> g_pool;
+static void* pinned_take(size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); i++)
+      if (g_pool[i].first >= bytes && g_pool[i].first <= 2 * bytes + 4096) {
+        void* p = g_pool[i].second;
+        g_pool.erase(g_pool.begin() + i);
+        return p;
+      }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) SB_THROW(SB_ENOMEM, "cudaMallocHost(proof, %zu bytes): %s", bytes, cudaGetErrorString(e));
+  return p;
+}
+static void pinned_give(void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool.size() >= 4) { cudaFreeHost(g_pool.front().second); g_pool.erase(g_pool.begin()); }
+  g_pool.push_back({bytes, p});
+}
+
 extern "C" {
 
 int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, const uint64_t* public_inputs, sb_proof** out) {
@@ -366,8 +394,7 @@ int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, con
     proof = new sb_proof();
     memset(proof, 0, sizeof(*proof));
     proof->layout = proof_layout(*p);
-    cudaError_t e = cudaMallocHost((void**)&proof->words, 8ull * proof->layout.total_words);
-    if (e != cudaSuccess) { proof->words = nullptr; SB_THROW(SB_ENOMEM, "cudaMallocHost(proof, %llu words): %s", (unsigned long long)proof->layout.total_words, cudaGetErrorString(e)); }
+    proof->words = (u64*)pinned_take(8ull * proof->layout.total_words);
     prove_impl(ctx, p, trace, layout, public_inputs, proof);
     *out = proof;
     return SB_OK;
@@ -384,7 +411,7 @@ int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, con
 
 void sb_proof_free(sb_proof* proof) {
   if (!proof) return;
-  if (proof->words) cudaFreeHost(proof->words);
+  if (proof->words) pinned_give(proof->words, 8ull * proof->layout.total_words);
   delete proof;
 }
 
