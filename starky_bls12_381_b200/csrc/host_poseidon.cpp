@@ -51,49 +51,104 @@ static void mds_scalar(u64 s[12]) {
   for (int r = 0; r < 12; r++) s[r] = recombine(al[r], ah[r]);
 }
 
-#if defined(__x86_64__)
-__attribute__((target("avx2"))) static void mds_avx2(u64 s[12]) {
-  alignas(32) u32 lo[32], hi[32];
-  alignas(32) u64 al[12], ah[12];
-  for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = (u32)s[i]; hi[i] = hi[i + 12] = (u32)(s[i] >> 32); }
-  __m256i a0 = _mm256_setzero_si256(), a1 = a0, a2 = a0, h0 = a0, h1 = a0, h2 = a0;
-  for (int i = 0; i < 12; i++) {
-    const __m256i c = _mm256_set1_epi64x(CIRC[i]);
-#define LD(p) _mm256_cvtepu32_epi64(_mm_loadu_si128((const __m128i*)(p)))
-    a0 = _mm256_add_epi64(a0, _mm256_mul_epu32(LD(lo + i), c));
-    a1 = _mm256_add_epi64(a1, _mm256_mul_epu32(LD(lo + i + 4), c));
-    a2 = _mm256_add_epi64(a2, _mm256_mul_epu32(LD(lo + i + 8), c));
-    h0 = _mm256_add_epi64(h0, _mm256_mul_epu32(LD(hi + i), c));
-    h1 = _mm256_add_epi64(h1, _mm256_mul_epu32(LD(hi + i + 4), c));
-    h2 = _mm256_add_epi64(h2, _mm256_mul_epu32(LD(hi + i + 8), c));
-#undef LD
-  }
-  _mm256_store_si256((__m256i*)al, a0); _mm256_store_si256((__m256i*)(al + 4), a1); _mm256_store_si256((__m256i*)(al + 8), a2);
-  _mm256_store_si256((__m256i*)ah, h0); _mm256_store_si256((__m256i*)(ah + 4), h1); _mm256_store_si256((__m256i*)(ah + 8), h2);
-  al[0] += 8 * (u64)lo[0]; ah[0] += 8 * (u64)hi[0];
-  for (int r = 0; r < 12; r++) s[r] = recombine(al[r], ah[r]);
-}
-#endif
-
-template <class Mds>
-static inline void permute_with(u64 s[12], Mds mds) {
+static void permute_scalar(u64 s[12]) {
   for (int r = 0; r < 30; r++) {
     for (int i = 0; i < 12; i++) { u64 v = s[i] + RC[12 * r + i]; v += mask_of(v < s[i]) & EPS; s[i] = v; }
     if (r < 4 || r >= 26) { for (int i = 0; i < 12; i++) s[i] = sbox(s[i]); }
     else s[0] = sbox(s[0]);
-    mds(s);
+    mds_scalar(s);
   }
   for (int i = 0; i < 12; i++) s[i] -= mask_of(s[i] >= P) & P;
 }
 
 #if defined(__x86_64__)
-__attribute__((target("avx2"))) static void permute_avx2(u64 s[12]) { permute_with(s, mds_avx2); }
+// ---- AVX2: the 12-word state lives in three 4-lane vectors; full-round S-boxes, round constants and the MDS layer
+// are vectorised, the single partial-round S-box stays scalar (it is a pure latency chain). ----
+#define TGT __attribute__((target("avx2"))) static inline
+typedef __m256i V;
+TGT V vset(u64 x) { return _mm256_set1_epi64x((long long)x); }
+TGT V ult(V a, V b) {   // unsigned a < b per lane -> all-ones
+  const V S = vset(1ull << 63);
+  return _mm256_cmpgt_epi64(_mm256_xor_si256(b, S), _mm256_xor_si256(a, S));
+}
+TGT V vadd_lazy(V a, V c) {   // lazy + canonical -> lazy
+  V s = _mm256_add_epi64(a, c);
+  return _mm256_add_epi64(s, _mm256_srli_epi64(ult(s, a), 32));
+}
+TGT V vmul(V a, V b) {        // lazy x lazy -> lazy
+  const V M32 = vset(EPS);
+  V ah = _mm256_srli_epi64(a, 32), bh = _mm256_srli_epi64(b, 32);
+  V ll = _mm256_mul_epu32(a, b), lh = _mm256_mul_epu32(a, bh), hl = _mm256_mul_epu32(ah, b), hh = _mm256_mul_epu32(ah, bh);
+  V mid = _mm256_add_epi64(lh, _mm256_srli_epi64(ll, 32));
+  V mid2 = _mm256_add_epi64(hl, _mm256_and_si256(mid, M32));
+  V lo = _mm256_or_si256(_mm256_and_si256(ll, M32), _mm256_slli_epi64(mid2, 32));
+  V hi = _mm256_add_epi64(_mm256_add_epi64(hh, _mm256_srli_epi64(mid, 32)), _mm256_srli_epi64(mid2, 32));
+  V hi_hi = _mm256_srli_epi64(hi, 32), hi_lo = _mm256_and_si256(hi, M32);
+  V t0 = _mm256_sub_epi64(_mm256_sub_epi64(lo, hi_hi), _mm256_srli_epi64(ult(lo, hi_hi), 32));
+  V t1 = _mm256_sub_epi64(_mm256_slli_epi64(hi_lo, 32), hi_lo);
+  V r = _mm256_add_epi64(t0, t1);
+  return _mm256_add_epi64(r, _mm256_srli_epi64(ult(r, t1), 32));
+}
+TGT V vsbox(V x) { V x2 = vmul(x, x), x4 = vmul(x2, x2), x3 = vmul(x2, x); return vmul(x3, x4); }
+
+// CV[w][j][l] = coefficient of input word w in output row 4j + l
+alignas(32) static u64 CV[12][3][4];
+static const bool cv_ready = [] {
+  for (int w = 0; w < 12; w++)
+    for (int j = 0; j < 3; j++)
+      for (int l = 0; l < 4; l++) {
+        int row = 4 * j + l;
+        CV[w][j][l] = CIRC[((w - row) % 12 + 12) % 12] + ((w == 0 && row == 0) ? 8 : 0);
+      }
+  return true;
+}();
+
+TGT void vmds(V& s0, V& s1, V& s2) {
+  alignas(32) u64 st[12];
+  _mm256_store_si256((__m256i*)st, s0); _mm256_store_si256((__m256i*)(st + 4), s1); _mm256_store_si256((__m256i*)(st + 8), s2);
+  V al0 = _mm256_setzero_si256(), al1 = al0, al2 = al0, ah0 = al0, ah1 = al0, ah2 = al0;
+  for (int w = 0; w < 12; w++) {
+    V b = _mm256_set1_epi64x((long long)st[w]), bh = _mm256_srli_epi64(b, 32);
+    V c0 = _mm256_load_si256((const __m256i*)CV[w][0]), c1 = _mm256_load_si256((const __m256i*)CV[w][1]),
+      c2 = _mm256_load_si256((const __m256i*)CV[w][2]);
+    al0 = _mm256_add_epi64(al0, _mm256_mul_epu32(b, c0)); al1 = _mm256_add_epi64(al1, _mm256_mul_epu32(b, c1));
+    al2 = _mm256_add_epi64(al2, _mm256_mul_epu32(b, c2));
+    ah0 = _mm256_add_epi64(ah0, _mm256_mul_epu32(bh, c0)); ah1 = _mm256_add_epi64(ah1, _mm256_mul_epu32(bh, c1));
+    ah2 = _mm256_add_epi64(ah2, _mm256_mul_epu32(bh, c2));
+  }
+  V al[3] = {al0, al1, al2}, ah[3] = {ah0, ah1, ah2}, out[3];
+  for (int j = 0; j < 3; j++) {   // al + ah * 2^32  (mod p), lazy
+    V a_hi = _mm256_srli_epi64(ah[j], 32);
+    V c = _mm256_sub_epi64(_mm256_slli_epi64(a_hi, 32), a_hi), b = _mm256_slli_epi64(ah[j], 32);
+    V t = _mm256_add_epi64(al[j], c), v = _mm256_add_epi64(b, t);
+    out[j] = _mm256_add_epi64(v, _mm256_srli_epi64(ult(v, t), 32));
+  }
+  s0 = out[0]; s1 = out[1]; s2 = out[2];
+}
+
+alignas(32) static const u64 RCA[POSEIDON_RC_COUNT] = POSEIDON_RC_TABLE;
+__attribute__((target("avx2"))) static void permute_avx2(u64 s[12]) {
+  V s0 = _mm256_loadu_si256((const __m256i*)s), s1 = _mm256_loadu_si256((const __m256i*)(s + 4)),
+    s2 = _mm256_loadu_si256((const __m256i*)(s + 8));
+  for (int r = 0; r < 30; r++) {
+    s0 = vadd_lazy(s0, _mm256_load_si256((const __m256i*)(RCA + 12 * r)));
+    s1 = vadd_lazy(s1, _mm256_load_si256((const __m256i*)(RCA + 12 * r + 4)));
+    s2 = vadd_lazy(s2, _mm256_load_si256((const __m256i*)(RCA + 12 * r + 8)));
+    if (r < 4 || r >= 26) { s0 = vsbox(s0); s1 = vsbox(s1); s2 = vsbox(s2); }
+    else {
+      u64 x = sbox((u64)_mm256_extract_epi64(s0, 0));
+      s0 = _mm256_blend_epi32(s0, _mm256_set1_epi64x((long long)x), 0x03);
+    }
+    vmds(s0, s1, s2);
+  }
+  _mm256_storeu_si256((__m256i*)s, s0); _mm256_storeu_si256((__m256i*)(s + 4), s1); _mm256_storeu_si256((__m256i*)(s + 8), s2);
+  for (int i = 0; i < 12; i++) s[i] -= mask_of(s[i] >= P) & P;
+}
 #endif
-static void permute_scalar(u64 s[12]) { permute_with(s, mds_scalar); }
 
 void sb_host_poseidon_permute(u64 s[12]) {
 #if defined(__x86_64__)
-  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  static const bool have_avx2 = __builtin_cpu_supports("avx2") && cv_ready;
   if (have_avx2) { permute_avx2(s); return; }
 #endif
   permute_scalar(s);
