@@ -52,48 +52,37 @@ GL_HD u64 gl_reduce128_lazy(u64 lo, u64 hi) {
   return r;
 }
 // any u64 x any u64 -> lazy.
-// Device path: every heavy kernel here is bound by the ALU pipe (IADD3/ISETP/SEL carry handling), not by the IMAD
-// (FMA) pipe -- ncu: lde_kernel alu 78% / fma 20% -- so the 128-bit product is built from five mad.wide.u32 on the
-// FMA pipe with no carry logic at all (each partial sum provably fits 64 bits), and the Goldilocks fold
-//   x0 + x1 2^32 + x2 2^64 + x3 2^96  =  (x1:x0) - x3 + x2 (2^32-1)      (2^64 = 2^32-1, 2^96 = -1 mod p)
-// uses 32-bit carry chains (add.cc/addc) instead of 64-bit compares and selects.
+// Device path.  The 128-bit product x3:x2:x1:x0 is left to ptxas (mul.lo.u64 + mul.hi.u64 share four IMAD.WIDE.U32,
+// two of them with carry-out / carry-in, seven instructions in four dependent levels -- shorter than anything that
+// can be spelled in PTX).  The Goldilocks fold
+//     x0 + x1 2^32 + x2 2^64 + x3 2^96  =  (x1:x0) + x2 eps - x3          (2^64 = eps = 2^32-1, 2^96 = -1 mod p)
+// is written with 32-bit carry chains instead of 64-bit compares and selects:
+//     w  = x2 * eps + x0 = (x2 : x0) - x2                       (fits 64 bits: <= (2^32-1)^2 + 2^32-1)
+//     w += x1 * 2^32   -> carry  c1          w -= x3   -> borrow b1
+//     r  = w + c1 * eps - b1 * eps            (a carry / borrow of 2^64 is worth eps mod p)
+// If only c1 is set the wrapped w is <= 2^64 - 2^33, if only b1 is set it is >= 2^64 - 2^32 + 1, so neither repair
+// can wrap; if both are set they cancel in Z/2^64.  12 ALU instructions in 8 dependent levels.
 GL_HD u64 gl_mul_lazy(u64 a, u64 b) {
 #if defined(__CUDA_ARCH__)
-  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  const u64 lo = a * b, hi = __umul64hi(a, b);
   u32 r0, r1;
   asm("{\n\t"
-      ".reg .u64 p, t, u, v, m;\n\t"
-      ".reg .u32 x0, x1, x2, x3, ph, tl, th, uh, bw, cy, m0, m1;\n\t"
-      "mul.wide.u32 p, %2, %4;\n\t"             // a0*b0
-      "mov.b64 {x0, ph}, p;\n\t"
-      "cvt.u64.u32 t, ph;\n\t"
-      "mad.wide.u32 t, %2, %5, t;\n\t"          // a0*b1 + hi(p)            < 2^64
-      "mov.b64 {tl, th}, t;\n\t"
-      "cvt.u64.u32 u, tl;\n\t"
-      "mad.wide.u32 u, %3, %4, u;\n\t"          // a1*b0 + lo(t)            < 2^64
-      "mov.b64 {x1, uh}, u;\n\t"
-      "cvt.u64.u32 v, th;\n\t"
-      "mad.wide.u32 v, %3, %5, v;\n\t"          // a1*b1 + hi(t)            < 2^64
-      "mad.wide.u32 v, uh, 1, v;\n\t"           // + hi(u)   (total product < 2^128)
-      "mov.b64 {x2, x3}, v;\n\t"
-      // fold: r = (x1:x0) - x3, borrow -> subtract 2^32-1 more
-      "sub.cc.u32 %0, x0, x3;\n\t"
-      "subc.cc.u32 %1, x1, 0;\n\t"
-      "subc.u32 bw, 0, 0;\n\t"                  // 0 or 0xFFFFFFFF
-      "sub.cc.u32 %0, %0, bw;\n\t"
-      "subc.u32 %1, %1, 0;\n\t"
-      // + x2 * (2^32 - 1), carry -> add 2^32-1 more
-      "mul.wide.u32 m, x2, 0xFFFFFFFF;\n\t"
-      "mov.b64 {m0, m1}, m;\n\t"
-      "add.cc.u32 %0, %0, m0;\n\t"
-      "addc.cc.u32 %1, %1, m1;\n\t"
-      "addc.u32 cy, 0, 0;\n\t"                  // 0 or 1
-      "neg.s32 cy, cy;\n\t"                     // 0 or 0xFFFFFFFF = the value to add
-      "add.cc.u32 %0, %0, cy;\n\t"
+      ".reg .u32 nc, nb;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"        // w = (x2:x0) - x2
+      "subc.u32 %1, %4, 0;\n\t"
+      "add.cc.u32 %1, %1, %3;\n\t"        // w += x1 * 2^32
+      "addc.u32 nc, 0, 0;\n\t"            // carry c1 (an add-chain flag must not feed subc: the borrow sense differs)
+      "neg.s32 nc, nc;\n\t"               // 0 or 0xFFFFFFFF = c1 * eps
+      "sub.cc.u32 %0, %0, %5;\n\t"        // w -= x3
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 nb, 0, 0;\n\t"            // 0 - borrow: 0 or 0xFFFFFFFF = b1 * eps
+      "add.cc.u32 %0, %0, nc;\n\t"        // + c1 * eps
       "addc.u32 %1, %1, 0;\n\t"
+      "sub.cc.u32 %0, %0, nb;\n\t"        // - b1 * eps
+      "subc.u32 %1, %1, 0;\n\t"
       "}"
       : "=&r"(r0), "=&r"(r1)
-      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
   return ((u64)r1 << 32) | r0;
 #else
   u64 lo, hi;

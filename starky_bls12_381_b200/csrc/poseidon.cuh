@@ -12,7 +12,32 @@
 #include "poseidon_rc.h"
 
 #if defined(__CUDACC__)
-static __constant__ u64 c_poseidon_rc[POSEIDON_RC_COUNT] = POSEIDON_RC_TABLE;
+// 30 x 12 round constants followed by 12 zeros ("the constants of the round after the last one"): kernels that fold
+// the next round's constant addition into the MDS accumulators read row rd + 1 unconditionally.
+static __constant__ u64 c_poseidon_rc[POSEIDON_RC_COUNT + 12] = POSEIDON_RC_TABLE;
+
+// (hi:lo) += x * c as ONE IMAD.WIDE.U32 on the FMA pipe: ptxas fuses the mad.lo.cc / madc.hi pair and, unlike
+// with mad.wide.u32, keeps a chain of them as written instead of re-associating it into IMAD + IADD3 trees.
+// No carry out: callers guarantee the running sum fits 64 bits.
+__device__ __forceinline__ void mac32(u32& lo, u32& hi, u32 x, u32 c) {
+  asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(x), "r"(c));
+}
+// MDS output word from its two half accumulators: al + ah * 2^32 with al, ah < 2^43  ->  lazy u64
+__device__ __forceinline__ u64 mds_recombine(u32 al0, u32 al1, u32 ah0, u32 ah1) {
+  // t = al + ah1 * (2^64 mod p) < 2^44;  hi(t) += ah0;  a carry out owes 2^64 = eps, and the wrapped value is < 2^44
+  asm("{\n\t"
+      ".reg .u32 cy;\n\t"
+      "mad.lo.cc.u32 %0, %3, 0xFFFFFFFF, %0;\n\t"
+      "madc.hi.u32 %1, %3, 0xFFFFFFFF, %1;\n\t"
+      "add.cc.u32 %1, %1, %2;\n\t"
+      "addc.u32 cy, 0, 0;\n\t"
+      "mad.lo.cc.u32 %0, cy, 0xFFFFFFFF, %0;\n\t"
+      "madc.hi.u32 %1, cy, 0xFFFFFFFF, %1;\n\t"
+      "}"
+      : "+r"(al0), "+r"(al1)
+      : "r"(ah0), "r"(ah1));
+  return ((u64)al1 << 32) | al0;
+}
 #endif
 static const u64 h_poseidon_rc[POSEIDON_RC_COUNT] = POSEIDON_RC_TABLE;
 
@@ -48,8 +73,17 @@ GL_HD void poseidon_mds(u64 s[12]) {
   }
 #pragma unroll
   for (int r = 0; r < 12; r++) {
-    u64 al = 0, ah = 0;
+#if defined(__CUDA_ARCH__)
+    u32 al0 = 0, al1 = 0, ah0 = 0, ah1 = 0;
 #pragma unroll
+    for (int i = 0; i < 12; i++) {
+      mac32(al0, al1, lo[(i + r) % 12], C[i]);
+      mac32(ah0, ah1, hi[(i + r) % 12], C[i]);
+    }
+    if (r == 0) { mac32(al0, al1, lo[0], 8u); mac32(ah0, ah1, hi[0], 8u); }
+    s[r] = mds_recombine(al0, al1, ah0, ah1);
+#else
+    u64 al = 0, ah = 0;
     for (int i = 0; i < 12; i++) {
       al += (u64)C[i] * lo[(i + r) % 12];
       ah += (u64)C[i] * hi[(i + r) % 12];
@@ -65,6 +99,7 @@ GL_HD void poseidon_mds(u64 s[12]) {
     u64 v = b + t;
     if (v < t) v += GL_EPS;
     s[r] = v;                             // lazy
+#endif
   }
 }
 

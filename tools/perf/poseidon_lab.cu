@@ -1,0 +1,219 @@
+// Standalone lab for the Poseidon leaf sponge (K2): times kernel variants on synthetic column-major data and checks
+// every variant against a one-thread-per-leaf kernel and a host permutation.  Not part of the product library.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I starky_bls12_381_b200/csrc \
+//        tools/perf/poseidon_lab.cu -o gpurun_out/poseidon_lab
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "leafhash.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__host__ __device__ inline u64 splitmix(u64 x) {
+  x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL; x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__host__ __device__ inline u64 cell(u64 idx) { u64 v = splitmix(idx); return v >= GL_P ? v - GL_P : v; }
+__global__ void fill_kernel(u64* d, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = cell(i);
+}
+
+// one thread per leaf, whole state in registers
+__global__ void __launch_bounds__(128) ref_leaf_kernel(const u64* __restrict__ cols, uint32_t leaf_len, uint32_t n_leaves, u64* digests) {
+  uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_leaves) return;
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  uint32_t chunks = (leaf_len + 7) / 8;
+  for (uint32_t c = 0; c < chunks; c++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (c * 8 + i < leaf_len) s[i] = cols[(size_t)(c * 8 + i) * n_leaves + pos];
+    poseidon_permute(s);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) digests[4ull * pos + i] = s[i];
+}
+
+__global__ void mul_check_kernel(const u64* a, const u64* b, u64* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = gl_mul(a[i], b[i]);
+}
+static int mul_check() {
+  std::vector<u64> edge = {0, 1, 2, 7, 0xFFFFFFFFULL, 0x100000000ULL, 0x100000001ULL, 0xFFFFFFFEULL, GL_P - 1, GL_P, GL_P + 1, GL_P - 2,
+                           0xFFFFFFFFFFFFFFFFULL, 0xFFFFFFFFFFFFFFFEULL, 0xFFFFFFFF00000000ULL, 0xFFFFFFFEFFFFFFFFULL, 0x8000000000000000ULL,
+                           0x7FFFFFFFFFFFFFFFULL, 0x00000000FFFFFFFEULL, 0xFFFFFFFE00000001ULL, 0xFFFFFFFE00000002ULL, 0x0000000100000000ULL - 2,
+                           0xFFFF0000FFFF0000ULL, 0x0000FFFF0000FFFFULL, 0x00000001FFFFFFFFULL, 0xFFFFFFFF00000002ULL};
+  std::vector<u64> a, b;
+  for (u64 x : edge) for (u64 y : edge) { a.push_back(x); b.push_back(y); }
+  for (int i = 0; i < 2000000; i++) {
+    u64 x = splitmix(2 * i + 11), y = splitmix(2 * i + 12);
+    if (i % 7 == 0) x &= 0xFFFFFFFFULL; if (i % 11 == 0) y |= 0xFFFFFFFF00000000ULL; if (i % 13 == 0) x |= 0xFFFFFFFF00000000ULL;
+    if (i % 17 == 0) y &= 0xFFFFFFFF00000000ULL; if (i % 19 == 0) x = edge[i % edge.size()];
+    a.push_back(x); b.push_back(y);
+  }
+  int n = (int)a.size();
+  u64 *da, *db, *dc;
+  CK(cudaMalloc(&da, 8ull * n)); CK(cudaMalloc(&db, 8ull * n)); CK(cudaMalloc(&dc, 8ull * n));
+  CK(cudaMemcpy(da, a.data(), 8ull * n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db, b.data(), 8ull * n, cudaMemcpyHostToDevice));
+  mul_check_kernel<<<(n + 255) / 256, 256>>>(da, db, dc, n);
+  std::vector<u64> c(n);
+  CK(cudaMemcpy(c.data(), dc, 8ull * n, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int i = 0; i < n; i++) {
+    unsigned __int128 m = (unsigned __int128)a[i] * b[i];
+    u64 want = (u64)(m % GL_P);
+    if (c[i] != want) { if (bad < 5) printf("  mul mismatch: %016llx * %016llx = %016llx want %016llx\n", (unsigned long long)a[i], (unsigned long long)b[i], (unsigned long long)c[i], (unsigned long long)want); bad++; }
+  }
+  printf("gl_mul check: %d pairs, %d mismatches\n", n, bad);
+  cudaFree(da); cudaFree(db); cudaFree(dc);
+  return bad;
+}
+
+// latency probes: one warp, dependent chains
+__global__ void mul_latency_kernel(u64* out, u64 a, int iters, long long* cycles) {
+  u64 x = a + threadIdx.x;
+  long long t0 = clock64();
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) x = gl_mul_lazy(x, x);
+  }
+  long long t1 = clock64();
+  out[threadIdx.x] = x;
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+template <int ILP>
+__global__ void mul_tput_kernel(u64* out, u64 a, int iters) {
+  u64 x[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; j++) x[j] = a + threadIdx.x * 7 + j + blockIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int j = 0; j < ILP; j++) x[j] = gl_mul_lazy(x[j], x[j]);
+  }
+  u64 acc = 0;
+#pragma unroll
+  for (int j = 0; j < ILP; j++) acc ^= x[j];
+  if (acc == 0x1234567) out[0] = acc;
+}
+__global__ void perm_latency_kernel(u64* out, int iters, long long* cycles) {
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = threadIdx.x + i;
+  long long t0 = clock64();
+  for (int i = 0; i < iters; i++) poseidon_permute(s);
+  long long t1 = clock64();
+#pragma unroll
+  for (int i = 0; i < 12; i++) out[threadIdx.x * 12 + i] = s[i];
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <class F>
+static float time_ms(F&& launch, int reps = 3) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int r = 0; r < reps; r++) {
+    cudaEventRecord(a); launch(); cudaEventRecord(b);
+    CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return best;
+}
+
+int main(int argc, char** argv) {
+  int dev = 0; CK(cudaSetDevice(dev));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
+  printf("device %s, %d SMs, %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
+
+  if (argc > 4 && !strcmp(argv[1], "one")) {   // one variant, one shape (for ncu): one <wps> <n_leaves> <leaf_len>
+    int wps = atoi(argv[2]); uint32_t nl = atoi(argv[3]), ll = atoi(argv[4]);
+    size_t cells = (size_t)nl * ll;
+    u64 *d_cols, *d_dig;
+    CK(cudaMalloc(&d_cols, 8 * cells)); CK(cudaMalloc(&d_dig, 32ull * nl));
+    fill_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_cols, cells);
+    CK(cudaDeviceSynchronize());
+    unsigned g32 = (nl + 31) / 32;
+    for (int rep = 0; rep < 2; rep++) {
+      float ms = time_ms([&] {
+        if (wps == 12) leaf_sponge_ws_kernel<12><<<g32, 384>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 4) leaf_sponge_ws_kernel<4><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
+        else leaf_sponge_ws_kernel<1><<<g32, 32>>>(d_cols, ll, nl, 0, d_dig);
+      }, 1);
+      printf("ws<%d> N=%u C=%u: %.3f ms\n", wps, nl, ll, ms);
+    }
+    return 0;
+  }
+  // ---- latency / throughput probes ----
+  if (mul_check()) return 1;
+  u64* d_out; long long* d_cyc; CK(cudaMalloc(&d_out, 1 << 20)); CK(cudaMalloc(&d_cyc, 64));
+  long long cyc;
+  mul_latency_kernel<<<1, 32>>>(d_out, 12345, 64, d_cyc); mul_latency_kernel<<<1, 32>>>(d_out, 12345, 64, d_cyc);
+  CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+  printf("gl_mul_lazy dependent latency: %.1f cycles\n", (double)cyc / (64 * 16));
+  perm_latency_kernel<<<1, 32>>>(d_out, 16, d_cyc); perm_latency_kernel<<<1, 32>>>(d_out, 16, d_cyc);
+  CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+  printf("poseidon_permute one-warp latency: %.0f cycles\n", (double)cyc / 16);
+  {
+    const int iters = 2048, grid = prop.multiProcessorCount * 8, block = 256;
+    float ms1 = time_ms([&] { mul_tput_kernel<1><<<grid, block>>>(d_out, 3, iters); });
+    float ms4 = time_ms([&] { mul_tput_kernel<4><<<grid, block>>>(d_out, 3, iters / 4); });
+    float ms8 = time_ms([&] { mul_tput_kernel<8><<<grid, block>>>(d_out, 3, iters / 8); });
+    double muls = (double)grid * block * iters * 4;
+    printf("gl_mul_lazy throughput: ILP1 %.1f  ILP4 %.1f  ILP8 %.1f Gmul/s\n", muls / ms1 / 1e6, muls / ms4 / 1e6, muls / ms8 / 1e6);
+  }
+
+  // ---- leaf sponge variants ----
+  struct Shape { const char* name; uint32_t n_leaves, leaf_len; };
+  std::vector<Shape> shapes = {{"ML-like", 2048, 8003}, {"PP-like", 4096, 8003}, {"ECC-like", 32768, 3339}, {"FE-like", 32768, 8003},
+                               {"ragged", 1000, 77}};
+  if (argc > 1 && !strcmp(argv[1], "full")) {
+    shapes.push_back({"PP", 4096, 29376}); shapes.push_back({"ML", 2048, 97330}); shapes.push_back({"FE", 32768, 73527});
+  }
+  for (const Shape& sh : shapes) {
+    const size_t cells = (size_t)sh.n_leaves * sh.leaf_len;
+    u64 *d_cols, *d_ref, *d_dig;
+    CK(cudaMalloc(&d_cols, 8 * cells)); CK(cudaMalloc(&d_ref, 32ull * sh.n_leaves)); CK(cudaMalloc(&d_dig, 32ull * sh.n_leaves));
+    fill_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_cols, cells);
+    CK(cudaDeviceSynchronize());
+    const double perms = (double)((sh.leaf_len + 7) / 8) * sh.n_leaves;
+    float ms = time_ms([&] { ref_leaf_kernel<<<(sh.n_leaves + 31) / 32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, d_ref); }, 2);
+    printf("%-8s N=%6u C=%6u  ref(1 thread/leaf, block 32): %9.3f ms  %7.1f Mperm/s\n", sh.name, sh.n_leaves, sh.leaf_len, ms, perms / ms / 1e3);
+    std::vector<u64> ref(4ull * sh.n_leaves), got(4ull * sh.n_leaves);
+    CK(cudaMemcpy(ref.data(), d_ref, 32ull * sh.n_leaves, cudaMemcpyDeviceToHost));
+    // host check of 3 leaves
+    for (uint32_t leaf : {0u, sh.n_leaves / 2 + 1, sh.n_leaves - 1}) {
+      u64 s[12] = {0};
+      for (uint32_t c = 0; c < (sh.leaf_len + 7) / 8; c++) {
+        for (int i = 0; i < 8; i++) if (c * 8 + i < sh.leaf_len) s[i] = cell((size_t)(c * 8 + i) * sh.n_leaves + leaf);
+        poseidon_permute(s);
+      }
+      if (memcmp(s, &ref[4ull * leaf], 32)) { printf("  HOST MISMATCH at leaf %u\n", leaf); return 1; }
+    }
+    auto run = [&](const char* name, auto launch) {
+      CK(cudaMemset(d_dig, 0, 32ull * sh.n_leaves));
+      float t = time_ms(launch);
+      CK(cudaMemcpy(got.data(), d_dig, 32ull * sh.n_leaves, cudaMemcpyDeviceToHost));
+      bool ok = !memcmp(got.data(), ref.data(), 32ull * sh.n_leaves);
+      printf("    %-28s %9.3f ms  %7.1f Mperm/s  %s\n", name, t, perms / t / 1e3, ok ? "ok" : "MISMATCH");
+    };
+    const unsigned g32 = (sh.n_leaves + 31) / 32;
+    run("ws<1>  (12 words/thread)", [&] { leaf_sponge_ws_kernel<1><<<g32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("ws<2>  (6 words/thread)", [&] { leaf_sponge_ws_kernel<2><<<g32, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("ws<3>  (4 words/thread)", [&] { leaf_sponge_ws_kernel<3><<<g32, 96>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("ws<4>  (3 words/thread)", [&] { leaf_sponge_ws_kernel<4><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("ws<6>  (2 words/thread)", [&] { leaf_sponge_ws_kernel<6><<<g32, 192>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("ws<12> (1 word/thread)", [&] { leaf_sponge_ws_kernel<12><<<g32, 384>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    cudaFree(d_cols); cudaFree(d_ref); cudaFree(d_dig);
+  }
+  printf("lab done\n");
+  return 0;
+}
