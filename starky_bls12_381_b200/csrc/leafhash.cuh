@@ -118,3 +118,133 @@ __global__ void __launch_bounds__(32 * WPS) leaf_sponge_ws_kernel(const u64* __r
       if (w0 + k < 4) d[w0 + k] = gl_canon(s[k]);
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// WPS = 12 specialisation (one word per warp) for the latency-bound shapes (N = 2048..4096 leaves: every leaf is in
+// flight at once, so wall time = permutations per leaf x time of one permutation of a 32-leaf group).
+// The 22 partial rounds are the critical path: word 0 goes through x^7 every round while the other eleven words are
+// only mixed.  Two named barriers per partial round split the MDS layer so that only the word-0 term waits for the
+// S-box:
+//   A: words 1..11 (known as soon as the previous layer ends) are published; every warp accumulates its eleven-term
+//      partial row while warp 0 is still inside the S-box (its own row's partial sum interleaves with the S-box);
+//   B: warp 0 publishes y0 = x0^7 and only *arrives*; the others wait, add c_j0 * y0 and reduce.
+// Row 0 of the exchange tile is kept zero during partial rounds so that all twelve row reads keep their immediate
+// coefficients.
+// ---------------------------------------------------------------------------------------------------------
+// Row of the MDS layer: sum_i c[i] * t[i] + rc as half accumulators, CH IMAD.WIDE chains per half.  (Measured on B200:
+// a dependent IMAD.WIDE accumulate costs ~9 cycles, yet CH = 2, 3 were not faster than CH = 1 -- the exchange through
+// shared memory, 144 LDS.64 per round and 32-leaf group = 40 % of the LSU data pipe, is what the round waits for.)
+template <int CH, class Coef>
+__device__ __forceinline__ void mds_row(const u64 (&t)[12], Coef coef, u64 rc, int k0, u32& al0, u32& al1, u32& ah0, u32& ah1) {
+  u32 l0[CH], l1[CH], h0[CH], h1[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) { l0[c] = 0; l1[c] = 0; h0[c] = 0; h1[c] = 0; }
+  l0[0] = (u32)rc; h0[0] = (u32)(rc >> 32);
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    if (k >= k0) {
+      mac32(l0[k % CH], l1[k % CH], (u32)t[k], coef(k));
+      mac32(h0[k % CH], h1[k % CH], (u32)(t[k] >> 32), coef(k));
+    }
+  }
+  u64 al = ((u64)l1[0] << 32) | l0[0], ah = ((u64)h1[0] << 32) | h0[0];
+#pragma unroll
+  for (int c = 1; c < CH; c++) { al += ((u64)l1[c] << 32) | l0[c]; ah += ((u64)h1[c] << 32) | h0[c]; }
+  al0 = (u32)al; al1 = (u32)(al >> 32); ah0 = (u32)ah; ah1 = (u32)(ah >> 32);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+static __constant__ u32 c_poseidon_circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+
+// LAYOUT 0: 12 warps, word = warp id.   LAYOUT 1: 12 warps, word = 11 - warp id (the arbiter favours high warp ids).
+// LAYOUT 2: 16 warps, word 0 on warp 11 alone in its SM sub-partition (warps 3, 7, 15 and 14 exit at once).
+template <int LAYOUT, int CH = 1>
+__global__ void __launch_bounds__(LAYOUT == 2 ? 512 : 384) leaf_sponge_w12_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                              uint32_t n_leaves, unsigned log_block,
+                                                              u64* __restrict__ digests) {
+  __shared__ __align__(16) u64 xch[2][24][32];
+  __shared__ __align__(16) u64 ysl[2][32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned wid;   // the state word this warp owns
+  if (LAYOUT == 0) wid = warp;
+  else if (LAYOUT == 1) wid = 11 - warp;
+  else {
+    if (((warp & 3) == 3 && warp != 11) || warp == 14) return;
+    wid = warp == 11 ? 0 : warp - (warp >> 2) + 1;
+  }
+  const uint32_t pos_raw = blockIdx.x * 32 + lane;
+  const bool live = pos_raw < n_leaves;
+  const uint32_t pos = live ? pos_raw : n_leaves - 1;
+  const u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  const u32 c_y0 = c_poseidon_circ[(12 - wid) % 12] + (wid == 0 ? 8u : 0u);   // coefficient of word 0 in row `wid`
+
+  u64 s = 0, nx = 0;
+  const uint32_t n_chunks = (leaf_len + 7) / 8;
+  if (wid < 8 && wid < leaf_len) nx = cols[(size_t)wid * n_leaves + pos];
+  unsigned xb = 0;
+
+  // twelve-term row: acc = rc(next round) + sum_i CIRC[i] * word(wid + i)
+  auto row_accumulate = [&](int rd, u32& al0, u32& al1, u32& ah0, u32& ah1) {
+    const u64 c = c_poseidon_rc[12 * (rd + 1) + wid];
+    u64 t[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) t[i] = xch[xb][wid + i][lane];
+    mds_row<CH>(t, [&](int i) { return CIRC[i]; }, c, 0, al0, al1, ah0, ah1);
+  };
+
+  for (uint32_t m = 0; m < n_chunks; m++) {
+    const unsigned take = min(8u, leaf_len - 8 * m);
+    if (wid < take) s = nx;
+    if (m + 1 < n_chunks) {
+      const uint32_t c = (m + 1) * 8 + wid;
+      if (wid < 8 && c < leaf_len) nx = cols[(size_t)c * n_leaves + pos];
+    }
+    s = gl_add_lazy_canon(s, c_poseidon_rc[wid]);
+
+    auto full_round = [&](int rd) {
+      const u64 v = poseidon_sbox(s);
+      xch[xb][wid][lane] = v; xch[xb][wid + 12][lane] = v;
+      named_bar_sync(1, 384);
+      u32 al0, al1, ah0, ah1;
+      row_accumulate(rd, al0, al1, ah0, ah1);
+      if (wid == 0) {   // DIAG[0] = 8
+        const u64 t = xch[xb][0][lane];
+        mac32(al0, al1, (u32)t, 8u); mac32(ah0, ah1, (u32)(t >> 32), 8u);
+      }
+      s = mds_recombine(al0, al1, ah0, ah1);
+      xb ^= 1;
+    };
+#pragma unroll 1
+    for (int rd = 0; rd < 4; rd++) full_round(rd);
+#pragma unroll 1
+    for (int rd = 4; rd < 26; rd++) {
+      u32 al0, al1, ah0, ah1;
+      u64 y0;
+      if (wid == 0) {
+        xch[xb][0][lane] = 0; xch[xb][12][lane] = 0;
+        const u64 x2 = gl_mul_lazy(s, s);                 // first S-box level runs before the others have published
+        named_bar_sync(1, 384);
+        row_accumulate(rd, al0, al1, ah0, ah1);           // interleaves with the rest of the S-box
+        const u64 x4 = gl_mul_lazy(x2, x2), x3 = gl_mul_lazy(x2, s);
+        y0 = gl_mul_lazy(x3, x4);
+        ysl[xb][lane] = y0;
+        named_bar_arrive(2, 384);
+      } else {
+        xch[xb][wid][lane] = s; xch[xb][wid + 12][lane] = s;
+        named_bar_sync(1, 384);
+        row_accumulate(rd, al0, al1, ah0, ah1);
+        named_bar_sync(2, 384);
+        y0 = ysl[xb][lane];
+      }
+      mac32(al0, al1, (u32)y0, c_y0);
+      mac32(ah0, ah1, (u32)(y0 >> 32), c_y0);
+      s = mds_recombine(al0, al1, ah0, ah1);
+      xb ^= 1;
+    }
+#pragma unroll 1
+    for (int rd = 26; rd < 30; rd++) full_round(rd);
+  }
+  if (live && wid < 4) digests[4ull * leaf_index_of(pos, log_block) + wid] = gl_canon(s);
+}

@@ -12,13 +12,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "poseidon.cuh"
-
-// position (coset-major, see ntt.cu) -> plonky2 leaf index:  J*n + k  ->  J*n + bitrev_n(k)
-__device__ __forceinline__ uint32_t leaf_index_of(uint32_t pos, unsigned log_block) {
-  uint32_t mask = (1u << log_block) - 1;
-  return (pos & ~mask) | bitrev32(pos & mask, log_block);
-}
+#include "leafhash.cuh"
 
 // One thread per leaf.  cols: [leaf_len][n_leaves].
 __global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
@@ -61,158 +55,23 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ 
   d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Cooperative leaf sponge: L lanes share one leaf's 12-word state (12/L words each).  A leaf is a strictly sequential
-// chain of ceil(C/8) permutations, so with only N = 2048..32768 leaves one thread per leaf leaves the machine idle
-// (and is latency-bound at ~31k dependent-ish instructions per permutation); splitting the state over lanes cuts the
-// chain latency ~L-fold.  Per round each lane applies constants + S-box to its own words, publishes them through a
-// double-buffered shared-memory exchange (one __syncwarp per round), reads back all 12 words with 128-bit loads and
-// forms its own MDS rows with per-lane rotated coefficient registers.  Input columns are staged through shared memory
-// by the whole block ([8 columns][leaves] tiles, coalesced along the leaf axis, prefetched one permutation ahead).
-// ---------------------------------------------------------------------------------------------------------
-template <int L>
-__global__ void __launch_bounds__(256) leaf_hash_coop_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
-                                                             uint32_t n_leaves, unsigned log_block,
-                                                             u64* __restrict__ digests) {
-  constexpr int G = (L == 12) ? 16 : L;   // lanes reserved per leaf
-  constexpr int W = 12 / L;               // state words per lane
-  constexpr int LPB = 256 / G;            // leaves per block
-  constexpr int EPT = (8 * LPB + 255) / 256;
-  __shared__ __align__(16) u64 tile[2][8][LPB];
-  __shared__ __align__(16) u64 xch[2][LPB][12];
-  __shared__ u64 rc[POSEIDON_RC_COUNT];
-  const unsigned tid = threadIdx.x;
-  const unsigned g = tid / G, r = tid % G;
-  const bool active = r < (unsigned)L;
-  const unsigned w0 = r * W;
-  const uint32_t pos0 = blockIdx.x * LPB;
-  for (unsigned i = tid; i < POSEIDON_RC_COUNT; i += 256) rc[i] = c_poseidon_rc[i];
-
-  // rotated MDS coefficients of this lane's rows: out[row] = sum_j CIRC[(j - row) mod 12] * t[j] (+ 8 t[0] on row 0)
-  const u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  u32 coef[W][12];
-#pragma unroll
-  for (int k = 0; k < W; k++)
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-      unsigned row = (w0 + k) % 12;
-      u32 c = 0;
-#pragma unroll
-      for (int i = 0; i < 12; i++) c = ((j + 12 - row) % 12 == (unsigned)i) ? CIRC[i] : c;
-      coef[k][j] = c + ((row == 0 && j == 0) ? 8u : 0u);
-    }
-
-  u64 s[W];
-#pragma unroll
-  for (int k = 0; k < W; k++) s[k] = 0;
-
-  const uint32_t n_chunks = (leaf_len + 7) / 8;
-  // stage chunk 0
-  u64 pre[EPT];
-  auto fetch = [&](uint32_t chunk) {
-#pragma unroll
-    for (int q = 0; q < EPT; q++) {
-      unsigned e = tid + q * 256;
-      unsigned col = e / LPB, leaf = e % LPB;
-      uint32_t c = chunk * 8 + col, pos = pos0 + leaf;
-      pre[q] = (e < 8 * LPB && c < leaf_len && pos < n_leaves) ? cols[(size_t)c * n_leaves + pos] : 0;
-    }
-  };
-  auto stash = [&](unsigned buf) {
-#pragma unroll
-    for (int q = 0; q < EPT; q++) {
-      unsigned e = tid + q * 256;
-      if (e < 8 * LPB) tile[buf][e / LPB][e % LPB] = pre[q];
-    }
-  };
-  fetch(0);
-  stash(0);
-  unsigned xb = 0;
-  for (uint32_t m = 0; m < n_chunks; m++) {
-    __syncthreads();
-    const unsigned take = min(8u, leaf_len - 8 * m);
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < W; k++)
-        if (w0 + k < take) s[k] = tile[m & 1][w0 + k][g];
-    }
-    if (m + 1 < n_chunks) fetch(m + 1);
-    // ---- one permutation: 4 full, 22 partial, 4 full rounds ----
-    auto linear_layer = [&]() {
-      __syncwarp();
-      if (active) {
-        u32 lo[12], hi[12];
-        const ulonglong2* src = (const ulonglong2*)&xch[xb][g][0];
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          ulonglong2 v = src[j];
-          lo[2 * j] = (u32)v.x; hi[2 * j] = (u32)(v.x >> 32);
-          lo[2 * j + 1] = (u32)v.y; hi[2 * j + 1] = (u32)(v.y >> 32);
-        }
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-          u64 al = 0, ah = 0;
-#pragma unroll
-          for (int j = 0; j < 12; j++) {
-            al += (u64)coef[k][j] * lo[j];
-            ah += (u64)coef[k][j] * hi[j];
-          }
-          u64 c = (ah >> 32) * GL_EPS, b = (ah & GL_EPS) << 32, t = al + c, v = b + t;
-          if (v < t) v += GL_EPS;
-          s[k] = v;
-        }
-      }
-      xb ^= 1;
-    };
-    auto full_round = [&](int rd) {
-      if (active) {
-#pragma unroll
-        for (int k = 0; k < W; k++) xch[xb][g][w0 + k] = poseidon_sbox(gl_add_lazy_canon(s[k], rc[12 * rd + w0 + k]));
-      }
-      linear_layer();
-    };
-#pragma unroll 1
-    for (int rd = 0; rd < 4; rd++) full_round(rd);
-#pragma unroll 1
-    for (int rd = 4; rd < 26; rd++) {
-      if (active) {
-        u64 v0 = gl_add_lazy_canon(s[0], rc[12 * rd + w0]);
-        if (w0 == 0) v0 = poseidon_sbox(v0);       // only the lane holding word 0
-        xch[xb][g][w0] = v0;
-#pragma unroll
-        for (int k = 1; k < W; k++) xch[xb][g][w0 + k] = gl_add_lazy_canon(s[k], rc[12 * rd + w0 + k]);
-      }
-      linear_layer();
-    }
-#pragma unroll 1
-    for (int rd = 26; rd < 30; rd++) full_round(rd);
-    if (m + 1 < n_chunks) stash((m + 1) & 1);
-  }
-  // digest = state words 0..3, canonical, scattered to plonky2's leaf index
-  const uint32_t pos = pos0 + g;
-  if (active && pos < n_leaves) {
-    u64* d = digests + 4ull * leaf_index_of(pos, log_block);
-#pragma unroll
-    for (int k = 0; k < W; k++)
-      if (w0 + k < 4) d[w0 + k] = gl_canon(s[k]);
-  }
-}
-
 void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, uint32_t n_leaves, unsigned log_block,
                            u64* d_digests) {
   const uint32_t perms = (leaf_len + 7) / 8;
-  // lanes per leaf: enough threads to fill the machine, but never wider than the chain needs.
-  // SB_LEAF_LANES=1|4|12 overrides the choice (profiling).
-  int lanes = 1;
-  if (leaf_len > 4 && perms >= 8) {
-    if ((uint64_t)n_leaves * 12 <= (uint64_t)ctx->sm_count * 512) lanes = 12;
-    else if ((uint64_t)n_leaves * 4 <= (uint64_t)ctx->sm_count * 1024) lanes = 4;
-  }
-  if (const char* e = getenv("SB_LEAF_LANES")) { int v = atoi(e); if (v == 1 || v == 4 || v == 12) lanes = v; }
-  if (lanes == 12) {
-    LAUNCH(ctx, leaf_hash_coop_kernel<12>, (n_leaves + 15) / 16, 256, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
-  } else if (lanes == 4) {
-    LAUNCH(ctx, leaf_hash_coop_kernel<4>, (n_leaves + 63) / 64, 256, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+  // Kernel choice (leafhash.cuh; measured on B200 with tools/perf/poseidon_lab.cu):
+  //   short chains (quotient / FRI leaves, <= 2 permutations): one thread per leaf, nothing to split;
+  //   few leaves (<= 2 groups of 32 per SM: PairingPrecomp 4096, MillerLoop 2048): every leaf is in flight at once and
+  //     wall time = chain length x latency of one permutation  ->  one state word per warp, two-barrier partial rounds;
+  //   many leaves (FinalExp / ECCAgg 32768): throughput-bound  ->  three words per thread, four warps per 32 leaves.
+  // SB_LEAF_KERNEL=1|4|12 overrides the choice (profiling).
+  int kind = 1;
+  if (leaf_len > 4 && perms > 2) kind = ((uint64_t)n_leaves <= 64ull * ctx->sm_count) ? 12 : 4;
+  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 4 || v == 12) && leaf_len > 4)) kind = v; }
+  const uint32_t groups = (n_leaves + 31) / 32;
+  if (kind == 12) {
+    LAUNCH(ctx, (leaf_sponge_w12_kernel<0, 1>), groups, 384, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+  } else if (kind == 4) {
+    LAUNCH(ctx, leaf_sponge_ws_kernel<4>, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else {
     unsigned block = n_leaves >= 128 * (unsigned)ctx->sm_count ? 128 : (n_leaves >= 64 * (unsigned)ctx->sm_count ? 64 : 32);
     LAUNCH(ctx, leaf_hash_kernel, (n_leaves + block - 1) / block, block, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);

@@ -54,6 +54,22 @@ def test_hash_leaves_ragged_lengths(ctx, leaf_len):
         assert np.array_equal(got[i], O.hash_or_noop(cols[:, i])), (leaf_len, i)
 
 
+@pytest.mark.parametrize("kernel", [1, 4, 12])
+@pytest.mark.parametrize("leaf_len,count", [(5, 33), (8, 64), (17, 1000), (24, 32), (135, 100), (1001, 70)])
+def test_hash_leaves_every_kernel_variant(ctx, monkeypatch, kernel, leaf_len, count):
+    """The three leaf-sponge kernels (one thread per leaf / 3 words per thread / 1 word per warp) are bit-identical
+    to hash_or_noop on ragged chain lengths and leaf counts that are not multiples of the 32-leaf group."""
+    monkeypatch.setenv("SB_LEAF_KERNEL", str(kernel))
+    rng = np.random.default_rng(100 * leaf_len + count)
+    cols = (rng.integers(0, 1 << 63, (leaf_len, count), dtype=np.uint64) * np.uint64(2)
+            + rng.integers(0, 2, (leaf_len, count), dtype=np.uint64)) % np.uint64(P)
+    cols[:, 0] = P - 1
+    cols[:, -1] = 0
+    got = ctx.hash_leaves(cols)
+    for i in list(range(0, count, 7)) + [count - 1]:
+        assert np.array_equal(got[i], O.hash_or_noop(cols[:, i])), (kernel, leaf_len, i)
+
+
 @pytest.mark.parametrize("log_n,n_cols,rate_bits,full", [
     (4, 8, 1, False), (4, 61, 1, True), (5, 3, 2, True), (6, 37, 1, False), (7, 20, 2, True),
     (10, 19, 1, False), (10, 11, 2, True), (13, 3, 2, True), (3, 300, 3, False)])
