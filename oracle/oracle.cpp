@@ -1,6 +1,10 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  C entry points (ctypes) over the CPU restatement in gl.h / hash.h /
 // poly.h / air.h / prover.h.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load this library; the product (starky_bls12_381_b200/) never does.
+// PARITY UNPINNED at proof-byte level: the reference's prove() lives in un-vendored Rust git dependencies (plonky2 @
+// 666f315) and cannot be built here; this restatement follows SURVEY.md Appendix A.  Pinned: Poseidon-12 (plonky2's
+// published KATs), Goldilocks constants, the five starks' constraint counts / fingerprints (tests/test_oracle_kat.py,
+// tests/test_air_programs.py, tests/golden/).
 #include "prover.h"
 #include <map>
 #include <memory>

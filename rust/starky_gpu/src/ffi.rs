@@ -1,0 +1,55 @@
+//! `extern "C"` block for include/starky_b200.h (field-for-field; keep in sync with the header).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const SB_OK: c_int = 0;
+pub const SB_EQUOTIENT_NOT_DIVISIBLE: c_int = -4;
+pub const SB_EZETA_IN_SUBGROUP: c_int = -5;
+
+pub const SB_TRACE_COLS_U64_PTRS: c_int = 1;
+pub const SB_TRACE_ROWMAJOR_U64: c_int = 2;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct sb_params {
+    pub stark_id: u32, pub log_n: u32, pub n_cols: u32, pub n_public_inputs: u32, pub constraint_degree: u32,
+    pub rate_bits: u32, pub cap_height: u32, pub num_challenges: u32, pub pow_bits: u32, pub num_query_rounds: u32,
+    pub fri_arity_bits: u32, pub fri_final_poly_bits: u32, pub flags: u32, pub reserved: u32,
+    pub fixed_pow_witness: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct sb_proof_layout {
+    pub log_n: u32, pub log_lde: u32, pub n_cols: u32, pub n_quotient_polys: u32, pub n_public_inputs: u32,
+    pub cap_len: u32, pub n_fri_rounds: u32, pub final_poly_len: u32, pub n_queries: u32, pub arity_bits: u32,
+    pub trace_path_len: u32, pub reserved: u32,
+    pub off_trace_cap: u64, pub off_quotient_cap: u64, pub off_local_values: u64, pub off_next_values: u64,
+    pub off_quotient_polys: u64, pub off_fri_caps: u64, pub off_final_poly: u64, pub off_pow_witness: u64,
+    pub off_queries: u64, pub query_stride: u64, pub q_off_trace_leaf: u64, pub q_off_trace_path: u64,
+    pub q_off_quot_leaf: u64, pub q_off_quot_path: u64, pub q_off_steps: u64, pub off_public_inputs: u64,
+    pub total_words: u64,
+}
+
+#[repr(C)]
+pub struct sb_proof {
+    pub layout: sb_proof_layout,
+    pub words: *mut u64,
+    pub ms_h2d: f32, pub ms_trace_commit: f32, pub ms_quotient: f32, pub ms_quotient_commit: f32,
+    pub ms_openings: f32, pub ms_fri: f32, pub ms_d2h: f32, pub ms_total: f32,
+}
+
+#[repr(C)]
+pub struct sb_ctx { _private: [u8; 0] }
+
+extern "C" {
+    pub fn sb_init(devices: *const c_int, n_devices: c_int, out: *mut *mut sb_ctx) -> c_int;
+    pub fn sb_destroy(ctx: *mut sb_ctx);
+    pub fn sb_last_error(ctx: *mut sb_ctx) -> *const c_char;
+    pub fn sb_params_standard(stark_id: u32, log_n: u32, out: *mut sb_params) -> c_int;
+    pub fn sb_prove(ctx: *mut sb_ctx, p: *const sb_params, trace: *const c_void, layout: c_int,
+                    public_inputs: *const u64, out: *mut *mut sb_proof) -> c_int;
+    pub fn sb_proof_free(proof: *mut sb_proof);
+    pub fn sb_fri_step_path_len(l: *const sb_proof_layout, round: u32) -> u32;
+    pub fn sb_fri_step_offset(l: *const sb_proof_layout, round: u32) -> u64;
+}
