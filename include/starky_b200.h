@@ -155,6 +155,23 @@ int sb_poseidon_permute_batch(sb_ctx* ctx, uint64_t* states, uint32_t count);
 /* hash_or_noop of `count` leaves of `leaf_len` elements: leaves given column-major [leaf_len][count]. */
 int sb_hash_leaves(sb_ctx* ctx, const uint64_t* cols, uint32_t leaf_len, uint32_t count, uint64_t* digests_out);
 
+/* Coefficients of the last committed trace, [n_cols][n] in bit-reversed coefficient order (parity tests). */
+int sb_coeffs_download(sb_ctx* ctx, uint64_t* coeffs_out);
+
+/* ---- multi-GPU stage entry points.  Device pointers in and out, work is queued on the ctx
+ *      stream; the exchange between them -- an all-to-all of LDE slabs, an all-gather of 32-byte digests -- is done by
+ *      the host with NCCL (torch.distributed in the harness, ncclSend/ncclRecv in a Rust/C++ host).
+ *      Phase 1, column-sharded: rank g runs K1 on its column slice and writes the LDE as n_row_blocks slabs
+ *        d_lde_out[b][c][N / n_row_blocks], slab b = the positions rank b will hash (replaces the per-column
+ *        ifft/lde/coset_fft of PolynomialBatch::from_values; aggregate_proof.rs:59,105,138,169,212).
+ *      Phase 2, row-sharded: after the all-to-all rank g holds [n_cols][N / G] and hashes its leaves (K2); the
+ *        position-ordered digests of all ranks are gathered and the tree is built to the cap (K3). ---- */
+int sb_lde_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_trace, uint32_t n_cols_local,
+                       uint32_t n_row_blocks, uint64_t* d_coeffs_out /* optional */, uint64_t* d_lde_out);
+int sb_hash_rows_device(sb_ctx* ctx, const uint64_t* d_cols, uint32_t leaf_len, uint32_t n_leaves, uint64_t* d_digests);
+int sb_merkle_from_position_digests(sb_ctx* ctx, const sb_params* p, const uint64_t* d_digests_pos, uint64_t* cap_out);
+int sb_synchronize(sb_ctx* ctx);
+
 /* ---- device-resident benchmarking hooks (bench.py `value` leg: inputs already in HBM) ---- */
 /* Upload a trace once; subsequent sb_prove(..., trace=NULL, layout=SB_TRACE_DEVICE_COLMAJOR_U64) re-uses it. */
 int sb_trace_upload(sb_ctx* ctx, const sb_params* p, const void* trace, int layout);

@@ -94,6 +94,10 @@ def lib():
         L.sb_stage_ms.argtypes = [C.c_void_p, C.c_char_p]
         L.sb_stage_ms.restype = C.c_float
         L.sb_measure_imad_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.sb_synchronize.argtypes = [C.c_void_p]
+        L.sb_lde_cols_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.sb_hash_rows_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.sb_merkle_from_position_digests.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -213,6 +217,9 @@ class Context:
         pis = _u64(public_inputs)
         self._check(lib().sb_prove(self._h, C.byref(p), _ptr(trace), layout, _ptr(pis), C.byref(out)))
         return Proof(out)
+
+    def synchronize(self):
+        self._check(lib().sb_synchronize(self._h))
 
     def kernel_launches(self):
         return int(lib().sb_kernel_launches(self._h))

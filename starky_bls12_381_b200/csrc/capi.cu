@@ -240,6 +240,64 @@ int sb_coeffs_download(sb_ctx* ctx, uint64_t* coeffs_out) {
   SB_CATCH(ctx)
 }
 
+// ---- multi-GPU stage entry points: device pointers in and out; the host does the exchange with NCCL ----
+int sb_synchronize(sb_ctx* ctx) {
+  if (!ctx) return SB_EINVAL;
+  SB_TRY(ctx)
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  stage_collect(ctx);
+  return SB_OK;
+  SB_CATCH(ctx)
+}
+
+int sb_lde_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_trace, uint32_t n_cols_local, uint32_t n_row_blocks,
+                       uint64_t* d_coeffs_out, uint64_t* d_lde_out) {
+  if (!ctx || !d_trace || !d_lde_out) return SB_EINVAL;
+  SB_TRY(ctx)
+  check_params(p);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  unsigned log_blocks = ilog2(n_row_blocks);
+  if (n_row_blocks == 0 || (1u << log_blocks) != n_row_blocks || p->log_n + p->rate_bits < log_blocks + 5)
+    SB_THROW(SB_EINVAL, "n_row_blocks %u must be a power of two leaving >= 32 positions per block", n_row_blocks);
+  if (n_cols_local == 0) return SB_OK;
+  stage_begin(ctx, "lde");
+  sb_lde_trace(ctx, d_trace, d_coeffs_out, d_lde_out, n_cols_local, p->log_n, p->rate_bits, log_blocks);
+  stage_end(ctx, "lde");
+  return SB_OK;
+  SB_CATCH(ctx)
+}
+
+int sb_hash_rows_device(sb_ctx* ctx, const uint64_t* d_cols, uint32_t leaf_len, uint32_t n_leaves, uint64_t* d_digests) {
+  if (!ctx || !d_cols || !d_digests || !leaf_len || !n_leaves) return SB_EINVAL;
+  SB_TRY(ctx)
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  stage_begin(ctx, "leaf_hash");
+  sb_hash_leaves_device(ctx, d_cols, leaf_len, n_leaves, 0, d_digests);   // log_block 0: digests stay in position order
+  stage_end(ctx, "leaf_hash");
+  return SB_OK;
+  SB_CATCH(ctx)
+}
+
+int sb_merkle_from_position_digests(sb_ctx* ctx, const sb_params* p, const uint64_t* d_digests_pos, uint64_t* cap_out) {
+  if (!ctx || !d_digests_pos || !cap_out) return SB_EINVAL;
+  SB_TRY(ctx)
+  check_params(p);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  const size_t N = size_t(1) << (p->log_n + p->rate_bits);
+  ctx->tree.ensure(32 * 2 * N);
+  stage_begin(ctx, "merkle");
+  sb_digests_to_leaf_order(ctx, d_digests_pos, ctx->tree.as<u64>(), (uint32_t)N, p->log_n);
+  sb_merkle_levels(ctx, ctx->tree.as<u64>(), (uint32_t)N, p->cap_height);
+  stage_end(ctx, "merkle");
+  CUDA_CHECK(cudaMemcpyAsync(cap_out, tree_cap_ptr(ctx->tree.as<u64>(), N, p->cap_height), 32ull << p->cap_height,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  stage_collect(ctx);
+  return SB_OK;
+  SB_CATCH(ctx)
+}
+
 int sb_ntt_batch(sb_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t count, int inverse) {
   if (!ctx || !data) return SB_EINVAL;
   SB_TRY(ctx)

@@ -115,10 +115,12 @@ static inline unsigned ilog2(uint64_t x) { unsigned b = 0; while ((uint64_t(1) <
 
 // ---- stage functions implemented across the .cu files ----
 // ntt.cu
-void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, uint32_t n_cols, unsigned log_n, unsigned rate_bits);
+void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, uint32_t n_cols, unsigned log_n, unsigned rate_bits,
+                  unsigned log_row_blocks = 0);
 void sb_ntt_device(sb_ctx* ctx, u64* d_data, unsigned log_size, uint32_t count, bool inverse, bool dif);
 void sb_transpose_rows_to_cols(sb_ctx* ctx, const void* d_rows, u64* d_cols, uint32_t n_rows, uint32_t n_cols, bool is_u32);
 // merkle.cu
 void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, uint32_t n_leaves, unsigned log_block, u64* d_digests);
 void sb_merkle_levels(sb_ctx* ctx, u64* d_tree, uint32_t n_leaves, unsigned cap_height);
 void sb_poseidon_permute_device(sb_ctx* ctx, u64* d_states, uint32_t count);
+void sb_digests_to_leaf_order(sb_ctx* ctx, const u64* d_pos_order, u64* d_leaf_order, uint32_t n_leaves, unsigned log_block);

@@ -103,6 +103,20 @@ void sb_merkle_levels(sb_ctx* ctx, u64* d_tree, uint32_t n_leaves, unsigned cap_
   }
 }
 
+// digests in device position order -> plonky2 leaf order (row-sharded leaf hashing gathers position-ordered digests)
+__global__ void digests_to_leaf_order_kernel(const ulonglong2* __restrict__ in, ulonglong2* __restrict__ out, uint32_t n_leaves,
+                                             unsigned log_block) {
+  uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_leaves) return;
+  const size_t d = leaf_index_of(pos, log_block);
+  out[2 * d] = in[2 * (size_t)pos];
+  out[2 * d + 1] = in[2 * (size_t)pos + 1];
+}
+void sb_digests_to_leaf_order(sb_ctx* ctx, const u64* d_pos_order, u64* d_leaf_order, uint32_t n_leaves, unsigned log_block) {
+  LAUNCH(ctx, digests_to_leaf_order_kernel, (n_leaves + 127) / 128, 128, 0, (const ulonglong2*)d_pos_order, (ulonglong2*)d_leaf_order,
+         n_leaves, log_block);
+}
+
 __global__ void permute_kernel(u64* states, uint32_t count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;

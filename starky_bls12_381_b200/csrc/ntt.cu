@@ -112,11 +112,10 @@ template <int EPT>
 __global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* __restrict__ values, u64* __restrict__ coeffs, u64* __restrict__ lde,
                            uint32_t n_cols, unsigned log_n, unsigned rate_bits, unsigned cpb,
                            const u64* __restrict__ tw_fwd, const u64* __restrict__ tw_inv,
-                           const u64* __restrict__ scale, u64 n_inv) {
+                           const u64* __restrict__ scale, u64 n_inv, unsigned log_rb) {
   extern __shared__ u64 buf[];
   const unsigned T = blockDim.x;
   const uint32_t n = 1u << log_n;
-  const size_t N = (size_t)n << rate_bits;
   const uint32_t col0 = blockIdx.x * cpb;
   u64 c[EPT];
 #pragma unroll
@@ -143,7 +142,10 @@ __global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* _
     for (int m = 0; m < EPT; m++) {
       unsigned e = threadIdx.x + m * T;
       uint32_t col = col0 + (e >> log_n);
-      if (col < n_cols) lde[(size_t)col * N + ((size_t)J << log_n) + (e & (n - 1))] = buf[e];
+      // output order [row block][column][position in block], blocks of 2^log_rb positions: one block (log_rb = log N) is
+      // the plain column-major [C][N]; G blocks make every destination rank's slab contiguous for the all-to-all (8e)
+      const size_t pos = ((size_t)J << log_n) + (e & (n - 1));
+      if (col < n_cols) lde[((((pos >> log_rb) * n_cols) + col) << log_rb) + (pos & (((size_t)1 << log_rb) - 1))] = buf[e];
     }
   }
   if (coeffs) {
@@ -158,7 +160,8 @@ __global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* _
 }
 
 void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, uint32_t n_cols, unsigned log_n,
-                  unsigned rate_bits) {
+                  unsigned rate_bits, unsigned log_row_blocks) {
+  const unsigned log_rb = log_n + rate_bits - log_row_blocks;
   if (log_n < 1 || log_n > 13) SB_THROW(SB_EINVAL, "trace height 2^%u unsupported (1 <= log_n <= 13)", log_n);
   const Twiddles& tw = sb_twiddles(ctx, log_n);
   const u64* scale = coset_scale(ctx, log_n, rate_bits);
@@ -173,11 +176,11 @@ void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, u
   if (ept == 8) {
     CUDA_CHECK(cudaFuncSetAttribute(lde_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH(ctx, lde_kernel<8>, grid, T, smem, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits, cpb,
-           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n));
+           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb);
   } else {
     CUDA_CHECK(cudaFuncSetAttribute(lde_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH(ctx, lde_kernel<4>, grid, T, smem, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits, cpb,
-           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n));
+           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb);
   }
 }
 

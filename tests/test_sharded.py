@@ -1,0 +1,103 @@
+"""Multi-GPU trace commitment: the shard plan, the column-sharded -> all-to-all -> row-sharded flow under a
+real world_size-2/4 gloo process group on CPU (kernels replaced by the oracle double), and -- on the B200 -- the CUDA
+stage kernels driven through the same plan with the ranks emulated on one GPU."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as O
+import starky_bls12_381_b200 as sb
+from helpers import P, random_trace
+from starky_bls12_381_b200.sharded import commit_sharded, shard_plan
+
+
+def test_shard_plan_ragged_and_limits():
+    pl = shard_plan(97330, 10, 1, 8)           # MillerLoop on 8 GPUs
+    assert sum(pl.col_count) == 97330 and pl.col_count == (12167, 12167) + (12166,) * 6
+    assert pl.col_start[0] == 0 and all(pl.col_start[g + 1] == pl.col_start[g] + pl.col_count[g] for g in range(7))
+    assert pl.rows_per_rank == 256 and pl.n_lde == 2048
+    assert pl.send_splits(0) == [12167 * 256] * 8 and pl.recv_splits(3) == [c * 256 for c in pl.col_count]
+    # what one rank sends is what the others expect from it
+    for g in range(8):
+        for h in range(8):
+            assert pl.send_splits(g)[h] == pl.recv_splits(h)[g]
+    assert pl.a2a_bytes_out(2) == 8 * 12166 * 256 * 7
+    fe = shard_plan(73527, 13, 2, 4)           # FinalExp on 4 GPUs: LDE bytes x 3/4 cross the fabric
+    assert sum(fe.a2a_bytes_out(g) for g in range(4)) == 8 * 73527 * 32768 * 3 // 4
+    assert shard_plan(5, 4, 1, 1).col_count == (5,)
+    with pytest.raises(ValueError):
+        shard_plan(100, 4, 1, 3)               # row blocks are power-of-two slices
+    with pytest.raises(ValueError):
+        shard_plan(100, 4, 1, 2 ** 4)          # < 32 positions per rank
+
+
+def _worker(rank, world, init_file, n_cols, log_n, rate_bits, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from sharded_double import OracleBackend
+    dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
+    try:
+        trace = random_trace(np.random.default_rng(4242), n_cols, log_n, full_width=True)     # same seed on every rank
+        plan = shard_plan(n_cols, log_n, rate_bits, world)
+        c0, cg = plan.col_start[rank], plan.col_count[rank]
+        out = commit_sharded(OracleBackend(), plan, rank, trace[c0:c0 + cg])
+        q.put((rank, out["cap"], out["digests"].numpy().view(np.uint64).copy(), out["rows"].numpy().view(np.uint64).copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_cols,log_n,rate_bits", [(2, 13, 5, 1), (4, 9, 5, 2), (2, 3, 6, 1)])
+def test_sharded_commit_over_gloo_matches_single_process_oracle(world, n_cols, log_n, rate_bits):
+    from helpers import pos_to_leaf
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        init_file = os.path.join(d, "rendezvous")
+        procs = [ctx.Process(target=_worker, args=(r, world, init_file, n_cols, log_n, rate_bits, q)) for r in range(world)]
+        for pr in procs:
+            pr.start()
+        results = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+        for pr in procs:
+            pr.join(timeout=60)
+            assert pr.exitcode == 0
+    trace = random_trace(np.random.default_rng(4242), n_cols, log_n, full_width=True)
+    want = O.lde_commit(O.make_params(log_n=log_n, n_cols=n_cols, rate_bits=rate_bits), trace)
+    perm = pos_to_leaf(log_n, rate_bits)
+    lde_pos = want["leaves"][perm].T                                   # [C][N] in device position order
+    rb = (1 << (log_n + rate_bits)) // world
+    for rank, cap, digests, rows in results:
+        assert np.array_equal(cap, want["cap"])                        # every rank ends with the reference's cap
+        assert np.array_equal(digests, want["digests"][perm])          # gathered digests, position order
+        assert np.array_equal(rows, lde_pos[:, rank * rb:(rank + 1) * rb])   # its row block holds ALL columns, in order
+
+
+# ---------------------------------------------------------------- CUDA stage kernels, ranks emulated on one GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n_cols,log_n,rate_bits", [(1, 20, 6, 1), (2, 37, 6, 1), (4, 45, 7, 2), (8, 203, 10, 2)])
+def test_gpu_sharded_stage_kernels_match_unsharded_commit(world, n_cols, log_n, rate_bits):
+    from starky_bls12_381_b200.sharded import GpuBackend
+    ctx = sb.Context(0)
+    try:
+        p = sb.Params(sb.StarkId.CUSTOM, log_n, n_cols, 0, 3, rate_bits, 4, 2, 16, 84, 4, 5, 0, 0, 0)
+        trace = random_trace(np.random.default_rng(77), n_cols, log_n, full_width=True)
+        base = ctx.lde_commit(p, trace)                                 # the single-GPU path (itself checked against the oracle)
+        plan = shard_plan(n_cols, log_n, rate_bits, world)
+        be = GpuBackend(ctx, p)
+        slabs = [be.lde_cols(plan, g, trace[plan.col_start[g]:plan.col_start[g] + plan.col_count[g]]) for g in range(world)]
+        rb = plan.rows_per_rank
+        digs = []
+        for h in range(world):                                          # what the all-to-all delivers to rank h
+            parts = [slabs[g].view(world, plan.col_count[g], rb)[h].reshape(-1) for g in range(world)]
+            rows = torch.cat(parts).view(n_cols, rb)
+            assert np.array_equal(rows.cpu().numpy().view(np.uint64), base["lde"][:, h * rb:(h + 1) * rb])
+            digs.append(be.hash_rows(plan, rows.contiguous()))
+        cap = be.merkle_cap(plan, torch.cat(digs, dim=0))
+        assert np.array_equal(cap, base["cap"])
+    finally:
+        ctx.close()
