@@ -90,6 +90,37 @@ GL_HD u64 gl_mul_lazy(u64 a, u64 b) {
   return gl_reduce128_lazy(lo, hi);
 #endif
 }
+// a * b + c for any u64 a, b, c -> lazy.  The addend joins the 128-bit product before the fold (no carry out:
+// (2^64-1)^2 + 2^64-1 < 2^128), so a multiply-add costs four instructions more than a multiply.
+GL_HD u64 gl_mad_lazy(u64 a, u64 b, u64 c) {
+#if defined(__CUDA_ARCH__)
+  u64 lo = a * b, hi = __umul64hi(a, b);
+  lo += c;
+  hi += (lo < c);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 nc, nb;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"
+      "subc.u32 %1, %4, 0;\n\t"
+      "add.cc.u32 %1, %1, %3;\n\t"
+      "addc.u32 nc, 0, 0;\n\t"
+      "neg.s32 nc, nc;\n\t"
+      "sub.cc.u32 %0, %0, %5;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 nb, 0, 0;\n\t"
+      "add.cc.u32 %0, %0, nc;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "sub.cc.u32 %0, %0, nb;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+  return ((u64)r1 << 32) | r0;
+#else
+  unsigned __int128 m = (unsigned __int128)a * b + c;
+  return gl_reduce128_lazy((u64)m, (u64)(m >> 64));
+#endif
+}
 // any x any -> canonical
 GL_HD u64 gl_mul(u64 a, u64 b) { return gl_canon(gl_mul_lazy(a, b)); }
 GL_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }

@@ -248,3 +248,204 @@ __global__ void __launch_bounds__(LAYOUT == 2 ? 512 : 384) leaf_sponge_w12_kerne
   }
   if (live && wid < 4) digests[4ull * leaf_index_of(pos, log_block) + wid] = gl_canon(s);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Sparse partial rounds (poseidon_fast.h, derived by tools/gen_poseidon_fast.py from MDS + round constants; the
+// factorisation plonky2 ships as FAST_PARTIAL_*).  In the kernel above a partial round is an all-to-all through shared
+// memory (144 LDS.64 per 32-leaf group and round, 40 % of the LSU pipe) and costs ~700 cycles.  In sparse form a partial
+// round is   y = x0^7 + a_r;   x0' = 25 y + sum_i w^_r[i] x_i;   x_i' = x_i + v_r[i] y   -- one broadcast of y and one
+// reduction, and with  sum_i w^_r[i] x_i(r) = sum_i w^_r[i] x_i(r-1) + U[r] y(r-1)  the reduction is known a round ahead,
+// so the warp that owns word 0 never waits for the others:
+//   13 warps per 32 leaves.  warps 0..11 own one word each (word = (warp + 9) % 12, so word 0 sits on warp 3), warp 12
+//   ("R") reduces.  Round r, slot q = r % 3 (triple-buffered slots and barrier ids: every reuse is ordered by a chain of
+//   barrier completions):
+//     word 0 : y = x0^7 + a_r -> ybuf[q]; wait F_q; arrive B_q and Y_q; x0 = 25 y + Ebuf[q]
+//     word i : wait B_q; x_i += v_r[i] y; e = w^_{r+2}[i] x_i -> ebuf[(r+2) % 3][i]; arrive G_{(r+2) % 3}
+//     R      : wait G_q; s = sum_i ebuf[q][i]; wait Y_{(r-1) % 3}; Ebuf[q] = s + U[r] y(r-1) (as two half sums); arrive F_q
+//   (letting word 0's warp multiply U[r] y(r-1) itself removes R from its loop but measured slower: that warp is
+//   issue-bound, 21 more instructions cost more than the wait)
+//   The dense 11x11 "initial" matrix of the sparse form is folded into the linear layer of full round 3 (D3ROT, K3).
+// Barrier ids: A = 1 (full rounds, 12 warps), B = 2..4, G = 5..7, F = 8..10, Y = 11..13.
+// ---------------------------------------------------------------------------------------------------------
+#include <type_traits>
+
+#include "poseidon_fast.h"
+static __constant__ u64 c_fast_post[22] = POSEIDON_FAST_POST;
+static __constant__ u64 c_fast_what[22 * 11] = POSEIDON_FAST_WHAT;
+static __constant__ u64 c_fast_vs[22 * 11] = POSEIDON_FAST_VS;
+static __constant__ u64 c_fast_d3rot[12 * 12] = POSEIDON_FAST_D3ROT;
+static __constant__ u64 c_fast_k3[12] = POSEIDON_FAST_K3;
+static __constant__ u64 c_fast_u[22] = POSEIDON_FAST_U;
+static __constant__ u64 c_fast_first[12] = POSEIDON_FAST_FIRST;
+
+__global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                             uint32_t n_leaves, unsigned log_block,
+                                                             u64* __restrict__ digests) {
+  __shared__ __align__(16) u64 xch[2][24][32];
+  __shared__ __align__(16) u64 ybuf[3][32];
+  __shared__ __align__(16) u64 ebuf[3][12][32];
+  __shared__ __align__(16) u64 Ebuf[3][64];   // per lane: (sum of low halves, sum of high halves)
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool reducer = warp == 12;
+  const unsigned wid = reducer ? 0 : (warp + 9) % 12;      // the state word this warp owns
+  const bool crit = !reducer && wid == 0;
+  const uint32_t pos_raw = blockIdx.x * 32 + lane;
+  const bool live = pos_raw < n_leaves;
+  const uint32_t pos = live ? pos_raw : n_leaves - 1;
+  const u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+
+  u64 s = 0, nx = 0;
+  const uint32_t n_chunks = (leaf_len + 7) / 8;
+  if (!reducer && wid < 8 && wid < leaf_len) nx = cols[(size_t)wid * n_leaves + pos];
+  unsigned xb = 0;
+
+  for (uint32_t m = 0; m < n_chunks; m++) {
+    if (!reducer) {
+      const unsigned take = min(8u, leaf_len - 8 * m);
+      if (wid < take) s = nx;
+      if (m + 1 < n_chunks) {
+        const uint32_t c = (m + 1) * 8 + wid;
+        if (wid < 8 && c < leaf_len) nx = cols[(size_t)c * n_leaves + pos];
+      }
+      s = gl_add_lazy_canon(s, c_poseidon_rc[wid]);
+
+      // full round rd: publish x^7, read the twelve words rotated, small-coefficient MDS row + constant `next`
+      auto full_round = [&](u64 next) {
+        const u64 v = poseidon_sbox(s);
+        xch[xb][wid][lane] = v; xch[xb][wid + 12][lane] = v;
+        named_bar_sync(1, 384);
+        u64 t[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) t[i] = xch[xb][wid + i][lane];
+        u32 al0, al1, ah0, ah1;
+        mds_row<1>(t, [&](int i) { return CIRC[i]; }, next, 0, al0, al1, ah0, ah1);
+        if (wid == 0) { mac32(al0, al1, (u32)t[0], 8u); mac32(ah0, ah1, (u32)(t[0] >> 32), 8u); }   // DIAG[0] = 8
+        s = mds_recombine(al0, al1, ah0, ah1);
+        xb ^= 1;
+      };
+#pragma unroll 1
+      for (int rd = 0; rd < 3; rd++) full_round(c_poseidon_rc[12 * (rd + 1) + wid]);
+      if (crit) {
+        full_round(c_fast_first[0]);        // word 0 passes the initial matrix unchanged
+      } else {
+        // round 3 with the dense initial matrix folded in: x_j = sum_i D3ROT[j][i] v_{(j+i) % 12} + K3[j]
+        const u64 v = poseidon_sbox(s);
+        xch[xb][wid][lane] = v; xch[xb][wid + 12][lane] = v;
+        named_bar_sync(1, 384);
+        u64 acc = c_fast_k3[wid];
+        u32 cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+          const u64 pr = gl_mul_lazy(c_fast_d3rot[12 * wid + i], xch[xb][wid + i][lane]);
+          acc += pr; cnt += (acc < pr);
+        }
+        const u64 tt = (u64)cnt * GL_EPS;    // every wrap of 2^64 is worth eps; cnt <= 12 so tt < 2^36
+        u64 r = acc + tt;
+        if (r < tt) r += GL_EPS;
+        s = gl_canon(r);
+        xb ^= 1;
+      }
+    }
+    // ---- 22 sparse partial rounds (bodies take the slot q = r % 3 as a compile-time constant) ----
+    if (crit) {
+      u64 x0 = s;
+      auto body = [&](int r, auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const u64 post = c_fast_post[r];
+        const u64 x2 = gl_mul_lazy(x0, x0);
+        const u64 x4 = gl_mul_lazy(x2, x2), x3 = gl_mul_lazy(x2, x0);
+        const u64 x7 = gl_mul_lazy(x3, x4);
+        // R needs y(r-1) for the look-ahead term and finishes Ebuf[q] ~200 cycles after it was published: waiting here,
+        // behind the issue of the whole S-box, costs nothing unless R is late
+        named_bar_sync(8 + q, 64);
+        const ulonglong2 E = *(const ulonglong2*)&Ebuf[q][2 * lane];
+        const u64 y = gl_add_lazy_canon(x7, post);
+        ybuf[q][lane] = y;
+        named_bar_arrive(2 + q, 384);
+        named_bar_arrive(11 + q, 64);
+        u32 al0 = (u32)E.x, al1 = (u32)(E.x >> 32), ah0 = (u32)E.y, ah1 = (u32)(E.y >> 32);   // half sums, < 2^37
+        mac32(al0, al1, (u32)y, 25u);
+        mac32(ah0, ah1, (u32)(y >> 32), 25u);
+        x0 = mds_recombine(al0, al1, ah0, ah1);
+      };
+#pragma unroll 1
+      for (int r = 0; r < 21; r += 3) {
+        body(r, std::integral_constant<int, 0>()); body(r + 1, std::integral_constant<int, 1>()); body(r + 2, std::integral_constant<int, 2>());
+      }
+      body(21, std::integral_constant<int, 0>());
+      s = x0;
+    } else if (!reducer) {
+      u64 x = s;                               // lazy
+      const u64* what = c_fast_what + (wid - 1);
+      const u64* vsp = c_fast_vs + (wid - 1);
+      ebuf[0][wid][lane] = gl_mul_lazy(what[0], x);
+      named_bar_arrive(5 + 0, 384);
+      ebuf[1][wid][lane] = gl_mul_lazy(what[11], x);
+      named_bar_arrive(5 + 1, 384);
+      auto body = [&](int r, auto qc) {
+        constexpr int q = decltype(qc)::value, q2 = (q + 2) % 3;
+        const u64 vs = vsp[r * 11];
+        const u64 wn = what[(r + 2 < 22 ? r + 2 : 0) * 11];
+        named_bar_sync(2 + q, 384);
+        const u64 y = ybuf[q][lane];
+        x = gl_mad_lazy(vs, y, x);
+        if (r + 2 < 22) {
+          ebuf[q2][wid][lane] = gl_mul_lazy(wn, x);
+          named_bar_arrive(5 + q2, 384);
+        }
+      };
+#pragma unroll 1
+      for (int r = 0; r < 21; r += 3) {
+        body(r, std::integral_constant<int, 0>()); body(r + 1, std::integral_constant<int, 1>()); body(r + 2, std::integral_constant<int, 2>());
+      }
+      body(21, std::integral_constant<int, 0>());
+      s = x;
+    } else {
+      // R: Ebuf[q] = (sum of low halves, sum of high halves) of the eleven products and of U[r] * y(r-1); the owner of
+      // word 0 adds 25 * y on top and reduces once (every half sum stays below 2^37).
+      auto body = [&](int r, auto qc) {
+        constexpr int q = decltype(qc)::value, qp = (q + 2) % 3;
+        const u64 u = c_fast_u[r];
+        named_bar_sync(5 + q, 384);
+        u64 e[12];
+#pragma unroll
+        for (int i = 1; i < 12; i++) e[i] = ebuf[q][i][lane];
+        u64 al = 0, ah = 0;
+#pragma unroll
+        for (int i = 1; i < 12; i++) { al += (u32)e[i]; ah += e[i] >> 32; }
+        if (r >= 1) {
+          named_bar_sync(11 + qp, 64);
+          const u64 uy = gl_mul_lazy(u, ybuf[qp][lane]);
+          al += (u32)uy; ah += uy >> 32;
+        }
+        *(ulonglong2*)&Ebuf[q][2 * lane] = make_ulonglong2(al, ah);
+        named_bar_arrive(8 + q, 64);
+      };
+#pragma unroll 1
+      for (int r = 0; r < 21; r += 3) {
+        body(r, std::integral_constant<int, 0>()); body(r + 1, std::integral_constant<int, 1>()); body(r + 2, std::integral_constant<int, 2>());
+      }
+      body(21, std::integral_constant<int, 0>());
+      named_bar_sync(11 + 21 % 3, 64);          // consume the last Y arrival so that the ids start clean next time
+    }
+    // ---- last four full rounds ----
+    if (!reducer) {
+      s = gl_add_lazy_canon(s, c_poseidon_rc[12 * 26 + wid]);
+#pragma unroll 1
+      for (int rd = 26; rd < 30; rd++) {
+        const u64 v = poseidon_sbox(s);
+        xch[xb][wid][lane] = v; xch[xb][wid + 12][lane] = v;
+        named_bar_sync(1, 384);
+        u64 t[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) t[i] = xch[xb][wid + i][lane];
+        u32 al0, al1, ah0, ah1;
+        mds_row<1>(t, [&](int i) { return CIRC[i]; }, c_poseidon_rc[12 * (rd + 1) + wid], 0, al0, al1, ah0, ah1);
+        if (wid == 0) { mac32(al0, al1, (u32)t[0], 8u); mac32(ah0, ah1, (u32)(t[0] >> 32), 8u); }
+        s = mds_recombine(al0, al1, ah0, ah1);
+        xb ^= 1;
+      }
+    }
+  }
+  if (live && !reducer && wid < 4) digests[4ull * leaf_index_of(pos, log_block) + wid] = gl_canon(s);
+}
