@@ -449,3 +449,278 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
   }
   if (live && !reducer && wid < 4) digests[4ull * leaf_index_of(pos, log_block) + wid] = gl_canon(s);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Throughput shapes (N = 32768 leaves: FinalExp, ECCAgg).  ncu on the dense-MDS kernels: sm__pipe_fmaheavy_cycles_active
+// 81 % -- every IMAD-class instruction runs on the "heavy" half of the FMA pipe and IMAD.WIDE takes two passes, so the
+// 288 IMAD.WIDE of a dense MDS layer are what bounds the machine, not issue slots (42 %) or the ALU pipe (26 %).
+// In sparse form a partial round is 22 full multiplies (~265 heavy-pipe passes instead of ~600) with twenty-odd
+// independent chains, so one thread can own a whole state: no shared memory, no barriers, lane = leaf.
+//   x += FIRST, x[1..] = INIT x[1..]      folded into round 3's linear layer (D3, K3), sums of 128-bit products
+//   per round: y = x0^7 + a_r;   x0 = 25 y + sum_i w^_r[i] x_i (one 192-bit accumulator, one reduction);   x_i += v_r[i] y
+// ---------------------------------------------------------------------------------------------------------
+static __constant__ u64 c_fast_d3[12 * 12] = POSEIDON_FAST_D3;
+
+// sum of 64x64 products as lo + hi 2^64 + top 2^128
+struct Acc192 { u64 lo, hi; u32 top; };
+__device__ __forceinline__ void acc192_mul(Acc192& a, u64 x, u64 y) {
+  const u64 pl = x * y, ph = __umul64hi(x, y);
+  a.lo += pl;
+  const u64 c = a.lo < pl;
+  a.hi += ph;
+  const u32 c1 = a.hi < ph;
+  a.hi += c;
+  a.top += c1 + (a.hi < c);
+}
+// (lo, hi, top) mod p -> lazy u64.   2^128 = -2^32 (mod p):  top * 2^128 = top * (p - 2^32) = top * (2^64 - 2^33 + 1)
+__device__ __forceinline__ u64 acc192_reduce(const Acc192& a) {
+  // t = top * (2^64 - 2^33 + 1), top <= 2^16:  t_hi:t_lo
+  const u64 top = a.top;
+  const u64 sub = top << 33;                       // top * 2^33 < 2^50
+  u64 t_lo = top - sub, t_hi = top - (top < sub);   // top*2^64 + top - top*2^33 (borrow iff top < sub, i.e. top > 0)
+  u64 lo = a.lo + t_lo;
+  u64 c = lo < t_lo;
+  u64 hi = a.hi + t_hi;
+  u64 c2 = hi < t_hi;
+  hi += c;
+  c2 += hi < c;
+  // a second wrap of 2^128 (c2 <= 1) is again worth 2^64 - 2^33 + 1; after a wrap hi is tiny, so this cannot wrap again
+  const u64 s2 = c2 << 33;
+  const u64 u_lo = c2 - s2, u_hi = c2 - (c2 < s2);
+  lo += u_lo;
+  hi += u_hi + (lo < u_lo);
+  // fold the 128-bit value (x3:x2:x1:x0) exactly like gl_mul_lazy
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 nc, nb;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"
+      "subc.u32 %1, %4, 0;\n\t"
+      "add.cc.u32 %1, %1, %3;\n\t"
+      "addc.u32 nc, 0, 0;\n\t"
+      "neg.s32 nc, nc;\n\t"
+      "sub.cc.u32 %0, %0, %5;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 nb, 0, 0;\n\t"
+      "add.cc.u32 %0, %0, nc;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "sub.cc.u32 %0, %0, nb;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+  return ((u64)r1 << 32) | r0;
+}
+
+// full round on a register-resident state: s[i] holds the pre-S-box value (constant already added); `next` = the
+// constants of the coming round (folded into the MDS accumulators)
+__device__ __forceinline__ void st_full_round(u64 (&s)[12], const u64* __restrict__ next) {
+  const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  u32 lo[12], hi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { const u64 v = poseidon_sbox(s[i]); lo[i] = (u32)v; hi[i] = (u32)(v >> 32); }
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    const u64 c = next[r];
+    u32 al0 = (u32)c, al1 = 0, ah0 = (u32)(c >> 32), ah1 = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { mac32(al0, al1, lo[(i + r) % 12], C[i]); mac32(ah0, ah1, hi[(i + r) % 12], C[i]); }
+    if (r == 0) { mac32(al0, al1, lo[0], 8u); mac32(ah0, ah1, hi[0], 8u); }
+    s[r] = mds_recombine(al0, al1, ah0, ah1);
+  }
+}
+
+__global__ void __launch_bounds__(64) leaf_sponge_st_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                            uint32_t n_leaves, unsigned log_block,
+                                                            u64* __restrict__ digests) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_leaves) return;
+  u64 s[12], nx[8];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  const uint32_t n_chunks = (leaf_len + 7) / 8;
+  const u64* p = cols + pos;
+#pragma unroll
+  for (int i = 0; i < 8; i++) nx[i] = ((uint32_t)i < leaf_len) ? p[(size_t)i * n_leaves] : 0;
+  for (uint32_t m = 0; m < n_chunks; m++) {
+    const unsigned take = min(8u, leaf_len - 8 * m);
+#pragma unroll
+    for (int i = 0; i < 8; i++) if ((unsigned)i < take) s[i] = nx[i];
+    if (m + 1 < n_chunks) {
+      const u64* q = p + (size_t)(m + 1) * 8 * n_leaves;
+#pragma unroll
+      for (int i = 0; i < 8; i++) if ((m + 1) * 8 + i < leaf_len) nx[i] = q[(size_t)i * n_leaves];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_canon(s[i], c_poseidon_rc[i]);
+#pragma unroll 1
+    for (int rd = 0; rd < 3; rd++) st_full_round(s, c_poseidon_rc + 12 * (rd + 1));
+    {  // round 3 with FIRST and the dense initial matrix folded in: x0 = (M v)_0 + FIRST[0], x_j = sum_c D3[j][c] v_c + K3[j]
+      u64 v[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) v[i] = poseidon_sbox(s[i]);
+      const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+      const u64 c0 = c_fast_first[0];
+      u32 al0 = (u32)c0, al1 = 0, ah0 = (u32)(c0 >> 32), ah1 = 0;
+#pragma unroll
+      for (int i = 0; i < 12; i++) { mac32(al0, al1, (u32)v[i], C[i]); mac32(ah0, ah1, (u32)(v[i] >> 32), C[i]); }
+      mac32(al0, al1, (u32)v[0], 8u); mac32(ah0, ah1, (u32)(v[0] >> 32), 8u);
+      s[0] = mds_recombine(al0, al1, ah0, ah1);
+#pragma unroll 1
+      for (int j = 1; j < 12; j++) {
+        Acc192 a = {c_fast_k3[j], 0, 0};
+#pragma unroll
+        for (int c = 0; c < 12; c++) acc192_mul(a, c_fast_d3[12 * j + c], v[c]);
+        const u64 r = acc192_reduce(a);
+        // s[j] with a runtime j: keep the state in registers
+#pragma unroll
+        for (int k = 1; k < 12; k++) if (k == j) s[k] = r;
+      }
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+      const u64 y = gl_add_lazy_canon(poseidon_sbox(s[0]), c_fast_post[r]);
+      const u64* wh = c_fast_what + 11 * r;
+      const u64* vs = c_fast_vs + 11 * r;
+      Acc192 a = {0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 11; i++) acc192_mul(a, wh[i], s[i + 1]);
+      const u64 d = gl_canon(acc192_reduce(a));
+      u32 al0 = (u32)d, al1 = 0, ah0 = (u32)(d >> 32), ah1 = 0;
+      mac32(al0, al1, (u32)y, 25u);
+      mac32(ah0, ah1, (u32)(y >> 32), 25u);
+      s[0] = mds_recombine(al0, al1, ah0, ah1);
+#pragma unroll
+      for (int i = 0; i < 11; i++) s[i + 1] = gl_mad_lazy(vs[i], y, s[i + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_canon(s[i], c_poseidon_rc[12 * 26 + i]);
+#pragma unroll 1
+    for (int rd = 26; rd < 30; rd++) st_full_round(s, c_poseidon_rc + 12 * (rd + 1));
+  }
+  u64* dg = digests + 4ull * leaf_index_of(pos, log_block);
+#pragma unroll
+  for (int i = 0; i < 4; i++) dg[i] = gl_canon(s[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dense MDS on the integer dot-product instruction.  Measured on B200 (tools/perf/pipe_lab.cu): IMAD.WIDE.U32 issues at
+// 32 lanes/clk/SM -- half the rate of IMAD, IDP.2A and IDP.4A (64) -- and ncu shows the throughput-bound shapes at 81 %
+// of sm__pipe_fmaheavy_cycles_active.  The MDS coefficients are <= 41, so a row is computed on 16-bit limbs with
+//     dp2a.lo.u32.u32  acc, (limb_k of word j | limb_k of word j+1 << 16), (c_j | c_{j+1} << 8), acc
+// : 7 word pairs x 4 limbs = 28 IDP per row (one pass each) instead of 24 IMAD.WIDE (two passes each), every limb sum
+// < 2^27.  The pair packing (28 PRMT on the ALU pipe) is shared by the three rows a thread owns, which is why this
+// variant exists for the three-words-per-thread layout only.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b, u32 c) {
+  u32 d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// limb accumulators (each < 2^28) -> lazy u64:  a0 + a1 2^16 + a2 2^32 + a3 2^48
+__device__ __forceinline__ u64 limbs_recombine(u32 a0, u32 a1, u32 a2, u32 a3) {
+  const u64 al = (u64)a0 + ((u64)a1 << 16), ah = (u64)a2 + ((u64)a3 << 16);     // both < 2^45
+  return mds_recombine((u32)al, (u32)(al >> 32), (u32)ah, (u32)(ah >> 32));
+}
+
+__global__ void __launch_bounds__(128) leaf_sponge_dp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                             uint32_t n_leaves, unsigned log_block,
+                                                             u64* __restrict__ digests) {
+  constexpr int W = 3, NW = W + 11, NP = NW / 2;
+  __shared__ __align__(16) u64 xch[2][24][32];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned w0 = wid * W;
+  const uint32_t pos_raw = blockIdx.x * 32 + lane;
+  const bool live = pos_raw < n_leaves;
+  const uint32_t pos = live ? pos_raw : n_leaves - 1;
+  constexpr u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+
+  u64 s[W], nx[W];
+#pragma unroll
+  for (int k = 0; k < W; k++) { s[k] = 0; nx[k] = 0; }
+  const uint32_t n_chunks = (leaf_len + 7) / 8;
+  auto fetch = [&](uint32_t chunk) {
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      uint32_t c = chunk * 8 + w0 + k;
+      if (w0 + k < 8 && c < leaf_len) nx[k] = cols[(size_t)c * n_leaves + pos];
+    }
+  };
+  fetch(0);
+  unsigned xb = 0;
+  for (uint32_t m = 0; m < n_chunks; m++) {
+    const unsigned take = min(8u, leaf_len - 8 * m);
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      if (w0 + k < take) s[k] = nx[k];
+    if (m + 1 < n_chunks) fetch(m + 1);
+#pragma unroll
+    for (int k = 0; k < W; k++) s[k] = gl_add_lazy_canon(s[k], c_poseidon_rc[w0 + k]);
+
+    auto linear_layer = [&](const u64 (&v)[W], int rd) {
+      u64* dst = &xch[xb][w0][lane];
+#pragma unroll
+      for (int k = 0; k < W; k++) { dst[32 * k] = v[k]; dst[32 * (k + 12)] = v[k]; }
+      u64 rc[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) rc[k] = c_poseidon_rc[12 * (rd + 1) + w0 + k];
+      __syncthreads();
+      const u64* src = &xch[xb][w0][lane];
+      u64 t[NW];
+#pragma unroll
+      for (int j = 0; j < NW; j++) t[j] = src[32 * j];       // word (w0 + j) mod 12
+      u32 acc[W][4];
+#pragma unroll
+      for (int k = 0; k < W; k++) {
+        const u32 lo = (u32)rc[k], hi = (u32)(rc[k] >> 32);
+        acc[k][0] = lo & 0xFFFFu; acc[k][1] = lo >> 16; acc[k][2] = hi & 0xFFFFu; acc[k][3] = hi >> 16;
+      }
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const u32 alo = (u32)t[2 * p], ahi = (u32)(t[2 * p] >> 32), blo = (u32)t[2 * p + 1], bhi = (u32)(t[2 * p + 1] >> 32);
+        const u32 q0 = __byte_perm(alo, blo, 0x5410), q1 = __byte_perm(alo, blo, 0x7632);
+        const u32 q2 = __byte_perm(ahi, bhi, 0x5410), q3 = __byte_perm(ahi, bhi, 0x7632);
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+          const int i0 = 2 * p - k, i1 = 2 * p + 1 - k;            // circulant index of the two words in row k
+          const u32 c0 = (i0 >= 0 && i0 < 12) ? CIRC[i0] : 0u, c1 = (i1 >= 0 && i1 < 12) ? CIRC[i1] : 0u;
+          const u32 b = c0 | (c1 << 8);
+          if (b) {
+            acc[k][0] = dp2a_lo(q0, b, acc[k][0]); acc[k][1] = dp2a_lo(q1, b, acc[k][1]);
+            acc[k][2] = dp2a_lo(q2, b, acc[k][2]); acc[k][3] = dp2a_lo(q3, b, acc[k][3]);
+          }
+        }
+        if (p == 0 && wid == 0) {                                   // DIAG[0] = 8 on row 0 / word 0
+          acc[0][0] = dp2a_lo(q0, 8u, acc[0][0]); acc[0][1] = dp2a_lo(q1, 8u, acc[0][1]);
+          acc[0][2] = dp2a_lo(q2, 8u, acc[0][2]); acc[0][3] = dp2a_lo(q3, 8u, acc[0][3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < W; k++) s[k] = limbs_recombine(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+      xb ^= 1;
+    };
+    auto full_round = [&](int rd) {
+      u64 v[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) v[k] = poseidon_sbox(s[k]);
+      linear_layer(v, rd);
+    };
+#pragma unroll 1
+    for (int rd = 0; rd < 4; rd++) full_round(rd);
+#pragma unroll 1
+    for (int rd = 4; rd < 26; rd++) {
+      u64 v[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) v[k] = s[k];
+      if (wid == 0) v[0] = poseidon_sbox(v[0]);
+      linear_layer(v, rd);
+    }
+#pragma unroll 1
+    for (int rd = 26; rd < 30; rd++) full_round(rd);
+  }
+  if (live) {
+    u64* d = digests + 4ull * leaf_index_of(pos, log_block);
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      if (w0 + k < 4) d[w0 + k] = gl_canon(s[k]);
+  }
+}

@@ -93,7 +93,7 @@ def derive():
     d3rot = [[d3[j][(j + i) % W] for i in range(W)] for j in range(W)]
     # two-round look-ahead: sum_i w^_r[i] x_i(r) = sum_i w^_r[i] x_i(r-1) + U[r] y(r-1),  U[r] = sum_i w^_r[i] v_{r-1}[i]
     u = [0] + [sum(a * b for a, b in zip(w_hat[r], vs[r - 1])) % P for r in range(1, RP)]
-    return dict(rc=rc, first=first, post=post, init=init, w_hat=w_hat, vs=vs, d3rot=d3rot, k3=k3, u=u)
+    return dict(rc=rc, first=first, post=post, init=init, w_hat=w_hat, vs=vs, d3rot=d3rot, k3=k3, u=u, d3=d3)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -175,6 +175,7 @@ def header(t):
     lines += ["// warp-split kernel: round 3's linear layer with INIT folded in, x_j = sum_i D3ROT[j][i] v_{(j+i)%12} + K3[j];",
               "// U[r] = sum_i WHAT[r][i] VS[r-1][i] (two-round look-ahead of the word-0 dot product)."]
     lines += arr("POSEIDON_FAST_D3ROT", [v for row in t["d3rot"] for v in row])
+    lines += arr("POSEIDON_FAST_D3", [v for row in t["d3"] for v in row])
     lines += arr("POSEIDON_FAST_K3", t["k3"])
     lines += arr("POSEIDON_FAST_U", t["u"])
     return "\n".join(lines) + "\n"
