@@ -82,6 +82,12 @@ void sb_destroy(sb_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   air_release_all(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (auto& e : ctx->slab_ev) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->fork_ev);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -184,6 +190,67 @@ void commit_trace(sb_ctx* ctx, const sb_params* p, const u64* d_values) {
   ctx->have_lde = true;
 }
 
+// Ingest + from_values in one pipeline for the host column layouts: the trace crosses PCIe in column slabs on a second
+// stream while K1 already extends the slabs that have arrived, so the H2D copy (the larger of the two for every stark:
+// 8 C n bytes at ~55 GB/s) hides the whole LDE.  `h2d_done` is recorded on the copy stream after the last slab.
+void ingest_and_commit_trace(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, cudaEvent_t h2d_done) {
+  const size_t n = size_t(1) << p->log_n, N = n << p->rate_bits, C = p->n_cols;
+  const bool pipelined = trace && (layout == SB_TRACE_COLMAJOR_U64 || layout == SB_TRACE_COLS_U64_PTRS);
+  if (!pipelined) {
+    const u64* d_values = ingest_trace(ctx, p, trace, layout);
+    if (h2d_done) CUDA_CHECK(cudaEventRecord(h2d_done, ctx->stream));
+    commit_trace(ctx, p, d_values);
+    return;
+  }
+  if (!ctx->copy_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->slab_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  }
+  ctx->trace.ensure(8 * n * C);
+  ctx->coeffs.ensure(8 * n * C);
+  ctx->lde.ensure(8 * N * C);
+  ctx->tree.ensure(32 * 2 * N);
+  const size_t slab_cols = std::max<size_t>(1, (32u << 20) / (8 * n));
+  u64* stage = nullptr;
+  if (layout == SB_TRACE_COLS_U64_PTRS) stage = (u64*)pinned_staging(ctx, 2 * slab_cols * 8 * n);
+  // the copy stream starts where the main stream is now (earlier work may still be using ctx->trace)
+  CUDA_CHECK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+  stage_begin(ctx, "lde");
+  size_t i = 0;
+  for (size_t c0 = 0; c0 < C; c0 += slab_cols, i++) {
+    const size_t cnt = std::min(slab_cols, C - c0);
+    cudaEvent_t ev = ctx->slab_ev[i % 4];
+    u64* d_slab = ctx->trace.as<u64>() + c0 * n;
+    if (layout == SB_TRACE_COLMAJOR_U64) {
+      CUDA_CHECK(cudaMemcpyAsync(d_slab, (const u64*)trace + c0 * n, 8 * n * cnt, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+      // Vec<PolynomialValues<F>>: gather the separately allocated columns into one of two pinned staging slabs
+      const u64* const* cols = (const u64* const*)trace;
+      u64* dst = stage + (i & 1) * slab_cols * n;
+      if (i >= 2) CUDA_CHECK(cudaEventSynchronize(ctx->slab_ev[(i - 2) % 4]));   // that staging slab has left the host
+      for (size_t c = 0; c < cnt; c++) memcpy(dst + c * n, cols[c0 + c], 8 * n);
+      CUDA_CHECK(cudaMemcpyAsync(d_slab, dst, 8 * n * cnt, cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    // (re-recording an event does not disturb a cudaStreamWaitEvent already enqueued on its previous record)
+    CUDA_CHECK(cudaEventRecord(ev, ctx->copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    sb_lde_trace(ctx, d_slab, ctx->coeffs.as<u64>() + c0 * n, ctx->lde.as<u64>() + c0 * N, (uint32_t)cnt, p->log_n, p->rate_bits);
+  }
+  stage_end(ctx, "lde");
+  if (h2d_done) CUDA_CHECK(cudaEventRecord(h2d_done, ctx->copy_stream));
+  ctx->have_trace = true;
+  stage_begin(ctx, "leaf_hash");
+  sb_hash_leaves_device(ctx, ctx->lde.as<u64>(), (uint32_t)C, (uint32_t)N, p->log_n, ctx->tree.as<u64>());
+  stage_end(ctx, "leaf_hash");
+  stage_begin(ctx, "merkle");
+  sb_merkle_levels(ctx, ctx->tree.as<u64>(), (uint32_t)N, p->cap_height);
+  stage_end(ctx, "merkle");
+  ctx->cur = *p;
+  ctx->have_lde = true;
+}
+
 const u64* tree_cap_ptr(const u64* d_tree, size_t n_leaves, unsigned cap_height) {
   // level l starts at digest offset 2N - (2N >> l); the cap is level log2(N) - cap_height
   size_t off = 2 * n_leaves - (size_t(2) << cap_height);
@@ -216,8 +283,7 @@ int sb_lde_commit(sb_ctx* ctx, const sb_params* p, const void* trace, int layout
   check_params(p);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   const size_t n = size_t(1) << p->log_n, N = n << p->rate_bits, C = p->n_cols;
-  const u64* d_values = ingest_trace(ctx, p, trace, layout);
-  commit_trace(ctx, p, d_values);
+  ingest_and_commit_trace(ctx, p, trace, layout, nullptr);
   if (lde_out) CUDA_CHECK(cudaMemcpyAsync(lde_out, ctx->lde.p, 8 * N * C, cudaMemcpyDeviceToHost, ctx->stream));
   if (digests_out) CUDA_CHECK(cudaMemcpyAsync(digests_out, ctx->tree.p, 32 * N, cudaMemcpyDeviceToHost, ctx->stream));
   if (cap_out)

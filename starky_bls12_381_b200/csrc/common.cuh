@@ -59,6 +59,8 @@ struct StageTimer {
 struct sb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;    // H2D of trace slabs, overlapped with K1 (capi.cu ingest_and_commit_trace)
+  cudaEvent_t slab_ev[4] = {nullptr, nullptr, nullptr, nullptr}, fork_ev = nullptr;
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;

@@ -139,9 +139,7 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
 
   // ---- 0. ingest, 1. trace commitment ----
   CUDA_CHECK(cudaEventRecord(ev[0], st));
-  const u64* d_values = ingest_trace(ctx, p, trace, layout);
-  CUDA_CHECK(cudaEventRecord(ev[1], st));
-  commit_trace(ctx, p, d_values);
+  ingest_and_commit_trace(ctx, p, trace, layout, ev[1]);   // ev[1] = trace fully on the device (copy stream)
   CUDA_CHECK(cudaMemcpyAsync(W + L.off_trace_cap, tree_cap_ptr(ctx->tree.as<u64>(), N, p->cap_height), 32ull * L.cap_len,
                              cudaMemcpyDeviceToHost, st));
   ctx->pis.ensure(8ull * (p->n_public_inputs + 1));

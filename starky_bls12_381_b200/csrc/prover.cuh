@@ -13,6 +13,7 @@ static inline unsigned quotient_degree_factor(const sb_params& p) { return p.con
 int sb_fail(sb_ctx* ctx, const SbError& e);
 const u64* ingest_trace(sb_ctx* ctx, const sb_params* p, const void* trace, int layout);
 void commit_trace(sb_ctx* ctx, const sb_params* p, const u64* d_values);
+void ingest_and_commit_trace(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, cudaEvent_t h2d_done);
 const u64* tree_cap_ptr(const u64* d_tree, size_t n_leaves, unsigned cap_height);
 
 // quotient.cu
