@@ -17,17 +17,71 @@ typedef uint32_t u32;
 #define GL_P 0xFFFFFFFF00000001ULL
 #define GL_EPS 0xFFFFFFFFULL
 
-GL_HD u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+// The three primitives below are on every kernel's inner loop and every kernel here is ALU-pipe bound (ncu: K1 78 %,
+// K4 64 %), so the device paths are 32-bit carry chains instead of 64-bit compares and selects:
+//   x >= p  <=>  x + eps carries out of 64 bits (eps = 2^32 - 1 = 2^64 - p), and x - p = x + eps (mod 2^64).
+GL_HD u64 gl_canon(u64 a) {
+#if defined(__CUDA_ARCH__)
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), r0, r1;
+  asm("{\n\t"
+      ".reg .u32 t0, t1, c;\n\t"
+      ".reg .pred q;\n\t"
+      "add.cc.u32 t0, %2, 0xFFFFFFFF;\n\t"
+      "addc.cc.u32 t1, %3, 0;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "setp.ne.u32 q, c, 0;\n\t"
+      "selp.u32 %0, t0, %2, q;\n\t"
+      "selp.u32 %1, t1, %3, q;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1) : "r"(a0), "r"(a1));
+  return ((u64)r1 << 32) | r0;
+#else
+  return a >= GL_P ? a - GL_P : a;
+#endif
+}
 
 // canonical + canonical -> canonical
 GL_HD u64 gl_add(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 s0, s1, t0, t1, c;\n\t"
+      ".reg .pred q;\n\t"
+      "add.cc.u32 s0, %2, %4;\n\t"           // s = a + b  (65 bits: c:s)
+      "addc.cc.u32 s1, %3, %5;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "add.cc.u32 t0, s0, 0xFFFFFFFF;\n\t"   // t = s - p (mod 2^64); carries iff s >= p
+      "addc.cc.u32 t1, s1, 0;\n\t"
+      "addc.u32 c, c, 0;\n\t"
+      "setp.ne.u32 q, c, 0;\n\t"
+      "selp.u32 %0, t0, s0, q;\n\t"
+      "selp.u32 %1, t1, s1, q;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  return ((u64)r1 << 32) | r0;
+#else
   u64 s = a + b;
   return (s < a) ? s + GL_EPS : (s >= GL_P ? s - GL_P : s);
+#endif
 }
 // canonical - canonical -> canonical
 GL_HD u64 gl_sub(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 m;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"
+      "subc.cc.u32 %1, %3, %5;\n\t"
+      "subc.u32 m, 0, 0;\n\t"                // 0xFFFFFFFF on borrow: + p = - eps (mod 2^64)
+      "sub.cc.u32 %0, %0, m;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  return ((u64)r1 << 32) | r0;
+#else
   u64 d = a - b;
   return (a < b) ? d + GL_P : d;
+#endif
 }
 GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 

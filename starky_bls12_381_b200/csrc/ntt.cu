@@ -11,6 +11,8 @@
 // values to bit-reversed coefficients, and per coset a decimation-in-time forward transform takes bit-reversed
 // (scaled) coefficients to natural-order coset values.  plonky2's leaf index of position (J,k) is J*n + bitrev_n(k);
 // only the 32-byte digests are scattered to it (merkle.cu), the 8*C*N bytes of LDE never are.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -159,6 +161,141 @@ __global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K1, radix-8 form (n >= 64).  The radix-2 kernel above spends its time on shared-memory round trips and barriers
+// (log n per transform) with the ALU pipe at 73 %; here a thread keeps eight elements in registers for three stages:
+//   inverse (DIF): group (log n - 1 .. log n - 3) straight from global memory (stride n/8: coalesced), middle groups
+//                  through shared memory, last group (2, 1, 0) leaves thread t with positions 8t .. 8t+7 = exactly the
+//                  eight it needs for the first forward group, so the coefficients never leave its registers;
+//   forward (DIT), per coset: scale, group (0, 1, 2) in registers, middle groups, last group (log n - 3 .. log n - 1)
+//                  straight to global memory (stride n/8: coalesced).
+// Barriers per column: (1 + 2^r) x (1 + middle groups) instead of (1 + 2^r) x log n.  Shared rows are padded by one
+// word per 32 so that the "eight consecutive words per thread" accesses stay at two wavefronts per warp.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned padi(unsigned i) { return i + (i >> 5); }
+
+// R stages of decimation in frequency on 2^R registers; element m sits at index i0 + m * unit, `low` = i0 mod unit,
+// the top stage is s = log2(unit) + R - 1
+template <int R>
+__device__ __forceinline__ void dif_group(u64 (&x)[1 << R], unsigned low, unsigned log_unit, unsigned log_tw, const u64* __restrict__ tw) {
+#pragma unroll
+  for (int st = 0; st < R; st++) {
+    constexpr int E = 1 << R;
+    const int half_m = E >> (st + 1);
+    const unsigned cur = log_unit + R - 1 - st;           // stage index: half = 2^cur
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      if (!(m & half_m)) {
+        const unsigned j = low + ((unsigned)(m & (half_m - 1)) << log_unit);
+        const u64 w = __ldg(tw + ((size_t)j << (log_tw - 1 - cur)));
+        const u64 u = x[m], v = x[m + half_m];
+        x[m] = gl_add(u, v);
+        x[m + half_m] = gl_mul(gl_sub(u, v), w);
+      }
+    }
+  }
+}
+// R stages of decimation in time; the bottom stage is s = log2(unit)
+template <int R>
+__device__ __forceinline__ void dit_group(u64 (&x)[1 << R], unsigned low, unsigned log_unit, unsigned log_tw, const u64* __restrict__ tw) {
+#pragma unroll
+  for (int st = 0; st < R; st++) {
+    constexpr int E = 1 << R;
+    const int half_m = 1 << st;
+    const unsigned cur = log_unit + st;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      if (!(m & half_m)) {
+        const unsigned j = low + ((unsigned)(m & (half_m - 1)) << log_unit);
+        const u64 w = __ldg(tw + ((size_t)j << (log_tw - 1 - cur)));
+        const u64 u = x[m], t = gl_mul(x[m + half_m], w);
+        x[m] = gl_add(u, t);
+        x[m + half_m] = gl_sub(u, t);
+      }
+    }
+  }
+}
+// one middle pass over a column held in (padded) shared memory: groups of R stages starting at stage `base` (DIT:
+// bottom stage, DIF: the group covers base + R - 1 .. base); every thread does 8 / 2^R work items
+template <int R, bool DIF>
+__device__ __forceinline__ void smem_pass(u64* b, unsigned t, unsigned log_n, unsigned base, const u64* __restrict__ tw) {
+  constexpr int E = 1 << R, ITEMS = 8 / E;
+  const unsigned per_col = 1u << (log_n - 3);
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    const unsigned wi = t + it * per_col;                              // work item in [0, n / 2^R)
+    const unsigned low = wi & ((1u << base) - 1), high = wi >> base;
+    const unsigned i0 = (high << (base + R)) | low;
+    u64 x[E];
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = b[padi(i0 + ((unsigned)m << base))];
+    if (DIF) dif_group<R>(x, low, base, log_n, tw); else dit_group<R>(x, low, base, log_n, tw);
+#pragma unroll
+    for (int m = 0; m < E; m++) b[padi(i0 + ((unsigned)m << base))] = x[m];
+  }
+}
+
+__global__ void __launch_bounds__(1024) lde8_kernel(const u64* __restrict__ values, u64* __restrict__ coeffs, u64* __restrict__ lde,
+                                                   uint32_t n_cols, unsigned log_n, unsigned rate_bits, unsigned log_cpb,
+                                                   const u64* __restrict__ tw_fwd, const u64* __restrict__ tw_inv,
+                                                   const u64* __restrict__ scale, u64 n_inv, unsigned log_rb) {
+  extern __shared__ u64 buf[];
+  const uint32_t n = 1u << log_n, unit = n >> 3;
+  const unsigned lc = threadIdx.x >> (log_n - 3), t = threadIdx.x & (unit - 1);
+  const uint32_t col = (blockIdx.x << log_cpb) + lc;
+  const bool live = col < n_cols;
+  u64* b = buf + (size_t)lc * (n + (n >> 5));
+  const unsigned mid = log_n - 6, r = mid % 3;          // middle stages 3 .. log n - 4: mid / 3 full groups + one of r
+  u64 x[8], c[8];
+
+  // ---- inverse transform, decimation in frequency ----
+  const u64* vin = values + (size_t)col * n + t;
+#pragma unroll
+  for (int m = 0; m < 8; m++) x[m] = live ? vin[(size_t)m * unit] : 0;
+  dif_group<3>(x, t, log_n - 3, log_n, tw_inv);
+#pragma unroll
+  for (int m = 0; m < 8; m++) b[padi(t + m * unit)] = x[m];
+  __syncthreads();
+  for (int base = (int)log_n - 6; base >= 3 + (int)r; base -= 3) { smem_pass<3, true>(b, t, log_n, base, tw_inv); __syncthreads(); }
+  if (r == 2) { smem_pass<2, true>(b, t, log_n, 3, tw_inv); __syncthreads(); }
+  if (r == 1) { smem_pass<1, true>(b, t, log_n, 3, tw_inv); __syncthreads(); }
+#pragma unroll
+  for (int m = 0; m < 8; m++) x[m] = b[padi(8 * t + m)];
+  dif_group<3>(x, 0, 0, log_n, tw_inv);
+#pragma unroll
+  for (int m = 0; m < 8; m++) c[m] = x[m];              // n * c_{bitrev(8t + m)}
+  if (coeffs && live) {
+    u64* co = coeffs + (size_t)col * n + 8 * t;
+#pragma unroll
+    for (int m = 0; m < 8; m += 2) *(ulonglong2*)(co + m) = make_ulonglong2(gl_mul(c[m], n_inv), gl_mul(c[m + 1], n_inv));
+  }
+
+  // ---- forward transforms, decimation in time, one per coset ----
+  for (unsigned J = 0; J < (1u << rate_bits); J++) {
+    const u64* sc = scale + ((size_t)J << log_n) + 8 * t;
+#pragma unroll
+    for (int m = 0; m < 8; m++) x[m] = gl_mul(c[m], __ldg(sc + m));
+    dit_group<3>(x, 0, 0, log_n, tw_fwd);
+    __syncthreads();                                      // everyone is done reading the previous contents of b
+#pragma unroll
+    for (int m = 0; m < 8; m++) b[padi(8 * t + m)] = x[m];
+    __syncthreads();
+    if (r == 1) { smem_pass<1, false>(b, t, log_n, 3, tw_fwd); __syncthreads(); }
+    if (r == 2) { smem_pass<2, false>(b, t, log_n, 3, tw_fwd); __syncthreads(); }
+    for (unsigned base = 3 + r; base + 3 <= log_n - 3; base += 3) { smem_pass<3, false>(b, t, log_n, base, tw_fwd); __syncthreads(); }
+#pragma unroll
+    for (int m = 0; m < 8; m++) x[m] = b[padi(t + m * unit)];
+    dit_group<3>(x, t, log_n - 3, log_n, tw_fwd);
+    if (live) {
+#pragma unroll
+      for (int m = 0; m < 8; m++) {
+        const size_t pos = ((size_t)J << log_n) + t + (size_t)m * unit;
+        lde[((((pos >> log_rb) * n_cols) + col) << log_rb) + (pos & (((size_t)1 << log_rb) - 1))] = x[m];
+      }
+    }
+  }
+}
+
 void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, uint32_t n_cols, unsigned log_n,
                   unsigned rate_bits, unsigned log_row_blocks) {
   const unsigned log_rb = log_n + rate_bits - log_row_blocks;
@@ -166,6 +303,18 @@ void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, u
   const Twiddles& tw = sb_twiddles(ctx, log_n);
   const u64* scale = coset_scale(ctx, log_n, rate_bits);
   const uint32_t n = 1u << log_n;
+  if (log_n >= 6 && !getenv("SB_LDE_RADIX2")) {
+    // radix-8 kernel: n / 8 threads per column, at least 256 threads per block
+    unsigned log_cpb = 0;
+    while (((n >> 3) << log_cpb) < 256) log_cpb++;
+    const unsigned T = (n >> 3) << log_cpb;
+    const size_t smem8 = 8ull * ((size_t)(n + (n >> 5)) << log_cpb);
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(lde8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 256))); attr_set = true; }
+    LAUNCH(ctx, lde8_kernel, (n_cols + (1u << log_cpb) - 1) >> log_cpb, T, smem8, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits,
+           log_cpb, tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb);
+    return;
+  }
   // block shape: EPT elements per thread, cpb columns per block so that a block has >= 128 threads
   int ept = n >= 4096 ? 8 : 4;
   unsigned cpb = 1;

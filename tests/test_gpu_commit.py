@@ -72,7 +72,8 @@ def test_hash_leaves_every_kernel_variant(ctx, monkeypatch, kernel, leaf_len, co
 
 @pytest.mark.parametrize("log_n,n_cols,rate_bits,full", [
     (4, 8, 1, False), (4, 61, 1, True), (5, 3, 2, True), (6, 37, 1, False), (7, 20, 2, True),
-    (10, 19, 1, False), (10, 11, 2, True), (13, 3, 2, True), (3, 300, 3, False)])
+    (10, 19, 1, False), (10, 11, 2, True), (13, 3, 2, True), (3, 300, 3, False),
+    (8, 5, 2, True), (9, 3, 1, True), (11, 2, 2, True), (12, 3, 1, True), (6, 3, 3, True)])
 def test_lde_commit_matches_oracle(ctx, log_n, n_cols, rate_bits, full):
     rng = np.random.default_rng(1000 * log_n + n_cols)
     p = custom(log_n, n_cols, rate_bits)
