@@ -2,6 +2,8 @@
 // the query gathers, for sm_100a.  Replaces StarkOpeningSet::new, PolynomialBatch::prove_openings,
 // fri_committed_trees, fri_proof_of_work and fri_prover_query_rounds (plonky2 / starky),
 // reached from starky::prover::prove (/root/reference/src/aggregate_proof.rs:59,105,138,169,212).
+#include <algorithm>
+
 #include "poseidon.cuh"
 #include "prover.cuh"
 
@@ -167,8 +169,10 @@ __global__ void __launch_bounds__(128) pow_kernel(PowState st, int pos, unsigned
 u64 sb_pow_device(sb_ctx* ctx, const u64 state[12], int pos, unsigned bits, unsigned long long* d_best) {
   PowState st;
   for (int i = 0; i < 12; i++) st.s[i] = state[i];
-  const u64 window = 1ull << 20;
-  for (u64 base = 0; base < (1ull << 40); base += window) {
+  // windows are scanned in order, so the SMALLEST witness is returned whatever their size; the first window is sized for
+  // the expected 2^bits candidates (x4: found in it with probability 1 - e^-4), later ones grow to keep the machine full
+  u64 window = std::max<u64>(1ull << 14, std::min<u64>(1ull << 20, 4ull << bits));
+  for (u64 base = 0; base < (1ull << 40); base += window, window = 1ull << 20) {
     unsigned long long init = ~0ull, got = ~0ull;
     CUDA_CHECK(cudaMemcpyAsync(d_best, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, pow_kernel, (unsigned)(window / 128), 128, 0, st, pos, bits, base, d_best);
