@@ -172,6 +172,10 @@ int sb_hash_rows_device(sb_ctx* ctx, const uint64_t* d_cols, uint32_t leaf_len, 
 int sb_merkle_from_position_digests(sb_ctx* ctx, const sb_params* p, const uint64_t* d_digests_pos, uint64_t* cap_out);
 int sb_synchronize(sb_ctx* ctx);
 
+/* The host-side transcript permutation (plonky2 Challenger, run between kernels): variant 0 = portable scalar,
+ * 1 = AVX2, 2 = AVX-512; returns 1 if that variant ran, 0 if the CPU lacks the extension.  Parity-test hook. */
+int sb_host_poseidon_permute_variant(uint64_t state[12], int variant);
+
 /* ---- device-resident benchmarking hooks (bench.py `value` leg: inputs already in HBM) ---- */
 /* Upload a trace once; subsequent sb_prove(..., trace=NULL, layout=SB_TRACE_DEVICE_COLMAJOR_U64) re-uses it. */
 int sb_trace_upload(sb_ctx* ctx, const sb_params* p, const void* trace, int layout);

@@ -146,8 +146,110 @@ __attribute__((target("avx2"))) static void permute_avx2(u64 s[12]) {
 }
 #endif
 
+#if defined(__x86_64__)
+// ---- AVX-512: the state lives in two 8-lane vectors (words 0..7, words 8..11 + four idle lanes); unsigned compares
+// are native mask operations, so every carry / borrow repair is one compare and one masked add. ----
+#define T512 __attribute__((target("avx512f,avx512dq,avx512bw,avx512vl"))) static inline
+typedef __m512i W;
+T512 W wset(u64 x) { return _mm512_set1_epi64((long long)x); }
+T512 W wadd_lazy(W a, W c) {   // lazy + canonical -> lazy
+  W s = _mm512_add_epi64(a, c);
+  return _mm512_mask_add_epi64(s, _mm512_cmplt_epu64_mask(s, a), s, wset(EPS));
+}
+T512 W wmul(W a, W b) {        // lazy x lazy -> lazy
+  const W M32 = wset(EPS);
+  W ah = _mm512_srli_epi64(a, 32), bh = _mm512_srli_epi64(b, 32);
+  W ll = _mm512_mul_epu32(a, b), lh = _mm512_mul_epu32(a, bh), hl = _mm512_mul_epu32(ah, b), hh = _mm512_mul_epu32(ah, bh);
+  W mid = _mm512_add_epi64(lh, _mm512_srli_epi64(ll, 32));
+  W mid2 = _mm512_add_epi64(hl, _mm512_and_si512(mid, M32));
+  W lo = _mm512_or_si512(_mm512_and_si512(ll, M32), _mm512_slli_epi64(mid2, 32));
+  W hi = _mm512_add_epi64(_mm512_add_epi64(hh, _mm512_srli_epi64(mid, 32)), _mm512_srli_epi64(mid2, 32));
+  W hi_hi = _mm512_srli_epi64(hi, 32), hi_lo = _mm512_and_si512(hi, M32);
+  W t0 = _mm512_sub_epi64(lo, hi_hi);
+  t0 = _mm512_mask_sub_epi64(t0, _mm512_cmplt_epu64_mask(lo, hi_hi), t0, M32);
+  W t1 = _mm512_sub_epi64(_mm512_slli_epi64(hi_lo, 32), hi_lo);
+  W r = _mm512_add_epi64(t0, t1);
+  return _mm512_mask_add_epi64(r, _mm512_cmplt_epu64_mask(r, t1), r, M32);
+}
+T512 W wsbox(W x) { W x2 = wmul(x, x), x4 = wmul(x2, x2), x3 = wmul(x2, x); return wmul(x3, x4); }
+
+// CW[w][j][l] = coefficient of input word w in output row 8j + l  (rows 12..15 do not exist: zero)
+alignas(64) static u64 CW[12][2][8];
+static const bool cw_ready = [] {
+  for (int w = 0; w < 12; w++)
+    for (int j = 0; j < 2; j++)
+      for (int l = 0; l < 8; l++) {
+        int row = 8 * j + l;
+        CW[w][j][l] = row < 12 ? CIRC[((w - row) % 12 + 12) % 12] + ((w == 0 && row == 0) ? 8 : 0) : 0;
+      }
+  return true;
+}();
+
+T512 void wmds(W& s0, W& s1) {
+  alignas(64) u64 st[16];
+  _mm512_store_si512((void*)st, s0); _mm512_store_si512((void*)(st + 8), s1);
+  W al0 = _mm512_setzero_si512(), al1 = al0, ah0 = al0, ah1 = al0;
+  for (int w = 0; w < 12; w++) {
+    W b = _mm512_set1_epi64((long long)st[w]), bh = _mm512_srli_epi64(b, 32);
+    W c0 = _mm512_load_si512((const void*)CW[w][0]), c1 = _mm512_load_si512((const void*)CW[w][1]);
+    al0 = _mm512_add_epi64(al0, _mm512_mul_epu32(b, c0)); al1 = _mm512_add_epi64(al1, _mm512_mul_epu32(b, c1));
+    ah0 = _mm512_add_epi64(ah0, _mm512_mul_epu32(bh, c0)); ah1 = _mm512_add_epi64(ah1, _mm512_mul_epu32(bh, c1));
+  }
+  W al[2] = {al0, al1}, ah[2] = {ah0, ah1}, out[2];
+  for (int j = 0; j < 2; j++) {   // al + ah * 2^32  (mod p), lazy
+    W a_hi = _mm512_srli_epi64(ah[j], 32);
+    W c = _mm512_sub_epi64(_mm512_slli_epi64(a_hi, 32), a_hi), b = _mm512_slli_epi64(ah[j], 32);
+    W t = _mm512_add_epi64(al[j], c), v = _mm512_add_epi64(b, t);
+    out[j] = _mm512_mask_add_epi64(v, _mm512_cmplt_epu64_mask(v, t), v, wset(EPS));
+  }
+  s0 = out[0]; s1 = out[1];
+}
+
+alignas(64) static u64 RCW[30][16];
+static const bool rcw_ready = [] {
+  for (int r = 0; r < 30; r++)
+    for (int i = 0; i < 16; i++) RCW[r][i] = i < 12 ? RC[12 * r + i] : 0;
+  return true;
+}();
+
+__attribute__((target("avx512f,avx512dq,avx512bw,avx512vl"))) static void permute_avx512(u64 s[12]) {
+  W s0 = _mm512_loadu_si512((const void*)s);
+  W s1 = _mm512_maskz_loadu_epi64(0x0F, (const void*)(s + 8));
+  for (int r = 0; r < 30; r++) {
+    s0 = wadd_lazy(s0, _mm512_load_si512((const void*)RCW[r]));
+    s1 = wadd_lazy(s1, _mm512_load_si512((const void*)(RCW[r] + 8)));
+    if (r < 4 || r >= 26) { s0 = wsbox(s0); s1 = wsbox(s1); }
+    else {
+      u64 x = sbox((u64)_mm_cvtsi128_si64(_mm512_castsi512_si128(s0)));
+      s0 = _mm512_mask_set1_epi64(s0, 0x01, (long long)x);
+    }
+    wmds(s0, s1);
+  }
+  _mm512_storeu_si512((void*)s, s0);
+  _mm512_mask_storeu_epi64((void*)(s + 8), 0x0F, s1);
+  for (int i = 0; i < 12; i++) s[i] -= mask_of(s[i] >= P) & P;
+}
+#endif
+
+// variant: 0 = scalar, 1 = AVX2, 2 = AVX-512 (tests compare them; returns 0 if the CPU lacks the extension)
+extern "C" int sb_host_poseidon_permute_variant(u64 s[12], int variant) {
+#if defined(__x86_64__)
+  if (variant == 2) {
+    if (!(__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512bw") &&
+          __builtin_cpu_supports("avx512vl"))) return 0;
+    permute_avx512(s); return 1;
+  }
+  if (variant == 1) { if (!__builtin_cpu_supports("avx2")) return 0; permute_avx2(s); return 1; }
+#endif
+  if (variant != 0) return 0;
+  permute_scalar(s); return 1;
+}
+
 void sb_host_poseidon_permute(u64 s[12]) {
 #if defined(__x86_64__)
+  static const bool have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") &&
+                                  __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && cw_ready && rcw_ready;
+  if (have_avx512) { permute_avx512(s); return; }
   static const bool have_avx2 = __builtin_cpu_supports("avx2") && cv_ready;
   if (have_avx2) { permute_avx2(s); return; }
 #endif

@@ -64,3 +64,23 @@ def test_proof_layout_matches_oracle_and_survey():
         assert bytes(l) == bytes(ol)
         for r in range(l.n_fri_rounds):
             assert sb.lib().sb_fri_step_path_len(C.byref(l), r) == l.log_lde - 4 * (r + 1) - 4
+
+
+def test_host_transcript_permutation_variants_match_oracle():
+    """The Fiat-Shamir sponge runs on the host (scalar / AVX2 / AVX-512 paths): each must equal the oracle's permutation."""
+    import numpy as np
+    L = sb.lib()
+    L.sb_host_poseidon_permute_variant.argtypes = [C.c_void_p, C.c_int]
+    rng = np.random.default_rng(5)
+    states = [np.zeros(12, np.uint64), np.arange(12, dtype=np.uint64), np.full(12, O.P - 1, np.uint64),
+              np.full(12, 2 ** 64 - 1, np.uint64)] + [rng.integers(0, 2 ** 63, 12, dtype=np.uint64) * np.uint64(2) for _ in range(50)]
+    ran = 0
+    for variant in (0, 1, 2):
+        for st in states:
+            got = st.copy()
+            if not L.sb_host_poseidon_permute_variant(got.ctypes.data_as(C.c_void_p), variant):
+                break
+            want = O.permute(st % np.uint64(O.P))
+            assert np.array_equal(got, want), (variant, st)
+            ran += 1
+    assert ran >= len(states)          # at least the scalar path
