@@ -266,7 +266,7 @@ def main():
             "frac": perms * U32_MACS_PER_PERM / t_hash / 1e9 / imad["mad_lo_u32_gops"],
             # dram__bytes_read.sum + dram__bytes_write.sum of the leaf sponge from the committed ncu --set full capture
             # (profiles/r1_top_kernels_pairing_precomp.txt); algorithmic = 8 C N = 962.6 MB
-            "traffic": 977568000 if args.stark == "pairing_precomp" else None,
+            "traffic": 973794304 if args.stark == "pairing_precomp" else None,
             "peak_source": "sb_measure_imad_peak: dependent-free mad.lo.u32, measured in this run",
             "share_of_step": (kern["leaf_hash"] + kern["merkle"]) / ms_step,
             "stages": {
