@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--stark", default="pairing_precomp", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded-stark", default="final_exp",
+                    help="shape of the second sharded trace commitment (column slices drawn per rank); '' to skip")
     ap.add_argument("--also", default="miller_loop,final_exp",
                     help="N=1 only: further starks proved once each after the headline workload (reported under 'also')")
     args = ap.parse_args()
@@ -228,6 +230,27 @@ def main():
     sh_cap = sh_out[-1]["cap"]
     del sh_out, sh, local
     torch.cuda.empty_cache()
+    # ---- the same sharded commitment on the FinalExp shape (BASELINE configs[3]; throughput-bound, the shape that scales):
+    # every rank draws its own column slice (seed + rank), so no 4.8 GB trace is replicated on the host ----
+    fe = None
+    if args.sharded_stark and args.sharded_stark != args.stark:
+        fi = sb.STARKS[args.sharded_stark]
+        fp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1)
+        fplan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, world)
+        fcg = fplan.col_count[rank]
+        frng = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id + 1000 * rank))
+        flocal = torch.from_numpy(frng.integers(0, 1 << 32, (fcg, fi.num_rows), dtype=np.uint64).view(np.int64)).cuda()
+        fbackend = GpuBackend(ctx, fp)
+        ffn = lambda: commit_sharded(fbackend, fplan, rank, flocal)["cap"]
+        ffn()
+        dt_fe, _ = timed(ffn, max(1, args.steps - 1))
+        fN = fi.num_rows << fi.rate_bits
+        ms_fe = 1e3 * dt_fe / max(1, args.steps - 1)
+        fe = {"workload": WORKLOADS[args.sharded_stark], "ranks": world, "ms": ms_fe,
+              "lde_merkle_gbs": 8.0 * fi.columns * fN / (ms_fe * 1e-3) / 1e9, "a2a_bytes_out_per_rank": fplan.a2a_bytes_out(0),
+              "leaf_hash_ms_rank0": ctx.stage_ms("leaf_hash"), "lde_ms_rank0": ctx.stage_ms("lde")}
+        del flocal, fbackend
+        torch.cuda.empty_cache()
     # ---- two proofs in flight on one GPU (two contexts, two host threads): the host transcript of one proof (a strictly
     # sequential sponge, ~1 us per permutation) overlaps the kernels of the other, as a scheduler for the reference's seven
     # independent proofs would run them ----
@@ -316,7 +339,7 @@ def main():
             "e2e": {"value": ms_e2e / world, "unit": "ms", "h2d_bytes_per_step": 8 * C * n + 8 * info.public_inputs,
                     "d2h_bytes_per_step": proof_bytes},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stage, "kernel_ms": kern, "sharded_commit": sharded, "also": also,
+            "stage_ms": stage, "kernel_ms": kern, "sharded_commit": sharded, "sharded_commit_scaling_shape": fe, "also": also,
             "two_in_flight": {"ms_per_proof": 1e3 * dt_pipe / (2 * args.steps) / world, "proofs": 2 * args.steps * world,
                               "note": "two contexts per GPU, one host thread each: transcript of one proof overlaps kernels of the other"},
         }
