@@ -530,3 +530,99 @@ def fill_trace_fp12_multiplication(tr, x, y, start_row, end_row, col):          
     t5 = fp6_mul(t3, t4); fill_trace_fp6_multiplication(tr, t3, t4, s, e, col + F12.FP12_MUL_T5_CALC_OFFSET)
     t6 = fp6_sub(t5, t0); sub_red6_rows(tr, t5, t0, s, e, col + F12.FP12_MUL_T6_CALC_OFFSET)
     sub_red6_rows(tr, t6, t1, s, e, col + F12.FP12_MUL_Y_CALC_OFFSET)
+
+
+def fill_trace_cyclotomic_sq(tr, x, start_row, end_row, col):                     # fp12.rs:234-332
+    rows = slice(start_row, end_row + 1)
+    tr[rows, col + F12.CYCLOTOMIC_SQ_INPUT_OFFSET:col + F12.CYCLOTOMIC_SQ_INPUT_OFFSET + 144] = _flat(x)
+    tr[rows, col + F12.CYCLOTOMIC_SQ_SELECTOR_OFFSET] = 1
+    tr[end_row, col + F12.CYCLOTOMIC_SQ_SELECTOR_OFFSET] = 0
+    c0c0, c0c1, c0c2, c1c0, c1c1, c1c2 = [(x[2 * i], x[2 * i + 1]) for i in range(6)]
+    s, e = start_row, end_row
+    t0 = fp4_square(c0c0, c1c1); fill_trace_fp4_sq(tr, c0c0, c1c1, s, e, col + F12.CYCLOTOMIC_SQ_T0_CALC_OFFSET)
+    t1 = fp4_square(c1c0, c0c2); fill_trace_fp4_sq(tr, c1c0, c0c2, s, e, col + F12.CYCLOTOMIC_SQ_T1_CALC_OFFSET)
+    t2 = fp4_square(c0c1, c1c2); fill_trace_fp4_sq(tr, c0c1, c1c2, s, e, col + F12.CYCLOTOMIC_SQ_T2_CALC_OFFSET)
+    t3 = fp2_mul_by_nonresidue(t2[1]); nonres_rows(tr, t2[1], s, e, col + F12.CYCLOTOMIC_SQ_T3_CALC_OFFSET)
+
+    def sub_branch(a, b, o_t, o_2, o_c):        # t = a - b ; t' = 2 t ; c = t' + a
+        t = fp2_sub(a, b); sub_red_rows(tr, a, b, s, e, col + o_t)
+        t_2 = fp2_mul_fp(t, 2); fill_trace_fp2_fp_mul(tr, t, 2, s, e, col + o_2)
+        add_red_rows(tr, t_2, a, s, e, col + o_c)
+
+    def add_branch(a, b, o_t, o_2, o_c):        # t = a + b ; t' = 2 t ; c = t' + a
+        t = fp2_add(a, b); add_red_rows(tr, a, b, s, e, col + o_t)
+        t_2 = fp2_mul_fp(t, 2); fill_trace_fp2_fp_mul(tr, t, 2, s, e, col + o_2)
+        add_red_rows(tr, t_2, a, s, e, col + o_c)
+
+    sub_branch(t0[0], c0c0, F12.CYCLOTOMIC_SQ_T4_CALC_OFFSET, F12.CYCLOTOMIC_SQ_T5_CALC_OFFSET, F12.CYCLOTOMIC_SQ_C0_CALC_OFFSET)
+    sub_branch(t1[0], c0c1, F12.CYCLOTOMIC_SQ_T6_CALC_OFFSET, F12.CYCLOTOMIC_SQ_T7_CALC_OFFSET, F12.CYCLOTOMIC_SQ_C1_CALC_OFFSET)
+    sub_branch(t2[0], c0c2, F12.CYCLOTOMIC_SQ_T8_CALC_OFFSET, F12.CYCLOTOMIC_SQ_T9_CALC_OFFSET, F12.CYCLOTOMIC_SQ_C2_CALC_OFFSET)
+    add_branch(t3, c1c0, F12.CYCLOTOMIC_SQ_T10_CALC_OFFSET, F12.CYCLOTOMIC_SQ_T11_CALC_OFFSET, F12.CYCLOTOMIC_SQ_C3_CALC_OFFSET)
+    add_branch(t0[1], c1c1, F12.CYCLOTOMIC_SQ_T12_CALC_OFFSET, F12.CYCLOTOMIC_SQ_T13_CALC_OFFSET, F12.CYCLOTOMIC_SQ_C4_CALC_OFFSET)
+    add_branch(t1[1], c1c2, F12.CYCLOTOMIC_SQ_T14_CALC_OFFSET, F12.CYCLOTOMIC_SQ_T15_CALC_OFFSET, F12.CYCLOTOMIC_SQ_C5_CALC_OFFSET)
+
+
+def fill_trace_cyclotomic_exp(tr, x, start_row, end_row, col):                    # fp12.rs:335-375
+    rows = slice(start_row, end_row + 1)
+    tr[rows, col + F12.INPUT_OFFSET:col + F12.INPUT_OFFSET + 144] = _flat(x)
+    tr[rows, col + F12.CYCLOTOMIC_EXP_SELECTOR_OFFSET] = 1
+    tr[end_row, col + F12.CYCLOTOMIC_EXP_SELECTOR_OFFSET] = 0
+    tr[start_row, col + F12.CYCLOTOMIC_EXP_START_ROW] = 1
+    z = (1,) + (0,) * 11
+    i = BLS_X.bit_length() - 1
+    bitone = False
+    assert end_row + 1 - start_row == 70 * 12 + 1
+    for j in range(70):
+        s_row = start_row + j * 12
+        e_row = s_row + 11
+        blk = slice(s_row, e_row + 1)
+        if bitone:
+            tr[blk, col + F12.BIT1_SELECTOR_OFFSET] = 1
+        tr[blk, col + F12.Z_OFFSET:col + F12.Z_OFFSET + 144] = _flat(z)
+        tr[s_row, col + F12.FIRST_ROW_SELECTOR_OFFSET] = 1
+        if bitone:
+            fill_trace_fp12_multiplication(tr, z, x, s_row, e_row, col + F12.Z_MUL_INPUT_OFFSET)
+            z = fp12_mul(z, x)
+        else:
+            fill_trace_cyclotomic_sq(tr, z, s_row, e_row, col + F12.Z_CYCLOTOMIC_SQ_OFFSET)
+            z = fp12_cyclotomic_square(z)
+        if ((BLS_X >> i) & 1) and not bitone:
+            bitone = True
+        elif j < 69:
+            i -= 1
+            bitone = False
+    tr[start_row + 70 * 12, col + F12.RES_ROW_SELECTOR_OFFSET] = 1
+    tr[start_row + 70 * 12, col + F12.Z_OFFSET:col + F12.Z_OFFSET + 144] = _flat(z)
+    return z
+
+
+def fill_trace_fp12_forbenius_map(tr, x, pw, start_row, end_row, col):            # fp12.rs:378-411
+    div, rem = pw // 12, pw % 12
+    rows = slice(start_row, end_row + 1)
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_INPUT_OFFSET:col + F12.FP12_FORBENIUS_MAP_INPUT_OFFSET + 144] = _flat(x)
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_SELECTOR_OFFSET] = 1
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_POW_OFFSET] = pw
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_DIV_OFFSET] = div
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_REM_OFFSET] = rem
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_BIT0_OFFSET] = rem & 1
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_BIT1_OFFSET] = (rem >> 1) & 1
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_BIT2_OFFSET] = (rem >> 2) & 1
+    tr[rows, col + F12.FP12_FORBENIUS_MAP_BIT3_OFFSET] = rem >> 3
+    tr[end_row, col + F12.FP12_FORBENIUS_MAP_SELECTOR_OFFSET] = 0
+    r0, r1 = tuple(x[:6]), tuple(x[6:])
+    s, e = start_row, end_row
+    fill_trace_fp6_forbenius_map(tr, r0, pw, s, e, col + F12.FP12_FORBENIUS_MAP_R0_CALC_OFFSET)
+    c0, c1, c2 = fp6_parts(fp6_frobenius(r1, pw))
+    fill_trace_fp6_forbenius_map(tr, r1, pw, s, e, col + F12.FP12_FORBENIUS_MAP_C0C1C2_CALC_OFFSET)
+    k = FP12_FROB[pw % 12]
+    generate_trace_fp2_mul(tr, c0, k, s, e, col + F12.FP12_FORBENIUS_MAP_C0_CALC_OFFSET)
+    generate_trace_fp2_mul(tr, c1, k, s, e, col + F12.FP12_FORBENIUS_MAP_C1_CALC_OFFSET)
+    generate_trace_fp2_mul(tr, c2, k, s, e, col + F12.FP12_FORBENIUS_MAP_C2_CALC_OFFSET)
+
+
+def fill_trace_fp12_conjugate(tr, x, row, col):                                   # fp12.rs:414-426
+    put(tr, row, col + F12.FP12_CONJUGATE_INPUT_OFFSET, _flat(x))
+    conj = tuple(x[:6]) + tuple(fp_neg(a) for a in x[6:])
+    put(tr, row, col + F12.FP12_CONJUGATE_OUTPUT_OFFSET, _flat(conj))
+    fill_trace_addition_fp6(tr, tuple(x[6:]), tuple(conj[6:]), row, col + F12.FP12_CONJUGATE_ADDITIION_OFFSET)
+    return conj

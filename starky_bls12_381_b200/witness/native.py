@@ -209,3 +209,134 @@ def fp12_cyclotomic_square(x):   # native.rs:1254-1298
     c4 = fp2_add(two(fp2_add(t0[1], c1c1)), t0[1])
     c5 = fp2_add(two(fp2_add(t1[1], c1c2)), t1[1])
     return c0 + c1 + c2 + c3 + c4 + c5
+
+
+def fp12_cyclotomic_exponent(x):  # native.rs:1300-1309
+    z = FP12_ONE
+    for i in reversed(range(BLS_X.bit_length())):
+        z = fp12_cyclotomic_square(z)
+        if (BLS_X >> i) & 1:
+            z = fp12_mul(z, x)
+    return z
+
+
+def fp12_final_exponentiate(x):  # native.rs:1311-1345
+    t0 = fp12_frobenius(x, 6)
+    t1 = fp12_mul(t0, fp12_inv(x))
+    t2 = fp12_frobenius(t1, 2)
+    t3 = fp12_mul(t2, t1)
+    t4 = fp12_cyclotomic_exponent(t3)
+    t5 = fp12_conjugate(t4)
+    t6 = fp12_cyclotomic_square(t3)
+    t7 = fp12_conjugate(t6)
+    t8 = fp12_mul(t7, t5)
+    t9 = fp12_cyclotomic_exponent(t8)
+    t10 = fp12_conjugate(t9)
+    t11 = fp12_cyclotomic_exponent(t10)
+    t12 = fp12_conjugate(t11)
+    t13 = fp12_cyclotomic_exponent(t12)
+    t14 = fp12_conjugate(t13)
+    t15 = fp12_cyclotomic_square(t5)
+    t16 = fp12_mul(t14, t15)
+    t17 = fp12_cyclotomic_exponent(t16)
+    t18 = fp12_conjugate(t17)
+    t19 = fp12_mul(t5, t12)
+    t20 = fp12_frobenius(t19, 2)
+    t21 = fp12_mul(t10, t3)
+    t22 = fp12_frobenius(t21, 3)
+    t23 = fp12_conjugate(t3)
+    t24 = fp12_mul(t16, t23)
+    t25 = fp12_frobenius(t24, 1)
+    t26 = fp12_conjugate(t8)
+    t27 = fp12_mul(t18, t26)
+    t28 = fp12_mul(t27, t3)
+    t29 = fp12_mul(t20, t22)
+    t30 = fp12_mul(t29, t25)
+    return fp12_mul(t30, t28)
+
+
+HALF = pow(2, -1, P)
+
+
+def calc_precomp_stuff_loop0(rx, ry, rz):   # native.rs:291-327 (same values as one doubling step of calc_pairing_precomp)
+    t0 = fp2_mul(ry, ry)
+    t1 = fp2_mul(rz, rz)
+    x0 = fp2_mul_fp(t1, 3)
+    t2 = fp2_multiply_by_b(x0)
+    t3 = fp2_mul_fp(t2, 3)
+    x1 = fp2_mul(ry, rz)
+    t4 = fp2_mul_fp(x1, 2)
+    x2 = fp2_sub(t2, t0)
+    x3 = fp2_mul(rx, rx)
+    x4 = fp2_mul_fp(x3, 3)
+    x5 = fp2_neg(t4)
+    x6 = fp2_sub(t0, t3)
+    x7 = fp2_mul(rx, ry)
+    x8 = fp2_mul(x6, x7)
+    x9 = fp2_add(t0, t3)
+    x10 = fp2_mul_fp(x9, HALF)
+    x11 = fp2_mul(x10, x10)
+    x12 = fp2_mul(t2, t2)
+    x13 = fp2_mul_fp(x12, 3)
+    new_rx = fp2_mul_fp(x8, HALF)
+    new_ry = fp2_sub(x11, x13)
+    new_rz = fp2_mul(t0, t4)
+    return [new_rx, new_ry, new_rz, t0, t1, x0, t2, t3, x1, t4, x3, x2, x4, x5, x6, x7, x8, x9, x10, x11, x12, x13]
+
+
+def calc_precomp_stuff_loop1(rx, ry, rz, qx, qy):   # native.rs:329-372
+    t0 = fp2_mul(qy, rz)
+    t1 = fp2_sub(ry, t0)
+    t2 = fp2_mul(qx, rz)
+    t3 = fp2_sub(rx, t2)
+    t4 = fp2_mul(t1, qx)
+    t5 = fp2_mul(t3, qy)
+    t6 = fp2_sub(t4, t5)
+    t7 = fp2_neg(t1)
+    t8 = fp2_mul(t3, t3)
+    t9 = fp2_mul(t8, t3)
+    t10 = fp2_mul(t8, rx)
+    t11 = fp2_mul(t1, t1)
+    t12 = fp2_mul(t11, rz)
+    t13 = fp2_mul_fp(t10, 2)
+    t14 = fp2_sub(t9, t13)
+    t15 = fp2_add(t14, t12)
+    t16 = fp2_sub(t10, t15)
+    t17 = fp2_mul(t16, t1)
+    t18 = fp2_mul(t9, ry)
+    new_rx = fp2_mul(t3, t15)
+    new_ry = fp2_sub(t17, t18)
+    new_rz = fp2_mul(rz, t9)
+    return [new_rx, new_ry, new_rz, t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18]
+
+
+def calc_pairing_precomp(x, y, z):   # native.rs:1358-1437
+    zi = fp2_inv(z)
+    qx, qy = fp2_mul(x, zi), fp2_mul(y, zi)
+    rx, ry, rz = qx, qy, (1, 0)
+    ell = []
+    for i in reversed(range(BLS_X.bit_length() - 1)):
+        v = calc_precomp_stuff_loop0(rx, ry, rz)
+        ell.append((v[11], v[12], v[13]))       # x2, x4, x5
+        rx, ry, rz = v[0], v[1], v[2]
+        if (BLS_X >> i) & 1:
+            w = calc_precomp_stuff_loop1(rx, ry, rz, qx, qy)
+            ell.append((w[9], w[10], w[6]))     # bit1_t6, bit1_t7, bit1_t3
+            rx, ry, rz = w[0], w[1], w[2]
+    return ell
+
+
+def miller_loop(px, py, qx, qy, qz):   # native.rs:1440-1466
+    pre = calc_pairing_precomp(qx, qy, qz)
+    f12, j = FP12_ONE, 0
+    for i in reversed(range(BLS_X.bit_length() - 1)):
+        e = pre[j]
+        f12 = fp12_multiply_by_014(f12, e[0], fp2_mul_fp(e[1], px), fp2_mul_fp(e[2], py))
+        if (BLS_X >> i) & 1:
+            j += 1
+            e = pre[j]
+            f12 = fp12_multiply_by_014(f12, e[0], fp2_mul_fp(e[1], px), fp2_mul_fp(e[2], py))
+        if i != 0:
+            f12 = fp12_mul(f12, f12)
+        j += 1
+    return fp12_conjugate(f12)
