@@ -7,9 +7,11 @@ by the tests and bench.py; it never computes anything itself and fails loudly wh
 """
 from .binding import (Params, ProofLayout, Proof, Context, StarkId, TraceLayout, Flags, lib, lib_path,  # noqa: F401
                       standard_params, SbError)
-from .api import StarkConfig, STARKS, prove  # noqa: F401
+from .api import (StarkConfig, STARKS, prove, FP12MulStark, PairingPrecompStark, MillerLoopStark,  # noqa: F401
+                  FinalExponentiateStark, ECCAggStark)
 from .sharded import ShardPlan, shard_plan, commit_sharded, GpuBackend  # noqa: F401
 
 __all__ = ["Params", "ProofLayout", "Proof", "Context", "StarkId", "TraceLayout", "Flags", "lib", "lib_path",
-           "standard_params", "SbError", "StarkConfig", "STARKS", "prove", "ShardPlan", "shard_plan", "commit_sharded",
+           "standard_params", "SbError", "StarkConfig", "STARKS", "prove", "FP12MulStark", "PairingPrecompStark", "MillerLoopStark",
+           "FinalExponentiateStark", "ECCAggStark", "ShardPlan", "shard_plan", "commit_sharded",
            "GpuBackend"]

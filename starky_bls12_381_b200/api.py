@@ -68,3 +68,61 @@ def prove(ctx, stark, config, trace_poly_values, public_inputs, num_rows=None, f
     """starky::prover::prove(stark, &config, trace_poly_values, &public_inputs, &mut timing) on the GPU of `ctx`."""
     p = params_for(stark, config, num_rows, flags)
     return ctx.prove(p, trace_poly_values, public_inputs, layout)
+
+
+class _Stark:
+    """`XStark::<F, D>::new(num_rows)` + `generate_trace(...)`.  generate_trace returns what
+    `trace_rows_to_poly_values(stark.generate_trace(...))` yields in the reference (column-major uint64 [COLUMNS, rows]);
+    `public_inputs(...)` assembles the vector the reference's *_main functions build (aggregate_proof.rs:24-227)."""
+    name = None
+
+    def __init__(self, num_rows=None):
+        self.info = STARKS[self.name]
+        self.num_rows = num_rows or self.info.num_rows
+
+    @classmethod
+    def new(cls, num_rows):
+        return cls(num_rows)
+
+    def constraint_degree(self):
+        return self.info.constraint_degree
+
+
+class FP12MulStark(_Stark):
+    name = "fp12_mul"
+
+    def generate_trace(self, x, y):                 # fp12_mul.rs:44-48
+        from . import witness
+        return witness.fp12_mul_trace(x, y, self.num_rows)
+
+
+class PairingPrecompStark(_Stark):
+    name = "pairing_precomp"
+
+    def generate_trace(self, x, y, z):              # calc_pairing_precomp.rs:150
+        from . import witness
+        return witness.pairing_precomp_trace(x, y, z, self.num_rows)
+
+
+class MillerLoopStark(_Stark):
+    name = "miller_loop"
+
+    def generate_trace(self, x, y, q):              # miller_loop.rs:157 (ell_coeffs derived from the G2 point q)
+        from . import witness
+        return witness.miller_loop_trace(x, y, q, self.num_rows)
+
+
+class FinalExponentiateStark(_Stark):
+    name = "final_exp"
+
+    def generate_trace(self, x):                    # final_exponentiate.rs:246
+        from . import witness
+        return witness.final_exp_trace(x, self.num_rows)
+
+
+class ECCAggStark(_Stark):
+    name = "ecc_agg"
+
+    def generate_trace(self, points, bits):         # ecc_aggregate.rs:37
+        from . import witness
+        return witness.ecc_aggregate_trace(points, bits, self.num_rows)[:2]

@@ -199,3 +199,199 @@ def final_exp_trace(x, num_rows=8192):
     pis = np.array(_flat(x) + _flat(t31), dtype=np.uint64)
     assert pis.size == E.PUBLIC_INPUTS
     return np.ascontiguousarray(tr.T), pis
+
+
+_PP = NS("calc_pairing_precomp")
+
+
+def pairing_precomp_trace(x, y, z, num_rows=1024):
+    """PairingPrecompStark::generate_trace (calc_pairing_precomp.rs:150-366) + calc_pairing_precomp_main's public inputs
+    (aggregate_proof.rs:24-69).  x, y, z: the projective G2 point (Fp2 each)."""
+    from .fills import (add_red_rows, fill_multiply_by_b_trace, fill_trace_fp2_fp_mul, fill_trace_negate_fp2,
+                        generate_trace_fp2_mul, sub_red_rows, _rep, F2)
+    A = _PP
+    tr = np.zeros((num_rows, A.TOTAL_COLUMNS), dtype=np.uint64)
+    z_inv = N.fp2_inv(z)
+    generate_trace_fp2_mul(tr, z, z_inv, 0, num_rows - 1, A.Z_MULT_Z_INV_OFFSET)
+    generate_trace_fp2_mul(tr, x, z_inv, 0, num_rows - 1, A.X_MULT_Z_INV_OFFSET)
+    generate_trace_fp2_mul(tr, y, z_inv, 0, num_rows - 1, A.Y_MULT_Z_INV_OFFSET)
+    qx, qy, qz = N.fp2_mul(x, z_inv), N.fp2_mul(y, z_inv), (1, 0)          # calc_qs (native.rs:277-286)
+    tr[:, A.QX_OFFSET:A.QX_OFFSET + 24] = _flat(qx)
+    tr[:, A.QY_OFFSET:A.QY_OFFSET + 24] = _flat(qy)
+    tr[:, A.QZ_OFFSET:A.QZ_OFFSET + 24] = _flat(qz)
+    rx, ry, rz = qx, qy, qz
+    bit_pos, bit1, num_coeffs = 62, False, 68
+
+    def negate_rows(v, s, e, col):
+        fill_trace_negate_fp2(tr, v, s, col)
+        _rep(tr, s, e, col, F2.FP2_ADDITION_TOTAL)
+
+    for n in range(num_rows // 12 + 1):
+        s, end_row = n * 12, (n + 1) * 12
+        blk = slice(s, min(end_row, num_rows))
+        if n == 0:
+            tr[blk, A.FIRST_LOOP_SELECTOR_OFFSET] = 1
+        tr[blk, A.RX_OFFSET:A.RX_OFFSET + 24] = _flat(rx)
+        tr[blk, A.RY_OFFSET:A.RY_OFFSET + 24] = _flat(ry)
+        tr[blk, A.RZ_OFFSET:A.RZ_OFFSET + 24] = _flat(rz)
+        if bit1:
+            tr[blk, A.BIT1_SELECTOR_OFFSET] = 1
+        if n < num_coeffs:
+            tr[blk, A.ELL_COEFFS_IDX_OFFSET + n] = 1
+        tr[s, A.FIRST_ROW_SELECTOR_OFFSET] = 1
+        if end_row > num_rows:
+            break
+        e = end_row - 1
+        if not bit1:
+            v = N.calc_precomp_stuff_loop0(rx, ry, rz)
+            generate_trace_fp2_mul(tr, ry, ry, s, e, A.T0_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, rz, rz, s, e, A.T1_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, v[4], 3, s, e, A.X0_CALC_OFFSET)
+            fill_multiply_by_b_trace(tr, v[5], s, e, A.T2_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, v[6], 3, s, e, A.T3_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, ry, rz, s, e, A.X1_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, v[8], 2, s, e, A.T4_CALC_OFFSET)
+            sub_red_rows(tr, v[6], v[3], s, e, A.X2_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, rx, rx, s, e, A.X3_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, v[10], 3, s, e, A.X4_CALC_OFFSET)
+            negate_rows(v[9], s, e, A.X5_CALC_OFFSET)
+            sub_red_rows(tr, v[3], v[7], s, e, A.X6_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, rx, ry, s, e, A.X7_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, v[14], v[15], s, e, A.X8_CALC_OFFSET)
+            add_red_rows(tr, v[3], v[7], s, e, A.X9_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, v[17], N.HALF, s, e, A.X10_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, v[18], v[18], s, e, A.X11_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, v[6], v[6], s, e, A.X12_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, v[20], 3, s, e, A.X13_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, v[16], N.HALF, s, e, A.NEW_RX_OFFSET)
+            sub_red_rows(tr, v[19], v[21], s, e, A.NEW_RY_OFFSET)
+            generate_trace_fp2_mul(tr, v[3], v[9], s, e, A.NEW_RZ_OFFSET)
+            rx, ry, rz = v[0], v[1], v[2]
+            bit1 = bool((N.BLS_X >> bit_pos) & 1)
+            bit_pos = bit_pos if bit1 else max(bit_pos - 1, 0)
+        else:
+            w = N.calc_precomp_stuff_loop1(rx, ry, rz, qx, qy)
+            generate_trace_fp2_mul(tr, qy, rz, s, e, A.BIT1_T0_CALC_OFFSET)
+            sub_red_rows(tr, ry, w[3], s, e, A.BIT1_T1_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, qx, rz, s, e, A.BIT1_T2_CALC_OFFSET)
+            sub_red_rows(tr, rx, w[5], s, e, A.BIT1_T3_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[4], qx, s, e, A.BIT1_T4_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[6], qy, s, e, A.BIT1_T5_CALC_OFFSET)
+            sub_red_rows(tr, w[7], w[8], s, e, A.BIT1_T6_CALC_OFFSET)
+            negate_rows(w[4], s, e, A.BIT1_T7_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[6], w[6], s, e, A.BIT1_T8_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[11], w[6], s, e, A.BIT1_T9_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[11], rx, s, e, A.BIT1_T10_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[4], w[4], s, e, A.BIT1_T11_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[14], rz, s, e, A.BIT1_T12_CALC_OFFSET)
+            fill_trace_fp2_fp_mul(tr, w[13], 2, s, e, A.BIT1_T13_CALC_OFFSET)
+            sub_red_rows(tr, w[12], w[16], s, e, A.BIT1_T14_CALC_OFFSET)
+            add_red_rows(tr, w[17], w[15], s, e, A.BIT1_T15_CALC_OFFSET)
+            sub_red_rows(tr, w[13], w[18], s, e, A.BIT1_T16_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[19], w[4], s, e, A.BIT1_T17_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[12], ry, s, e, A.BIT1_T18_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, w[6], w[18], s, e, A.BIT1_RX_CALC_OFFSET)
+            sub_red_rows(tr, w[20], w[21], s, e, A.BIT1_RY_CALC_OFFSET)
+            generate_trace_fp2_mul(tr, rz, w[12], s, e, A.BIT1_RZ_CALC_OFFSET)
+            rx, ry, rz = w[0], w[1], w[2]
+            bit1 = False
+            bit_pos = max(bit_pos - 1, 0)
+    pi = _flat(x) + _flat(y) + _flat(z)
+    for cs in N.calc_pairing_precomp(x, y, z):
+        for f2 in cs:
+            pi += _flat(f2)
+    pis = np.array(pi, dtype=np.uint64)
+    assert pis.size == A.PUBLIC_INPUTS
+    return np.ascontiguousarray(tr.T), pis
+
+
+_EC = NS("ecc_aggregate")
+_G1 = NS("g1")
+
+
+def fill_trace_g1_addition(tr, pt1, pt2, start_row, col):
+    """g1.rs:26-255: chord addition of two affine points, x3 = l^2 - x2 - x1, y3 = l (x1 - x3) - y1."""
+    from .fills import (F, fill_multiplication_trace_no_mod_reduction, fill_range_check_trace, fill_reduction_trace,
+                        fill_trace_addition_fp, fill_trace_subtraction_fp, _rep)
+    G, P = _G1, N.P
+    x1, y1, x2, y2 = pt1[0], pt1[1], pt2[0], pt2[1]
+    lam = N.fp_mul(N.fp_sub(y2, y1), N.fp_inv(N.fp_sub(x2, x1)))
+    x3 = N.fp_sub(N.fp_sub(N.fp_mul(lam, lam), x2), x1)
+    y3 = N.fp_sub(N.fp_mul(lam, N.fp_sub(x1, x3)), y1)
+    s, e = start_row, start_row + 11
+    tr[s:e + 1, col + G.G1_POINT_ADDITION_X1:col + G.G1_POINT_ADDITION_X1 + 72] = _flat((x1, y1, x2, y2, x3, y3))
+    MULW = F.FP_MULTIPLICATION_TOTAL_COLUMNS
+
+    def add_rows(a, b, c):
+        fill_trace_addition_fp(tr, a, b, s, c)
+        _rep(tr, s, e, c, F.FP_ADDITION_TOTAL)
+
+    def sub_rows(a, b, c):
+        fill_trace_subtraction_fp(tr, a, b, s, c)
+        _rep(tr, s, e, c, F.FP_SUBTRACTION_TOTAL)
+
+    def mul_red(a, b, c):
+        fill_multiplication_trace_no_mod_reduction(tr, a, b, s, e, c)
+        res = fill_reduction_trace(tr, a * b, s, e, c + MULW)
+        fill_range_check_trace(tr, res, e, c + MULW + F.REDUCTION_TOTAL)
+        return res
+
+    add_rows(x2, P, col + G.X2_X1_DIFF)
+    x2_x1 = x2 + P - x1
+    sub_rows(x2 + P, x1, col + G.X2_X1_DIFF + F.FP_ADDITION_TOTAL)
+    add_rows(y2, P, col + G.Y2_Y1_DIFF)
+    y2_y1 = y2 + P - y1
+    sub_rows(y2 + P, y1, col + G.Y2_Y1_DIFF + F.FP_ADDITION_TOTAL)
+    x2_x1_sq = mul_red(x2_x1, x2_x1, col + G.X2_X1_SQ)
+    y2_y1_sq = mul_red(y2_y1, y2_y1, col + G.Y2_Y1_SQ)
+    add_rows(x1, x2, col + G.X1_X2_X3_SUM)
+    add_rows(x1 + x2, x3, col + G.X1_X2_X3_SUM + F.FP_ADDITION_TOTAL)
+    lhs = mul_red(x1 + x2 + x3, x2_x1_sq, col + G.X1_X2_X3_X2_X1_SQ)
+    assert lhs == y2_y1_sq
+    add_rows(y1, y3, col + G.Y1_Y3)
+    add_rows(x1, P, col + G.X1_X3)
+    x1_x3 = x1 + P - x3
+    sub_rows(x1 + P, x3, col + G.X1_X3 + F.FP_ADDITION_TOTAL)
+    a = mul_red(y1 + y3, x2_x1, col + G.Y1_Y3_X2_X1)
+    b = mul_red(y2_y1, x1_x3, col + G.Y2_Y1_X1_X3)
+    assert a == b
+    return (x3, y3)
+
+
+def ecc_aggregate_trace(points, bits, num_rows=8192):
+    """ECCAggStark::generate_trace (ecc_aggregate.rs:37-82) + ec_aggregate_main's public inputs
+    (aggregate_proof.rs:186-227).  points: 512 affine G1 points (x, y); bits: 512 participation bits."""
+    E = _EC
+    assert len(points) == E.NUM_POINTS == len(bits)
+    assert (len(points) - 1) * 12 < num_rows, "stark doesn't have enough rows"
+    tr = np.zeros((num_rows, E.TOTAL_COLUMNS), dtype=np.uint64)
+    idx = np.arange(num_rows)
+    tr[idx, E.ROW_NUM + idx % 12] = 1
+    row = 0
+    for i in range(E.NUM_POINTS):
+        if i >= 2:
+            row += 12
+        tr[row:row + 12, E.PIS_IDX + i] = 1
+    row = 0
+    res = fill_trace_g1_addition(tr, points[0], points[1], row, E.OP)
+    tr[row:row + 12, E.A_IS_INF] = int(not bits[0])
+    tr[row:row + 12, E.B_IS_INF] = int(not bits[1])
+    if not bits[0]:
+        res = points[1]
+    elif not bits[1]:
+        res = points[0]
+    for i in range(2, E.NUM_POINTS):
+        row += 12
+        tmp = fill_trace_g1_addition(tr, res, points[i], row, E.OP)
+        tr[row:row + 12, E.A_IS_INF] = 0
+        tr[row:row + 12, E.B_IS_INF] = int(not bits[i])
+        if bits[i]:
+            res = tmp
+    pi = []
+    for pt in points:
+        pi += limbs(pt[0]) + limbs(pt[1])
+    pi += [int(b) for b in bits]
+    pi += limbs(res[0]) + limbs(res[1])
+    pis = np.array(pi, dtype=np.uint64)
+    assert pis.size == E.PUBLIC_INPUTS
+    return np.ascontiguousarray(tr.T), pis, res
