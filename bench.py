@@ -217,17 +217,29 @@ def main():
     dt_e2e, proofs_e2e = timed(e2e_fn, args.steps)
     # ---- ONE trace commitment sharded over all ranks (column-sharded LDE -> all-to-all -> row-sharded leaf
     # hashing -> digest all-gather -> tree), the LDE+Merkle GB/s half of BASELINE.json's metric ----
-    from starky_bls12_381_b200.sharded import GpuBackend, commit_sharded, shard_plan
+    from starky_bls12_381_b200.sharded import GpuBackend, commit_sharded, quotient_sharded, shard_plan
     plan = shard_plan(C, info.num_rows.bit_length() - 1, info.rate_bits, world)
     base_trace = trace if rank == 0 else synthetic(info, 0xB2000000 + info.stark_id)[0]
     c0, cg = plan.col_start[rank], plan.col_count[rank]
     local = torch.from_numpy(np.ascontiguousarray(base_trace[c0:c0 + cg]).view(np.int64)).cuda()
     backend = GpuBackend(ctx, p)
-    sharded_fn = lambda: commit_sharded(backend, plan, rank, local)
+    pis0 = pis if rank == 0 else np.random.Generator(np.random.PCG64(7)).integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
+    if world > 1:                      # every rank must evaluate with rank 0's public inputs
+        t_pis = torch.from_numpy(pis0.view(np.int64).copy()).cuda()
+        dist.broadcast(t_pis, 0)
+        pis0 = t_pis.cpu().numpy().view(np.uint64).copy()
+
+    def sharded_fn():
+        out = commit_sharded(backend, plan, rank, local)
+        out["quotient"] = quotient_sharded(backend, plan, rank, out["rows"], out["cap"], pis0)
+        return out
     for _ in range(args.warmup):
         sh = sharded_fn()
     dt_sh, sh_out = timed(sharded_fn, args.steps)
     sh_cap = sh_out[-1]["cap"]
+    sh_q = sh_out[-1]["quotient"]["q"].cpu().numpy().view(np.uint64).copy()
+    sh_q_ms = ctx.stage_ms("quotient")
+    sh_out_alphas = sh_out[-1]["quotient"]["alphas"]
     del sh_out, sh, local
     torch.cuda.empty_cache()
     # ---- the same sharded commitment on the FinalExp shape (BASELINE configs[3]; throughput-bound, the shape that scales):
@@ -241,14 +253,23 @@ def main():
         frng = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id + 1000 * rank))
         flocal = torch.from_numpy(frng.integers(0, 1 << 32, (fcg, fi.num_rows), dtype=np.uint64).view(np.int64)).cuda()
         fbackend = GpuBackend(ctx, fp)
-        ffn = lambda: commit_sharded(fbackend, fplan, rank, flocal)["cap"]
+        airfiles.air_path(args.sharded_stark, "airbin")
+        fpis = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
+
+        def ffn():
+            out = commit_sharded(fbackend, fplan, rank, flocal)
+            qq = quotient_sharded(fbackend, fplan, rank, out["rows"], out["cap"], fpis)
+            return out["cap"], qq["q"][:, :4]
         ffn()
         dt_fe, _ = timed(ffn, max(1, args.steps - 1))
         fN = fi.num_rows << fi.rate_bits
         ms_fe = 1e3 * dt_fe / max(1, args.steps - 1)
         fe = {"workload": WORKLOADS[args.sharded_stark], "ranks": world, "ms": ms_fe,
               "lde_merkle_gbs": 8.0 * fi.columns * fN / (ms_fe * 1e-3) / 1e9, "a2a_bytes_out_per_rank": fplan.a2a_bytes_out(0),
-              "leaf_hash_ms_rank0": ctx.stage_ms("leaf_hash"), "lde_ms_rank0": ctx.stage_ms("lde")}
+              "leaf_hash_ms_rank0": ctx.stage_ms("leaf_hash"), "lde_ms_rank0": ctx.stage_ms("lde"),
+              "quotient_ms_rank0": ctx.stage_ms("quotient"),
+              "note": "column-sharded LDE -> all-to-all -> row-sharded leaf hashing -> digest all-gather -> tree -> alphas -> "
+                      "halo row exchange -> row-sharded quotient -> all-gather of the 2 x N quotient values"}
         del flocal, fbackend
         torch.cuda.empty_cache()
     # ---- two proofs in flight on one GPU (two contexts, two host threads): the host transcript of one proof (a strictly
@@ -316,10 +337,16 @@ def main():
             cpu = {"value": cpu_ms, "unit": "ms", "cores": int(O.lib().orc_num_threads()), "kind": "port",
                    "sample": "one full proof of the same trace", "proof_bit_identical_to_gpu": same}
         ms_sh = 1e3 * dt_sh / args.steps
+        from helpers import pos_to_natural
+        ctx.lde_commit(p, trace, want_lde=False, want_digests=False)
+        q_one = ctx.quotient_values(p, pis0, sh_out_alphas)[:, pos_to_natural(p.log_n, p.rate_bits)]
+        sh_q_same = bool(np.array_equal(q_one, sh_q))
         sharded = {"ms": ms_sh, "lde_merkle_gbs": 8.0 * C * N / (ms_sh * 1e-3) / 1e9, "ranks": world,
                    "a2a_bytes_out_per_rank": plan.a2a_bytes_out(0), "digest_allgather_bytes": 32 * N,
                    "cap_equals_single_gpu_path": bool(np.array_equal(sh_cap, proofs[0].words[:4 * (1 << p.cap_height)].reshape(-1, 4))),
-                   "note": "one trace, columns sharded for K1, rows sharded for K2, NCCL all-to-all + all-gather in the timed region"}
+                   "quotient_ms_rank0": sh_q_ms, "quotient_equals_single_gpu_path": sh_q_same,
+                   "note": "one trace, columns sharded for K1, rows sharded for K2 and K4 (quotient), NCCL all-to-all + "
+                           "all-gathers (digests, halo rows, quotient values) in the timed region"}
         also = {}
         if world == 1 and args.also:
             for name in [x for x in args.also.split(",") if x and x != args.stark]:

@@ -170,6 +170,15 @@ int sb_lde_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_trace,
                        uint32_t n_row_blocks, uint64_t* d_coeffs_out /* optional */, uint64_t* d_lde_out);
 int sb_hash_rows_device(sb_ctx* ctx, const uint64_t* d_cols, uint32_t leaf_len, uint32_t n_leaves, uint64_t* d_digests);
 int sb_merkle_from_position_digests(sb_ctx* ctx, const sb_params* p, const uint64_t* d_digests_pos, uint64_t* cap_out);
+/*      Phase 2 continued: the quotient values q_j(x) (j < 2) of this rank's row block: d_rows = [n_cols][rows_per_block]
+ *        holding LDE positions block_index * rows_per_block ..., d_halo_next_row = the n_cols values of the row after
+ *        the block's last position when that row lives on another rank (rows_per_block < n; NULL otherwise),
+ *        d_out = [2][rows_per_block] on the device (this rank's share of starky::prover::compute_quotient_polys).
+ *        sb_transcript_alphas: observe the gathered trace cap, draw the alphas (every rank gets the same values). */
+int sb_quotient_rows_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_rows, uint32_t rows_per_block,
+                            uint32_t block_index, const uint64_t* d_halo_next_row, const uint64_t* public_inputs,
+                            const uint64_t* alphas, uint64_t* d_out);
+int sb_transcript_alphas(const uint64_t* trace_cap, uint32_t cap_len, uint32_t num_challenges, uint64_t* alphas_out);
 int sb_synchronize(sb_ctx* ctx);
 
 /* The host-side transcript permutation (plonky2 Challenger, run between kernels): variant 0 = portable scalar,

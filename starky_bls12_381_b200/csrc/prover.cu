@@ -108,6 +108,16 @@ struct HostChallenger {
   e2_t ext_challenge() { u64 a = challenge(); u64 b = challenge(); return e2_make(a, b); }
 };
 
+// The first step of the transcript, for callers that run the stages themselves (the sharded path: every rank derives
+// the same alphas from the gathered cap): observe the trace cap, draw `num_challenges` challenges.
+extern "C" int sb_transcript_alphas(const uint64_t* trace_cap, uint32_t cap_len, uint32_t num_challenges, uint64_t* alphas_out) {
+  if (!trace_cap || !alphas_out || !cap_len || num_challenges > 8) return SB_EINVAL;
+  HostChallenger ch;
+  ch.observe_many(trace_cap, 4ull * cap_len);
+  for (uint32_t j = 0; j < num_challenges; j++) alphas_out[j] = ch.challenge();
+  return SB_OK;
+}
+
 struct Arena {
   char* base; size_t off = 0, cap;
   Arena(void* b, size_t c) : base((char*)b), cap(c) {}

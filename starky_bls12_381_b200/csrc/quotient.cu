@@ -203,23 +203,30 @@ __device__ __forceinline__ u64 reduce192(const Acc192& g) {
   return gl_sub(r, gl_mul_2_32(g.c));
 }
 
+// One launch serves both the single-GPU layout (rows = the whole LDE, stride = N, pos0 = 0, halo = NULL) and a row
+// block of the sharded layout (SURVEY 8e phase 2: rows = [C][n_local] holding LDE positions pos0 .. pos0 + n_local - 1;
+// the "next" row of a position whose successor lives on another rank is read from `halo`, C contiguous values).
 __global__ void __launch_bounds__(128) quotient_vm_kernel(
-    const u64* __restrict__ lde, uint32_t N, unsigned log_n, uint32_t C, const u64* __restrict__ pis,
+    const u64* __restrict__ lde, size_t stride, uint32_t n_local, uint32_t pos0, const u64* __restrict__ halo,
+    uint32_t N, unsigned log_n, uint32_t C, const u64* __restrict__ pis,
     const u64* __restrict__ code, const u64* __restrict__ consts, const ulonglong2* __restrict__ wt,
     const uint4* __restrict__ chunks, const u64* __restrict__ dom, u64* __restrict__ part) {
-  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= N) return;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_local) return;
+  const uint32_t pos = pos0 + idx;
   const uint32_t n = 1u << log_n;
   const uint32_t pos_next = (pos & ~(n - 1)) | ((pos + 1) & (n - 1));   // next row = same coset, k+1 (wraps)
-  const u64* Lb = lde + pos;
-  const u64* Nb = lde + pos_next;
+  const u64* Lb = lde + idx;
+  const bool next_local = pos_next - pos0 < n_local;                     // unsigned: also false when pos_next < pos0
+  const u64* Nb = next_local ? lde + (pos_next - pos0) : halo;
+  const size_t nstride = next_local ? stride : 1;
   const uint4 ch = chunks[blockIdx.y];
   uint32_t pc = ch.x, slot = ch.z;
   const uint32_t pc_end = ch.y;
 
   auto var = [&](uint32_t v) -> u64 {
-    if (v < C) return Lb[(size_t)v * N];
-    if (v < 2 * C) return Nb[(size_t)(v - C) * N];
+    if (v < C) return Lb[(size_t)v * stride];
+    if (v < 2 * C) return Nb[(size_t)(v - C) * nstride];
     return __ldg(pis + (v - 2 * C));
   };
   auto class_factor = [&](uint32_t cls) -> u64 { return cls == 1 ? 1 : dom[(size_t)(cls - 2) * N + pos]; };
@@ -292,19 +299,19 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(
     acc0 = gl_add(acc0, gl_mul(S, reduce192(g0)));
     acc1 = gl_add(acc1, gl_mul(S, reduce192(g1)));
   }
-  part[((size_t)blockIdx.y * 2) * N + pos] = acc0;
-  part[((size_t)blockIdx.y * 2 + 1) * N + pos] = acc1;
+  part[((size_t)blockIdx.y * 2) * n_local + idx] = acc0;
+  part[((size_t)blockIdx.y * 2 + 1) * n_local + idx] = acc1;
 }
 
-// out[j][pos] = (sum over chunks) * Z_H(x_pos)^-1
-__global__ void quotient_reduce_kernel(const u64* __restrict__ part, uint32_t n_chunks, uint32_t N,
+// out[j][idx] = (sum over chunks) * Z_H(x_pos)^-1,  pos = pos0 + idx
+__global__ void quotient_reduce_kernel(const u64* __restrict__ part, uint32_t n_chunks, uint32_t n_local, uint32_t pos0,
                                        const u64* __restrict__ zh_inv, u64* __restrict__ out) {
-  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * N) return;
-  uint32_t j = idx / N, pos = idx % N;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n_local) return;
+  uint32_t j = t / n_local, idx = t % n_local;
   u64 acc = 0;
-  for (uint32_t c = 0; c < n_chunks; c++) acc = gl_add(acc, part[((size_t)c * 2 + j) * N + pos]);
-  out[idx] = gl_mul(acc, zh_inv[pos]);
+  for (uint32_t c = 0; c < n_chunks; c++) acc = gl_add(acc, part[((size_t)c * 2 + j) * n_local + idx]);
+  out[t] = gl_mul(acc, zh_inv[pos0 + idx]);
 }
 
 static void build_chunks(sb_ctx* ctx, AirProgram* a, uint32_t want) {
@@ -329,28 +336,66 @@ static void build_chunks(sb_ctx* ctx, AirProgram* a, uint32_t want) {
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // tab is a stack vector
 }
 
-// q_j(x) for every LDE position of the committed trace (ctx->lde), j < 2, into d_out[j][pos].
-void sb_quotient_device(sb_ctx* ctx, const sb_params* p, const u64* d_pis, const u64* alphas, u64* d_out) {
+// q_j(x), j < 2, at the n_local LDE positions pos0 .. pos0 + n_local - 1 held in d_rows ([C][n_local], row stride
+// `stride`), into d_out[j][idx].  d_halo: the row that follows the block's last position when that row is not in the
+// block (NULL for the whole domain).
+void sb_quotient_rows(sb_ctx* ctx, const sb_params* p, const u64* d_rows, size_t stride, uint32_t n_local, uint32_t pos0,
+                      const u64* d_halo, const u64* d_pis, const u64* alphas, u64* d_out) {
   if (p->num_challenges != 2) SB_THROW(SB_EINVAL, "num_challenges must be 2 (StarkConfig::standard_fast_config)");
   unsigned qdf = quotient_degree_factor(*p);
   if (ilog2(qdf) != p->rate_bits)
     SB_THROW(SB_EINVAL, "quotient_degree_bits %u != rate_bits %u: unsupported (all five starks have them equal)", ilog2(qdf), p->rate_bits);
   AirProgram* a = air_get(ctx, p);
   const uint32_t N = 1u << (p->log_n + p->rate_bits);
-  const unsigned block = N < 128 ? N : 128;
-  const uint32_t xtiles = (N + block - 1) / block;
+  const unsigned block = n_local < 128 ? n_local : 128;
+  const uint32_t xtiles = (n_local + block - 1) / block;
   build_chunks(ctx, a, (uint32_t)((ctx->sm_count * 64 + xtiles - 1) / xtiles));
   a->pw.ensure(16ull * a->K);
   a->wt.ensure(16ull * a->n_slots + 16);
-  a->part.ensure(16ull * a->n_chunks * N);
+  a->part.ensure(16ull * a->n_chunks * n_local);
   LAUNCH(ctx, alpha_pow_kernel, (a->K + 255) / 256, 256, 0, a->pw.as<u64>(), a->K, alphas[0], alphas[1], 0ull, 0ull, 2u);
   LAUNCH(ctx, slot_weight_kernel, (a->n_slots + 255) / 256, 256, 0, a->wt.as<u64>(), a->slot_off.as<uint32_t>(),
          a->slot_ks.as<uint32_t>(), a->pw.as<u64>(), a->n_slots, a->K, 2u);
   const u64* dom = domain_tables(ctx, p->log_n, p->rate_bits);
   dim3 grid(xtiles, a->n_chunks);
-  LAUNCH(ctx, quotient_vm_kernel, grid, block, 0, ctx->lde.as<u64>(), N, p->log_n, p->n_cols, d_pis, a->code.as<u64>(),
-         a->consts.as<u64>(), a->wt.as<ulonglong2>(), a->chunks.as<uint4>(), dom, a->part.as<u64>());
-  LAUNCH(ctx, quotient_reduce_kernel, (2 * N + 255) / 256, 256, 0, a->part.as<u64>(), a->n_chunks, N, dom + 3ull * N, d_out);
+  LAUNCH(ctx, quotient_vm_kernel, grid, block, 0, d_rows, stride, n_local, pos0, d_halo, N, p->log_n, p->n_cols, d_pis,
+         a->code.as<u64>(), a->consts.as<u64>(), a->wt.as<ulonglong2>(), a->chunks.as<uint4>(), dom, a->part.as<u64>());
+  LAUNCH(ctx, quotient_reduce_kernel, (2 * n_local + 255) / 256, 256, 0, a->part.as<u64>(), a->n_chunks, n_local, pos0,
+         dom + 3ull * N, d_out);
+}
+
+// q_j(x) for every LDE position of the committed trace (ctx->lde), j < 2, into d_out[j][pos].
+void sb_quotient_device(sb_ctx* ctx, const sb_params* p, const u64* d_pis, const u64* alphas, u64* d_out) {
+  const uint32_t N = 1u << (p->log_n + p->rate_bits);
+  sb_quotient_rows(ctx, p, ctx->lde.as<u64>(), N, N, 0, nullptr, d_pis, alphas, d_out);
+}
+
+// SURVEY 8e phase 2: the quotient values of ONE row block of the sharded LDE (device pointers; the caller exchanged the
+// halo row).  Replaces this rank's share of starky::prover::compute_quotient_polys.
+extern "C" int sb_quotient_rows_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_rows, uint32_t rows_per_block,
+                                       uint32_t block_index, const uint64_t* d_halo_next_row, const uint64_t* public_inputs,
+                                       const uint64_t* alphas, uint64_t* d_out) {
+  if (!ctx || !p || !d_rows || !alphas || !d_out || !rows_per_block) return SB_EINVAL;
+  try {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    const uint32_t N = 1u << (p->log_n + p->rate_bits), n = 1u << p->log_n;
+    if (rows_per_block > N || N % rows_per_block || (uint64_t)block_index * rows_per_block >= N)
+      SB_THROW(SB_EINVAL, "row block %u x %u does not tile the %u LDE positions", block_index, rows_per_block, N);
+    if (rows_per_block < n && !d_halo_next_row)
+      SB_THROW(SB_EINVAL, "a row block shorter than one coset (%u < %u) needs the halo row of its successor", rows_per_block, n);
+    ctx->pis.ensure(8ull * (p->n_public_inputs + 1));
+    if (p->n_public_inputs) {
+      if (!public_inputs) SB_THROW(SB_EINVAL, "public_inputs is NULL");
+      CUDA_CHECK(cudaMemcpyAsync(ctx->pis.p, public_inputs, 8ull * p->n_public_inputs, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    stage_begin(ctx, "quotient");
+    sb_quotient_rows(ctx, p, d_rows, rows_per_block, rows_per_block, block_index * rows_per_block, d_halo_next_row,
+                     ctx->pis.as<u64>(), alphas, d_out);
+    stage_end(ctx, "quotient");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
+    return SB_OK;
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
 }
 
 extern "C" int sb_quotient_values(sb_ctx* ctx, const sb_params* p, const uint64_t* public_inputs, const uint64_t* alphas,

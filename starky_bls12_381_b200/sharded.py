@@ -6,6 +6,11 @@ PolynomialBatch::from_values as called by starky::prover::prove (aggregate_proof
     exchange all-to-all       slab b of every rank -> rank b (NCCL over NVLink; LDE bytes x (G-1)/G cross the fabric)
     phase 2  row-sharded      rank g holds all C columns of its N / world positions: K2 leaf sponge, row-local
     gather   all-gather       N x 32-byte digests (<= 1 MB); K3 tree to the cap, redundantly on every rank
+    phase 2' row-sharded      K4 quotient values of the rank's positions (quotient_sharded): the alphas come from the
+                              gathered cap (same transcript on every rank); the "next" row of a block's last position
+                              lives on another rank when a block is shorter than one coset, so the ranks all-gather
+                              their FIRST rows (C x 8 bytes each) and each picks its successor's; the 2 x N quotient
+                              values (<= 0.5 MB) are all-gathered for the (small, unsharded) quotient commitment
 
 The module is backend-agnostic plumbing (torch.distributed only): `backend` supplies the three kernels -- GpuBackend
 (libstarkyb200 through the C ABI, device pointers of torch CUDA tensors) in production, an oracle-backed CPU double in
@@ -79,6 +84,40 @@ def commit_sharded(backend, plan, rank, local_trace, group=None):
     return dict(cap=cap, digests=digests, rows=rows)
 
 
+def successor_block(plan, rank):
+    """The rank whose first row is the `next` row of this rank's last position (position J*n + k, next = J*n + (k+1) mod n):
+    the following block inside the coset, wrapping to the coset's first block."""
+    blocks_per_coset = (1 << plan.log_n) // plan.rows_per_rank
+    if blocks_per_coset <= 1:
+        return None                      # a block holds whole cosets: every successor is local
+    nxt = rank + 1
+    return nxt if nxt % blocks_per_coset else nxt - blocks_per_coset
+
+
+def quotient_sharded(backend, plan, rank, rows, cap, public_inputs, group=None):
+    """Row-sharded quotient evaluation (this rank's share of starky::prover::compute_quotient_polys, SURVEY a7 / 8e).
+    rows: [C][N/world] from commit_sharded; cap: the trace cap every rank holds.  Returns dict(alphas, q = tensor
+    [2][N] in device position order, gathered on every rank; q_local = this rank's [2][N/world])."""
+    import torch
+    import torch.distributed as dist
+    alphas = backend.alphas(cap)
+    halo = None
+    nb = successor_block(plan, rank)
+    if nb is not None:
+        first = rows[:, 0].contiguous()
+        parts = [torch.empty_like(first) for _ in range(plan.world)]
+        dist.all_gather(parts, first, group=group)
+        halo = parts[nb]
+    q_local = backend.quotient_rows(plan, rank, rows, halo, public_inputs, alphas)          # [2][rows_per_rank]
+    if plan.world == 1:
+        q = q_local
+    else:
+        parts = [torch.empty_like(q_local) for _ in range(plan.world)]
+        dist.all_gather(parts, q_local, group=group)
+        q = torch.cat(parts, dim=1)
+    return dict(alphas=alphas, q=q, q_local=q_local)
+
+
 class GpuBackend:
     """The three kernels through the C ABI (sb_lde_cols_device / sb_hash_rows_device / sb_merkle_from_position_digests)."""
 
@@ -120,3 +159,24 @@ class GpuBackend:
         self.ctx._check(self.B.lib().sb_merkle_from_position_digests(self.ctx._h, self.B.C.byref(self.p), digests.data_ptr(),
                                                                    cap.ctypes.data_as(self.B.C.c_void_p)))
         return cap
+
+    def alphas(self, cap):
+        cap = np.ascontiguousarray(cap, dtype=np.uint64)
+        out = np.zeros(self.p.num_challenges, np.uint64)
+        rc = self.B.lib().sb_transcript_alphas(cap.ctypes.data_as(self.B.C.c_void_p), cap.shape[0], self.p.num_challenges,
+                                               out.ctypes.data_as(self.B.C.c_void_p))
+        if rc:
+            raise self.B.SbError(rc, "sb_transcript_alphas")
+        return out
+
+    def quotient_rows(self, plan, rank, rows, halo, public_inputs, alphas):
+        t = self.torch
+        out = t.empty((2, plan.rows_per_rank), dtype=t.int64, device=self.device)
+        pis = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+        al = np.ascontiguousarray(alphas, dtype=np.uint64)
+        self._sync_torch()
+        self.ctx._check(self.B.lib().sb_quotient_rows_device(
+            self.ctx._h, self.B.C.byref(self.p), rows.data_ptr(), plan.rows_per_rank, rank,
+            halo.data_ptr() if halo is not None else None, pis.ctypes.data_as(self.B.C.c_void_p) if pis.size else None,
+            al.ctypes.data_as(self.B.C.c_void_p), out.data_ptr()))
+        return out

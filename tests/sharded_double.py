@@ -8,6 +8,30 @@ from helpers import pos_to_leaf
 
 
 class OracleBackend:
+    """`air`, `params`, `full_trace`: only for quotient_rows (the double evaluates the whole quotient with the oracle and
+    returns the rank's block; it also CHECKS that the halo row it was handed is the successor of the block's last row)."""
+
+    def __init__(self, air=None, params=None, full_trace=None):
+        self.air, self.params, self.full_trace = air, params, full_trace
+
+    def alphas(self, cap):
+        return O.challenger_run(np.ascontiguousarray(cap, dtype=np.uint64).reshape(-1), 2)
+
+    def quotient_rows(self, plan, rank, rows, halo, public_inputs, alphas):
+        from helpers import pos_to_natural
+        n, R = 1 << plan.log_n, plan.rows_per_rank
+        r = rows.numpy().view(np.uint64)
+        last = rank * R + R - 1
+        nxt = (last & ~(n - 1)) | ((last + 1) & (n - 1))
+        if not (rank * R <= nxt < (rank + 1) * R):
+            leaves = O.lde_commit(self.params, self.full_trace)["leaves"]
+            lde_pos = leaves[pos_to_leaf(plan.log_n, plan.rate_bits)].T
+            assert halo is not None and np.array_equal(halo.numpy().view(np.uint64), lde_pos[:, nxt]), "wrong halo row"
+            assert np.array_equal(r[:, -1], lde_pos[:, last])
+        q_nat = O.quotient_values(self.air, self.params, self.full_trace, public_inputs, alphas)     # [2][N], natural LDE index
+        q_pos = q_nat[:, pos_to_natural(plan.log_n, plan.rate_bits)]
+        return torch.from_numpy(np.ascontiguousarray(q_pos[:, rank * R:(rank + 1) * R]).view(np.int64))
+
     def lde_cols(self, plan, rank, local_trace):
         cg = plan.col_count[rank]
         p = O.make_params(log_n=plan.log_n, n_cols=cg, rate_bits=plan.rate_bits)
