@@ -18,6 +18,7 @@
 
 #include "prover.cuh"
 
+enum { AIR_CODE_PAD = 8 };
 enum { OP_NOP = 0, OP_ADD1, OP_ADD2, OP_SHL1, OP_MULS, OP_MUL2, OP_MULC1, OP_MULC2, OP_MUL3C, OP_CONSTI, OP_CONSTC, OP_GROUP };
 
 struct AirProgram {
@@ -48,7 +49,7 @@ static void air_load_file(sb_ctx* ctx, uint32_t stark_id, const char* path) {
   if (ok) {
     a->n_cols = h.v[0]; a->n_pis = h.v[1]; a->degree = h.v[2]; a->K = h.v[3]; a->n_code = h.v[4]; a->n_consts = h.v[5];
     a->n_slots = h.v[6]; a->n_groups = h.v[7];
-    code.resize(a->n_code + 1); consts.resize(a->n_consts + 1); slot_off.resize(a->n_slots + 1); slot_ks.resize(a->K);
+    code.resize(a->n_code + 1); consts.resize(a->n_consts + 1); /* consts.back(): spare slot */ slot_off.resize(a->n_slots + 1); slot_ks.resize(a->K);
     gpc.resize(a->n_groups + 1); gslot.resize(a->n_groups + 1);
     auto rd = [&](void* p, size_t sz, size_t n) { return n == 0 || fread(p, sz, n, f) == n; };
     ok = rd(code.data(), 8, a->n_code) && rd(consts.data(), 8, a->n_consts) && rd(slot_off.data(), 4, a->n_slots + 1) &&
@@ -76,12 +77,31 @@ static void air_load_file(sb_ctx* ctx, uint32_t stark_id, const char* path) {
     }
     if (bad) { delete a; SB_THROW(SB_EAIR, "constraint program %s: invalid instruction at pc %u", path, pc); }
   }
-  code[a->n_code] = OP_NOP;  // one word of padding for the prefetch
-  a->code.ensure(8ull * (a->n_code + 1));
+  // Fast words.  ADD1 / ADD2 / SHL1 / MUL2 whose operands are all LOCAL columns are 85-90 % of every program (limb sums,
+  // carries times 2^32, limb products); they are re-encoded for a branch-light path of the interpreter:
+  //   bit 7 set, v0 in bits 8..31, v1 in bits 32..55 (one shift / one mask each), op / end / neg0 / neg1 unchanged.
+  for (uint32_t pc = 0; pc < a->n_code; pc++) {
+    const u64 w = code[pc];
+    const unsigned op = w & 15;
+    const u64 v0 = (w >> 8) & 0x3FFFF, v1 = (w >> 26) & 0x3FFFF;
+    if (op == OP_MUL3C) {       // the inline constant word would look like an instruction to the operand prefetcher
+      consts.back() = code[pc + 1];
+      code[pc + 1] = (u64)OP_NOP | ((u64)(consts.size() - 1) << 8);
+      consts.push_back(0);
+      pc++;
+      continue;
+    }
+    const bool two = op == OP_ADD2 || op == OP_MUL2;
+    if ((op == OP_ADD1 || op == OP_SHL1 || two) && v0 < a->n_cols && (!two || v1 < a->n_cols))
+      code[pc] = (w & 0x7F) | 0x80 | (v0 << 8) | ((two ? v1 : 0) << 32);
+  }
+  a->n_consts = (uint32_t)consts.size() - 1;
+  code.resize(a->n_code + AIR_CODE_PAD, (u64)OP_NOP);   // padding for the look-ahead
+  a->code.ensure(8ull * (a->n_code + AIR_CODE_PAD));
   a->consts.ensure(8ull * (a->n_consts + 1));
   a->slot_off.ensure(4ull * (a->n_slots + 1));
   a->slot_ks.ensure(4ull * (a->K + 1));
-  CUDA_CHECK(cudaMemcpyAsync(a->code.p, code.data(), 8ull * (a->n_code + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(a->code.p, code.data(), 8ull * (a->n_code + AIR_CODE_PAD), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync(a->consts.p, consts.data(), 8ull * a->n_consts, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync(a->slot_off.p, slot_off.data(), 4ull * (a->n_slots + 1), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync(a->slot_ks.p, slot_ks.data(), 4ull * a->K, cudaMemcpyHostToDevice, ctx->stream));
@@ -206,6 +226,7 @@ __device__ __forceinline__ u64 reduce192(const Acc192& g) {
 // One launch serves both the single-GPU layout (rows = the whole LDE, stride = N, pos0 = 0, halo = NULL) and a row
 // block of the sharded layout (SURVEY 8e phase 2: rows = [C][n_local] holding LDE positions pos0 .. pos0 + n_local - 1;
 // the "next" row of a position whose successor lives on another rank is read from `halo`, C contiguous values).
+template <int D>
 __global__ void __launch_bounds__(128) quotient_vm_kernel(
     const u64* __restrict__ lde, size_t stride, uint32_t n_local, uint32_t pos0, const u64* __restrict__ halo,
     uint32_t N, unsigned log_n, uint32_t C, const u64* __restrict__ pis,
@@ -235,9 +256,62 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(
   Acc192 g0 = {0, 0, 0}, g1 = {0, 0, 0};
   uint32_t sel_left = 0, cls = 1;
   bool have_group = false;
-  u64 w = __ldg(code + pc);
+  const char* Lb8 = (const char*)Lb;
+  const uint32_t stride8 = (uint32_t)(stride * 8);   // < 2^32: checked by the host
+  auto end_poly = [&]() {
+    if (sel_left) {
+      S = gl_mul(S, T);
+      if (--sel_left == 0) S = gl_mul(S, class_factor(cls));
+    } else {
+      const ulonglong2 ww = __ldg(wt + slot);
+      mac192(g0, T, ww.x);
+      mac192(g1, T, ww.y);
+      slot++;
+    }
+    T = 0;
+  };
+  // Software pipeline.  The interpreter is a serial chain (load operand -> add -> next word) and ncu shows it waiting on
+  // memory (long-scoreboard stalls 4.5 per issue, L1 hit rate 36 %): the program is static, so the operands of fast
+  // words are requested D words ahead and the code words D + 1 ahead.
+  u64 wq[D + 2], pa[D + 1], pb[D + 1];
+  auto issue = [&](u64 ww, u64& a, u64& b) {
+    const uint32_t l = (uint32_t)ww, h = (uint32_t)(ww >> 32);
+    if (l & 0x80u) {
+      a = *(const u64*)(Lb8 + (size_t)(l >> 8) * stride8);
+      b = *(const u64*)(Lb8 + (size_t)(h & 0xFFFFFFu) * stride8);    // column 0 for one-operand words: harmless
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < D + 2; i++) wq[i] = __ldg(code + pc + i);
+#pragma unroll
+  for (int i = 0; i < D + 1; i++) { pa[i] = 0; pb[i] = 0; issue(wq[i], pa[i], pb[i]); }
   while (pc < pc_end) {
-    const u64 wn = __ldg(code + pc + 1);      // prefetch (the table is padded by one word)
+    const u64 w = wq[0], wn = wq[1];
+    const u64 wfar = __ldg(code + pc + D + 2);
+    const uint32_t wl = (uint32_t)w;
+    const u64 a0 = pa[0], b0 = pb[0];
+#pragma unroll
+    for (int i = 0; i < D + 1; i++) wq[i] = wq[i + 1];
+    wq[D + 1] = wfar;
+#pragma unroll
+    for (int i = 0; i < D; i++) { pa[i] = pa[i + 1]; pb[i] = pb[i + 1]; }
+    issue(wq[D], pa[D], pb[D]);
+    if (wl & 0x80u) {
+      // fast word (see air_load_file): local columns only, operands already in flight
+      const unsigned fop = wl & 15u;
+      u64 a = a0;
+      if (fop == OP_ADD2) {
+        T = (wl & 32u) ? gl_sub(T, a) : gl_add(T, a);
+        T = (wl & 64u) ? gl_sub(T, b0) : gl_add(T, b0);
+      } else {
+        if (fop == OP_MUL2) a = gl_mul(a, b0);
+        else if (fop == OP_SHL1) a = gl_mul_2_32(a);
+        T = (wl & 32u) ? gl_sub(T, a) : gl_add(T, a);
+      }
+      if (wl & 16u) end_poly();
+      pc += 1;
+      continue;
+    }
     const unsigned op = (unsigned)w & 15u;
     const bool neg = (w >> 5) & 1;
     const uint32_t v0 = (uint32_t)(w >> 8) & 0x3FFFF, v1 = (uint32_t)(w >> 26) & 0x3FFFF, v2 = (uint32_t)(w >> 44) & 0x3FFFF;
@@ -257,7 +331,7 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(
       case OP_MUL2: x = gl_mul(var(v0), var(v1)); break;
       case OP_MULC1: x = gl_mul(var(v0), __ldg(consts + v2)); break;
       case OP_MULC2: x = gl_mul(gl_mul(var(v0), var(v1)), __ldg(consts + v2)); break;
-      case OP_MUL3C: x = gl_mul(gl_mul(gl_mul(var(v0), var(v1)), var(v2)), wn); break;
+      case OP_MUL3C: x = gl_mul(gl_mul(gl_mul(var(v0), var(v1)), var(v2)), __ldg(consts + (wn >> 8))); break;   // next word: NOP | idx
       case OP_CONSTI: x = (w >> 26) & 0xFFFFFFFFull; break;
       case OP_CONSTC: x = __ldg(consts + v2); break;
       case OP_GROUP: {
@@ -275,25 +349,8 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(
       default: has_x = false; break;
     }
     if (has_x) T = neg ? gl_sub(T, x) : gl_add(T, x);
-    if ((w >> 4) & 1) {     // end of a polynomial
-      if (sel_left) {
-        S = gl_mul(S, T);
-        if (--sel_left == 0) S = gl_mul(S, class_factor(cls));
-      } else {
-        const ulonglong2 ww = __ldg(wt + slot);
-        mac192(g0, T, ww.x);
-        mac192(g1, T, ww.y);
-        slot++;
-      }
-      T = 0;
-    }
-    if (op == OP_MUL3C) {
-      pc += 2;
-      w = __ldg(code + pc);
-    } else {
-      pc += 1;
-      w = wn;
-    }
+    if ((w >> 4) & 1) end_poly();     // end of a polynomial
+    pc += 1;                           // (the constant slot after a MUL3C is a NOP word)
   }
   if (have_group) {
     acc0 = gl_add(acc0, gl_mul(S, reduce192(g0)));
@@ -347,6 +404,7 @@ void sb_quotient_rows(sb_ctx* ctx, const sb_params* p, const u64* d_rows, size_t
     SB_THROW(SB_EINVAL, "quotient_degree_bits %u != rate_bits %u: unsupported (all five starks have them equal)", ilog2(qdf), p->rate_bits);
   AirProgram* a = air_get(ctx, p);
   const uint32_t N = 1u << (p->log_n + p->rate_bits);
+  if ((uint64_t)stride * 8 >= (1ull << 32)) SB_THROW(SB_EINVAL, "row stride %zu too large", stride);
   const unsigned block = n_local < 128 ? n_local : 128;
   const uint32_t xtiles = (n_local + block - 1) / block;
   build_chunks(ctx, a, (uint32_t)((ctx->sm_count * 64 + xtiles - 1) / xtiles));
@@ -358,8 +416,12 @@ void sb_quotient_rows(sb_ctx* ctx, const sb_params* p, const u64* d_rows, size_t
          a->slot_ks.as<uint32_t>(), a->pw.as<u64>(), a->n_slots, a->K, 2u);
   const u64* dom = domain_tables(ctx, p->log_n, p->rate_bits);
   dim3 grid(xtiles, a->n_chunks);
-  LAUNCH(ctx, quotient_vm_kernel, grid, block, 0, d_rows, stride, n_local, pos0, d_halo, N, p->log_n, p->n_cols, d_pis,
-         a->code.as<u64>(), a->consts.as<u64>(), a->wt.as<ulonglong2>(), a->chunks.as<uint4>(), dom, a->part.as<u64>());
+  static const int depth = [] { const char* e = getenv("SB_QUOTIENT_DEPTH"); return e ? atoi(e) : 0; }();
+#define QVM_LAUNCH(DD)                                                                                                    \
+  LAUNCH(ctx, quotient_vm_kernel<DD>, grid, block, 0, d_rows, stride, n_local, pos0, d_halo, N, p->log_n, p->n_cols, d_pis, \
+         a->code.as<u64>(), a->consts.as<u64>(), a->wt.as<ulonglong2>(), a->chunks.as<uint4>(), dom, a->part.as<u64>())
+  if (depth <= 0) QVM_LAUNCH(0); else if (depth == 1) QVM_LAUNCH(1); else if (depth == 2) QVM_LAUNCH(2); else if (depth == 3) QVM_LAUNCH(3); else QVM_LAUNCH(5);
+#undef QVM_LAUNCH
   LAUNCH(ctx, quotient_reduce_kernel, (2 * n_local + 255) / 256, 256, 0, a->part.as<u64>(), a->n_chunks, n_local, pos0,
          dom + 3ull * N, d_out);
 }
