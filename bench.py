@@ -144,6 +144,60 @@ def run_also(ctx, sb, name):
             "leaf_hash_mperm_s": (-(-C // 8) * N) / (kern["leaf_hash"] * 1e-3) / 1e6, "h2d_bytes": 8 * C * n}
 
 
+FULL_SET = ["final_exp", "miller_loop", "miller_loop", "pairing_precomp", "pairing_precomp", "ecc_agg", "fp12_mul"]
+FULL_SET_COST = {"final_exp": 650.0, "miller_loop": 225.0, "pairing_precomp": 75.0, "ecc_agg": 35.0, "fp12_mul": 6.0}
+
+
+def full_set_assignment(world):
+    """BASELINE configs[4]: the seven starky proofs of one BLS signature verification (aggregate_proof.rs:279-370 proves
+    them one after the other; they are independent once the native inputs are known).  Longest-processing-time-first
+    onto `world` GPUs; returns one list of stark names per rank."""
+    loads, out = [0.0] * world, [[] for _ in range(world)]
+    for name in sorted(FULL_SET, key=lambda k: -FULL_SET_COST[k]):
+        g = min(range(world), key=lambda r: loads[r])
+        out[g].append(name)
+        loads[g] += FULL_SET_COST[name]
+    return out
+
+
+def run_full_set(sb, contexts, names, rank, timed):
+    """Proves `names` on this rank's GPU, end to end from pinned host memory, with len(contexts) proofs in flight (one host
+    thread per context, work queue in cost order).  Returns (seconds max over ranks, per-proof ms)."""
+    import torch
+    jobs = []
+    for i, name in enumerate(names):
+        info = sb.STARKS[name]
+        trace, pis = synthetic(info, 0xB2300000 + 16 * rank + i)
+        host = torch.from_numpy(trace.view(np.int64)).pin_memory()
+        del trace
+        p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+        jobs.append((name, p, host, pis))
+    lock, per = threading.Lock(), []
+
+    def go():
+        queue = list(jobs)
+
+        def worker(c):
+            while True:
+                with lock:
+                    if not queue:
+                        return
+                    name, p, host, pis = queue.pop(0)
+                t0 = time.perf_counter()
+                c.prove(p, host.data_ptr(), pis, sb.TraceLayout.COLMAJOR_U64)
+                with lock:
+                    per.append((name, 1e3 * (time.perf_counter() - t0)))
+        ts = [threading.Thread(target=worker, args=(c,)) for c in contexts]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    go()                 # warm-up: buffers of every shape allocated, constraint programs loaded
+    per.clear()
+    dt, _ = timed(go, 1)
+    return dt, per
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +208,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded-stark", default="final_exp",
                     help="shape of the second sharded trace commitment (column slices drawn per rank); '' to skip")
+    ap.add_argument("--no-full-set", action="store_true", help="skip the 7-proof BLS set (BASELINE configs[4])")
     ap.add_argument("--also", default="miller_loop,final_exp",
                     help="N=1 only: further starks proved once each after the headline workload (reported under 'also')")
     args = ap.parse_args()
@@ -289,6 +344,17 @@ def main():
         for t in ts:
             t.join()
     dt_pipe, _ = timed(two_in_flight, 1)
+    # ---- BASELINE configs[4]: the seven proofs of one BLS signature verification over all ranks, two in flight per GPU ----
+    full = None
+    if not args.no_full_set:
+        for nm in set(FULL_SET):
+            airfiles.air_path(nm, "airbin")
+        mine = full_set_assignment(world)[rank]
+        dt_full, per = run_full_set(sb, (ctx, ctx2), mine, rank, timed)
+        full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
+                            "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
+                "assignment": full_set_assignment(world), "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
+                "note": "longest-first assignment of whole proofs to GPUs, two proofs in flight per GPU; ms = makespan, max over ranks"}
     ctx2.close()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = 1e3 * dt / args.steps
@@ -367,6 +433,7 @@ def main():
                     "d2h_bytes_per_step": proof_bytes},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "stage_ms": stage, "kernel_ms": kern, "sharded_commit": sharded, "sharded_commit_scaling_shape": fe, "also": also,
+            "full_bls_set": full,
             "two_in_flight": {"ms_per_proof": 1e3 * dt_pipe / (2 * args.steps) / world, "proofs": 2 * args.steps * world,
                               "note": "two contexts per GPU, one host thread each: transcript of one proof overlaps kernels of the other"},
         }

@@ -1,0 +1,23 @@
+"""CPU-only checks of bench.py's host logic (no GPU, no library calls)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def test_full_set_assignment_covers_the_seven_proofs_and_balances():
+    for world in (1, 2, 4, 8):
+        a = bench.full_set_assignment(world)
+        assert len(a) == world
+        assert sorted(x for r in a for x in r) == sorted(bench.FULL_SET)
+        loads = [sum(bench.FULL_SET_COST[x] for x in r) for r in a]
+        # FinalExp is the critical path as soon as there are two GPUs
+        assert max(loads) == (sum(bench.FULL_SET_COST[x] for x in bench.FULL_SET) if world == 1 else bench.FULL_SET_COST["final_exp"])
+    assert bench.full_set_assignment(4)[0] == ["final_exp"]
+
+
+def test_workload_tables_are_consistent():
+    import starky_bls12_381_b200 as sb
+    assert set(bench.WORKLOADS) == set(sb.STARKS) == set(bench.K_CONSTRAINTS)
+    assert set(bench.FULL_SET) == set(sb.STARKS)
