@@ -465,30 +465,30 @@ static __constant__ u64 c_fast_d3[12 * 12] = POSEIDON_FAST_D3;
 struct Acc192 { u64 lo, hi; u32 top; };
 __device__ __forceinline__ void acc192_mul(Acc192& a, u64 x, u64 y) {
   const u64 pl = x * y, ph = __umul64hi(x, y);
-  a.lo += pl;
-  const u64 c = a.lo < pl;
-  a.hi += ph;
-  const u32 c1 = a.hi < ph;
-  a.hi += c;
-  a.top += c1 + (a.hi < c);
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+      : "+l"(a.lo), "+l"(a.hi), "+r"(a.top) : "l"(pl), "l"(ph));
 }
 // (lo, hi, top) mod p -> lazy u64.   2^128 = -2^32 (mod p):  top * 2^128 = top * (p - 2^32) = top * (2^64 - 2^33 + 1)
 __device__ __forceinline__ u64 acc192_reduce(const Acc192& a) {
-  // t = top * (2^64 - 2^33 + 1), top <= 2^16:  t_hi:t_lo
-  const u64 top = a.top;
-  const u64 sub = top << 33;                       // top * 2^33 < 2^50
-  u64 t_lo = top - sub, t_hi = top - (top < sub);   // top*2^64 + top - top*2^33 (borrow iff top < sub, i.e. top > 0)
-  u64 lo = a.lo + t_lo;
-  u64 c = lo < t_lo;
-  u64 hi = a.hi + t_hi;
-  u64 c2 = hi < t_hi;
-  hi += c;
-  c2 += hi < c;
-  // a second wrap of 2^128 (c2 <= 1) is again worth 2^64 - 2^33 + 1; after a wrap hi is tiny, so this cannot wrap again
-  const u64 s2 = c2 << 33;
-  const u64 u_lo = c2 - s2, u_hi = c2 - (c2 < s2);
-  lo += u_lo;
-  hi += u_hi + (lo < u_lo);
+  u64 lo = a.lo, hi = a.hi;
+  // t = top * (2^64 - 2^33 + 1) = (top - borrow) : (top - top 2^33), added to hi:lo; a wrap of 2^128 (at most one) is again
+  // worth 2^64 - 2^33 + 1, and after a wrap hi is tiny, so the second addition cannot wrap
+  asm("{\n\t"
+      ".reg .u64 t, sb, tlo, thi, c2, s2, ulo, uhi;\n\t"
+      "cvt.u64.u32 t, %2;\n\t"
+      "shl.b64 sb, t, 33;\n\t"
+      "sub.cc.u64 tlo, t, sb;\n\t"
+      "subc.u64 thi, t, 0;\n\t"
+      "add.cc.u64 %0, %0, tlo;\n\t"
+      "addc.cc.u64 %1, %1, thi;\n\t"
+      "addc.u64 c2, 0, 0;\n\t"
+      "shl.b64 s2, c2, 33;\n\t"
+      "sub.cc.u64 ulo, c2, s2;\n\t"
+      "subc.u64 uhi, c2, 0;\n\t"
+      "add.cc.u64 %0, %0, ulo;\n\t"
+      "addc.u64 %1, %1, uhi;\n\t"
+      "}"
+      : "+l"(lo), "+l"(hi) : "r"(a.top));
   // fold the 128-bit value (x3:x2:x1:x0) exactly like gl_mul_lazy
   u32 r0, r1;
   asm("{\n\t"
@@ -713,6 +713,193 @@ __global__ void __launch_bounds__(128) leaf_sponge_dp_kernel(const u64* __restri
       for (int k = 0; k < W; k++) v[k] = s[k];
       if (wid == 0) v[0] = poseidon_sbox(v[0]);
       linear_layer(v, rd);
+    }
+#pragma unroll 1
+    for (int rd = 26; rd < 30; rd++) full_round(rd);
+  }
+  if (live) {
+    u64* d = digests + 4ull * leaf_index_of(pos, log_block);
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      if (w0 + k < 4) d[w0 + k] = gl_canon(s[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Throughput shapes, second form: dp2a full rounds + SPARSE partial rounds in the same three-words-per-thread layout.
+// The dp kernel spends 22 of its 30 rounds on a dense MDS of which only word 0 went through the S-box: per leaf and
+// round 336 IDP.2A + 112 PRMT + 12 recombinations, with three of the four warps waiting at the barrier for warp 0's
+// S-box (ncu: 26 % of the warp samples).  In sparse form (tables as in the sp kernel) a partial round is
+//     helpers:  x_i += v_{r-1}[i] y(r-1)            (the update of the PREVIOUS round, 3 multiply-adds per thread)
+//               d_w  = sum_{i in mine} w^_r[i] x_i    (3 multiplies into one 192-bit accumulator, one reduction)
+//     warp 0 :  the same for words 1, 2 and  y(r) = x0^7 + a_r          -- its S-box overlaps everybody's linear part
+//     one barrier, then  x0 = 25 y(r) + d_0 + d_1 + d_2 + d_3  (warp 0)  and everybody picks up y(r)
+// : ~635 instructions per leaf and round instead of ~940, one barrier per round as before.  Round 3's linear layer is
+// the dense D3 / K3 form (FIRST and the 11x11 INIT matrix folded in), 12 full multiplies per row.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void acc192_add(Acc192& a, u64 x) {
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, 0;\n\taddc.u32 %2, %2, 0;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.top) : "l"(x));
+}
+
+__global__ void __launch_bounds__(128) leaf_sponge_ds_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                             uint32_t n_leaves, unsigned log_block,
+                                                             u64* __restrict__ digests) {
+  constexpr int W = 3, NW = W + 11, NP = NW / 2;
+  __shared__ __align__(16) u64 xch[2][24][32];
+  __shared__ __align__(16) u64 dsl[2][5][32];
+  // the sparse tables in shared memory: indexed per warp and per round, 8 KB in all -- more than the constant cache
+  // holds, and an indexed LDC that misses costs hundreds of cycles on the round's critical path
+  __shared__ u64 tb_what[22 * 11], tb_vs[22 * 11], tb_post[22], tb_d3[144], tb_k3[12];
+  for (unsigned i = threadIdx.x; i < 22 * 11; i += blockDim.x) { tb_what[i] = c_fast_what[i]; tb_vs[i] = c_fast_vs[i]; }
+  for (unsigned i = threadIdx.x; i < 144; i += blockDim.x) tb_d3[i] = c_fast_d3[i];
+  if (threadIdx.x < 22) tb_post[threadIdx.x] = c_fast_post[threadIdx.x];
+  if (threadIdx.x < 12) tb_k3[threadIdx.x] = c_fast_k3[threadIdx.x];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned w0 = wid * W;
+  const uint32_t pos_raw = blockIdx.x * 32 + lane;
+  const bool live = pos_raw < n_leaves;
+  const uint32_t pos = live ? pos_raw : n_leaves - 1;
+  constexpr u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+
+  u64 s[W], nx[W];
+#pragma unroll
+  for (int k = 0; k < W; k++) { s[k] = 0; nx[k] = 0; }
+  const uint32_t n_chunks = (leaf_len + 7) / 8;
+  auto fetch = [&](uint32_t chunk) {
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      uint32_t c = chunk * 8 + w0 + k;
+      if (w0 + k < 8 && c < leaf_len) nx[k] = cols[(size_t)c * n_leaves + pos];
+    }
+  };
+  fetch(0);
+  unsigned xb = 0, db = 0;
+  for (uint32_t m = 0; m < n_chunks; m++) {
+    const unsigned take = min(8u, leaf_len - 8 * m);
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      if (w0 + k < take) s[k] = nx[k];
+    if (m + 1 < n_chunks) fetch(m + 1);
+#pragma unroll
+    for (int k = 0; k < W; k++) s[k] = gl_add_lazy_canon(s[k], c_poseidon_rc[w0 + k]);
+
+    // dense MDS on dp2a (identical to leaf_sponge_dp_kernel): S-box the three words, exchange, three rows, next constants
+    auto full_round = [&](int rd) {
+      u64 v[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) v[k] = poseidon_sbox(s[k]);
+      u64* dst = &xch[xb][w0][lane];
+#pragma unroll
+      for (int k = 0; k < W; k++) { dst[32 * k] = v[k]; dst[32 * (k + 12)] = v[k]; }
+      u64 rc[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) rc[k] = c_poseidon_rc[12 * (rd + 1) + w0 + k];
+      __syncthreads();
+      const u64* src = &xch[xb][w0][lane];
+      u64 t[NW];
+#pragma unroll
+      for (int j = 0; j < NW; j++) t[j] = src[32 * j];       // word (w0 + j) mod 12
+      u32 acc[W][4];
+#pragma unroll
+      for (int k = 0; k < W; k++) {
+        const u32 lo = (u32)rc[k], hi = (u32)(rc[k] >> 32);
+        acc[k][0] = lo & 0xFFFFu; acc[k][1] = lo >> 16; acc[k][2] = hi & 0xFFFFu; acc[k][3] = hi >> 16;
+      }
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const u32 alo = (u32)t[2 * p], ahi = (u32)(t[2 * p] >> 32), blo = (u32)t[2 * p + 1], bhi = (u32)(t[2 * p + 1] >> 32);
+        const u32 q0 = __byte_perm(alo, blo, 0x5410), q1 = __byte_perm(alo, blo, 0x7632);
+        const u32 q2 = __byte_perm(ahi, bhi, 0x5410), q3 = __byte_perm(ahi, bhi, 0x7632);
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+          const int i0 = 2 * p - k, i1 = 2 * p + 1 - k;
+          const u32 c0 = (i0 >= 0 && i0 < 12) ? CIRC[i0] : 0u, c1 = (i1 >= 0 && i1 < 12) ? CIRC[i1] : 0u;
+          const u32 b = c0 | (c1 << 8);
+          if (b) {
+            acc[k][0] = dp2a_lo(q0, b, acc[k][0]); acc[k][1] = dp2a_lo(q1, b, acc[k][1]);
+            acc[k][2] = dp2a_lo(q2, b, acc[k][2]); acc[k][3] = dp2a_lo(q3, b, acc[k][3]);
+          }
+        }
+        if (p == 0 && wid == 0) {
+          acc[0][0] = dp2a_lo(q0, 8u, acc[0][0]); acc[0][1] = dp2a_lo(q1, 8u, acc[0][1]);
+          acc[0][2] = dp2a_lo(q2, 8u, acc[0][2]); acc[0][3] = dp2a_lo(q3, 8u, acc[0][3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < W; k++) s[k] = limbs_recombine(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+      xb ^= 1;
+    };
+#pragma unroll 1
+    for (int rd = 0; rd < 3; rd++) full_round(rd);
+    // ---- partial rounds in their own layout: warp 0 owns x0 and nothing else (its S-box + combine chain IS the critical
+    // path of a round), warps 1..3 own words 1-4, 5-8, 9-11 ----
+    const unsigned p0 = wid == 0 ? 0u : 1u + 4u * (wid - 1u), np = wid == 0 ? 1u : (wid == 3 ? 3u : 4u);
+    u64 x[4] = {0, 0, 0, 0};
+    {  // round 3: x = D3 v + K3  (row 0 of D3 is the MDS row, K3[0] = FIRST[0]); every thread computes the rows it owns
+      u64* dst = &xch[xb][w0][lane];
+#pragma unroll
+      for (int k = 0; k < W; k++) dst[32 * k] = poseidon_sbox(s[k]);
+      __syncthreads();
+      u64 t[12];
+#pragma unroll
+      for (int c = 0; c < 12; c++) t[c] = xch[xb][c][lane];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if ((unsigned)q < np) {
+          const u64* row = tb_d3 + 12 * (p0 + q);
+          Acc192 a = {tb_k3[p0 + q], 0, 0};
+#pragma unroll
+          for (int c = 0; c < 12; c++) acc192_mul(a, row[c], t[c]);
+          x[q] = acc192_reduce(a);
+        }
+      }
+      xb ^= 1;
+    }
+    u64 y = 0;
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+      Acc192 b = {0, 0, 0};
+      if (wid == 0) {
+        y = gl_add_lazy_canon(poseidon_sbox(x[0]), tb_post[r]);
+        dsl[db][3][lane] = y;
+        acc192_mul(b, 25ull, y);
+      } else {
+        const u64* wh = tb_what + 11 * r + (p0 - 1);
+        const u64* vp = tb_vs + 11 * (r - 1) + (p0 - 1);
+        Acc192 a = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if ((unsigned)q < np) {
+            if (r > 0) x[q] = gl_mad_lazy(vp[q], y, x[q]);
+            acc192_mul(a, wh[q], x[q]);
+          }
+        }
+        dsl[db][wid - 1][lane] = acc192_reduce(a);
+      }
+      __syncthreads();
+      if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) acc192_add(b, dsl[db][q][lane]);
+        x[0] = acc192_reduce(b);
+      } else {
+        y = dsl[db][3][lane];
+      }
+      db ^= 1;
+    }
+    {  // the update of the last partial round, the constants of round 26, and back to the three-words-per-thread layout
+      const u64* vp = tb_vs + 11 * 21 + (p0 - 1);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if ((unsigned)q < np) {
+          if (wid > 0) x[q] = gl_mad_lazy(vp[q], y, x[q]);
+          xch[xb][p0 + q][lane] = gl_add_lazy_canon(x[q], c_poseidon_rc[12 * 26 + p0 + q]);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < W; k++) s[k] = xch[xb][w0 + k][lane];
+      xb ^= 1;
     }
 #pragma unroll 1
     for (int rd = 26; rd < 30; rd++) full_round(rd);

@@ -65,10 +65,10 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
   //     reducer warp (13); the dense-MDS variant with two-barrier partial rounds (12) is kept for comparison;
   //   many leaves (FinalExp / ECCAgg 32768): throughput-bound on the heavy FMA pipe (IMAD.WIDE is half rate)  ->  three
   //     words per thread, four warps per 32 leaves, dense MDS on dp2a (4); 3 = the same layout on IMAD.WIDE.
-  // SB_LEAF_KERNEL=1|3|4|12|13 overrides the choice (profiling, tests).
+  // SB_LEAF_KERNEL=1|3|4|5|12|13 overrides the choice (profiling, tests).
   int kind = 1;
   if (leaf_len > 4 && perms > 2) kind = ((uint64_t)n_leaves <= 64ull * ctx->sm_count) ? 13 : 4;
-  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
+  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
   const uint32_t groups = (n_leaves + 31) / 32;
   if (kind == 13) {
     LAUNCH(ctx, leaf_sponge_sp_kernel, groups, 416, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
@@ -76,6 +76,8 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
     LAUNCH(ctx, (leaf_sponge_w12_kernel<0, 1>), groups, 384, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 4) {
     LAUNCH(ctx, leaf_sponge_dp_kernel, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+  } else if (kind == 5) {
+    LAUNCH(ctx, leaf_sponge_ds_kernel, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 3) {
     LAUNCH(ctx, leaf_sponge_ws_kernel<4>, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else {

@@ -145,6 +145,7 @@ int main(int argc, char** argv) {
     for (int rep = 0; rep < 2; rep++) {
       float ms = time_ms([&] {
         if (wps == 43) leaf_sponge_dp_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 45) leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 101) leaf_sponge_st_kernel<<<g32, 32>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 130) leaf_sponge_sp_kernel<<<g32, 416>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 122) leaf_sponge_w12_kernel<2><<<g32, 512>>>(d_cols, ll, nl, 0, d_dig);
@@ -219,6 +220,7 @@ int main(int argc, char** argv) {
     run("ws<12> (1 word/thread)", [&] { leaf_sponge_ws_kernel<12><<<g32, 384>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("w12<0> (two-barrier partial)", [&] { leaf_sponge_w12_kernel<0><<<g32, 384>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("dp (3 words/thread, dp2a MDS)", [&] { leaf_sponge_dp_kernel<<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("ds (dp2a full + sparse partial)", [&] { leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("st (sparse, one thread per leaf, block 32)", [&] { leaf_sponge_st_kernel<<<g32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("st (sparse, one thread per leaf, block 64)", [&] { leaf_sponge_st_kernel<<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("sp (sparse partial rounds, 13 warps)", [&] { leaf_sponge_sp_kernel<<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
