@@ -179,6 +179,37 @@ int sb_quotient_rows_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_r
                             uint32_t block_index, const uint64_t* d_halo_next_row, const uint64_t* public_inputs,
                             const uint64_t* alphas, uint64_t* d_out);
 int sb_transcript_alphas(const uint64_t* trace_cap, uint32_t cap_len, uint32_t num_challenges, uint64_t* alphas_out);
+/*      The tail of a sharded proof (SURVEY 8e "small collectives").  sb_prove_sharded runs the SAME orchestration as
+ *      sb_prove on every rank (same transcript, same proof on every rank) but asks the host, through five hooks, for the
+ *      five things that are distributed: the hooks are collective (every rank calls them in the same order) and are
+ *      implemented with the per-rank stage functions above and below plus NCCL (starky_bls12_381_b200/sharded.py).
+ *        commit     : the sharded trace commitment; on return the ctx holds the trace Merkle tree
+ *                     (sb_merkle_from_position_digests) and cap_out the cap
+ *        quotient   : q_j(x) at all N positions, device [2][N], position order
+ *        openings   : P_c(zeta), P_c(g zeta) of all n_cols trace columns, host [n_cols][2] each (column-sharded
+ *                     coefficient slices, all-gathered)
+ *        combine    : sum_c alpha^c coeffs_c over all trace columns, device [n][2], bit-reversed coefficient order
+ *                     (per-rank partial sums with the rank's alpha-power offset, all-gathered and added)
+ *        query_rows : the full trace rows at `count` device LDE positions, device [count][n_cols] (from the row owners)
+ *      Every hook returns 0 or an SB_E* code.  Everything else (quotient commitment, transcript, FRI rounds, proof of
+ *      work, Merkle paths) is small and is computed redundantly on every rank. */
+typedef struct sb_shard_hooks {
+  void* user;
+  int (*commit)(void* user, uint64_t* cap_out);
+  int (*quotient)(void* user, const uint64_t* alphas, uint64_t* d_q_out);
+  int (*openings)(void* user, const uint64_t* zeta, const uint64_t* zeta_next, uint64_t* local_out, uint64_t* next_out);
+  int (*combine)(void* user, const uint64_t* alpha, uint64_t* d_out);
+  int (*query_rows)(void* user, const uint32_t* positions, uint32_t count, uint64_t* d_rows_out);
+} sb_shard_hooks;
+int sb_prove_sharded(sb_ctx* ctx, const sb_params* p, const sb_shard_hooks* hooks, const uint64_t* public_inputs,
+                     sb_proof** out);
+/*      Per-rank pieces for the hooks: openings and alpha-weighted sum of a column slice of coefficients
+ *      (d_coeffs = [n_cols_local][n], bit-reversed coefficient order, as sb_lde_cols_device leaves them). */
+int sb_openings_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_coeffs, uint32_t n_cols_local,
+                            const uint64_t* zeta, const uint64_t* zeta_next, uint64_t* local_out, uint64_t* next_out);
+int sb_combine_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_coeffs, uint32_t n_cols_local,
+                           const uint64_t* alpha, uint32_t first_col, uint64_t* d_out);
+int sb_memcpy_device(sb_ctx* ctx, void* d_dst, const void* d_src, uint64_t bytes);
 int sb_synchronize(sb_ctx* ctx);
 
 /* The host-side transcript permutation (plonky2 Challenger, run between kernels): variant 0 = portable scalar,

@@ -54,6 +54,20 @@ class _CProof(C.Structure):
         "ms_total")]
 
 
+HOOK_COMMIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64))
+HOOK_QUOTIENT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p)
+HOOK_OPENINGS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                            C.POINTER(C.c_uint64))
+HOOK_COMBINE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p)
+HOOK_QUERY_ROWS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p)
+
+
+class ShardHooks(C.Structure):
+    """Binary-identical to sb_shard_hooks (include/starky_b200.h)."""
+    _fields_ = [("user", C.c_void_p), ("commit", HOOK_COMMIT), ("quotient", HOOK_QUOTIENT), ("openings", HOOK_OPENINGS),
+                ("combine", HOOK_COMBINE), ("query_rows", HOOK_QUERY_ROWS)]
+
+
 def lib_path():
     return os.path.join(_HERE, "libstarkyb200.so")
 
@@ -101,6 +115,13 @@ def lib():
         L.sb_quotient_rows_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p]
         L.sb_transcript_alphas.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.sb_prove_sharded.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(ShardHooks), C.c_void_p,
+                                       C.POINTER(C.POINTER(_CProof))]
+        L.sb_openings_cols_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        L.sb_combine_cols_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                             C.c_void_p]
+        L.sb_memcpy_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _LIB = L
     return _LIB
 

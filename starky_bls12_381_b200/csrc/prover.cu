@@ -132,8 +132,16 @@ struct Arena {
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+#define HOOK(call)                                                                              \
+  do {                                                                                          \
+    int rc_ = (call);                                                                           \
+    if (rc_) SB_THROW(rc_, "sharded proof: hook %s failed with code %d", #call, rc_);           \
+  } while (0)
+
+// hooks == nullptr: one GPU holds everything.  hooks != nullptr: the trace is sharded over the GPUs of a box and the five
+// distributed steps are done by the host (include/starky_b200.h: sb_shard_hooks); every rank runs this same function.
 static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, const uint64_t* public_inputs,
-                       sb_proof* proof) {
+                       sb_proof* proof, const sb_shard_hooks* hooks = nullptr) {
   const unsigned log_n = p->log_n, r = p->rate_bits, log_N = log_n + r, qdf = quotient_degree_factor(*p);
   const uint32_t n = 1u << log_n, N = 1u << log_N, C = p->n_cols;
   const sb_proof_layout L = proof_layout(*p);
@@ -149,9 +157,14 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
 
   // ---- 0. ingest, 1. trace commitment ----
   CUDA_CHECK(cudaEventRecord(ev[0], st));
-  ingest_and_commit_trace(ctx, p, trace, layout, ev[1]);   // ev[1] = trace fully on the device (copy stream)
-  CUDA_CHECK(cudaMemcpyAsync(W + L.off_trace_cap, tree_cap_ptr(ctx->tree.as<u64>(), N, p->cap_height), 32ull * L.cap_len,
-                             cudaMemcpyDeviceToHost, st));
+  if (hooks) {
+    CUDA_CHECK(cudaEventRecord(ev[1], st));
+    HOOK(hooks->commit(hooks->user, W + L.off_trace_cap));
+  } else {
+    ingest_and_commit_trace(ctx, p, trace, layout, ev[1]);   // ev[1] = trace fully on the device (copy stream)
+    CUDA_CHECK(cudaMemcpyAsync(W + L.off_trace_cap, tree_cap_ptr(ctx->tree.as<u64>(), N, p->cap_height), 32ull * L.cap_len,
+                               cudaMemcpyDeviceToHost, st));
+  }
   ctx->pis.ensure(8ull * (p->n_public_inputs + 1));
   if (p->n_public_inputs)
     CUDA_CHECK(cudaMemcpyAsync(ctx->pis.p, public_inputs, 8ull * p->n_public_inputs, cudaMemcpyHostToDevice, st));
@@ -167,6 +180,7 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
   const size_t partial_elems = (size_t)(ctx->sm_count * 16 + 8) * 128 + 2 * (size_t)n;
   size_t need = 16ull * N * 2 + 8ull * nq * n * 2 + 16ull * n * 2 + 16ull * (2ull * C + nq + 8) + 16ull * (C + nq + 8) +
                 16ull * partial_elems + 16ull * n * 2 + 8ull * L.query_stride * L.n_queries + 16ull * N * 2 + 64ull * N +
+                (hooks ? 8ull * L.n_queries * C + 4096 : 0) +
                 (1 << 16);
   ctx->scratch2.ensure(need);
   Arena ar(ctx->scratch2.p, ctx->scratch2.cap);
@@ -174,9 +188,13 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
   // ---- 3. quotient values, K5: quotient polynomials and their commitment ----
   ctx->qvals.ensure(16ull * N);
   u64* d_q = ctx->qvals.as<u64>();
-  stage_begin(ctx, "quotient");
-  sb_quotient_device(ctx, p, ctx->pis.as<u64>(), alphas, d_q);
-  stage_end(ctx, "quotient");
+  if (hooks) {
+    HOOK(hooks->quotient(hooks->user, alphas, d_q));
+  } else {
+    stage_begin(ctx, "quotient");
+    sb_quotient_device(ctx, p, ctx->pis.as<u64>(), alphas, d_q);
+    stage_end(ctx, "quotient");
+  }
   CUDA_CHECK(cudaEventRecord(ev[3], st));
   u64* d_qtmp = ar.take<u64>(2ull * N);
   int* d_flag = ar.take<int>(4);
@@ -220,10 +238,15 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
   e2_t* d_tab_a = ar.take<e2_t>(n);
   e2_t* d_tab_b = ar.take<e2_t>(n);
   e2_t* d_open = ar.take<e2_t>(2ull * C + nq);
-  sb_openings_device(ctx, ctx->coeffs.as<u64>(), log_n, C, zeta, &zeta_next, d_tab_a, d_tab_b, d_open, d_open + C);
+  if (hooks) {
+    const u64 z[2] = {zeta.a, zeta.b}, zn[2] = {zeta_next.a, zeta_next.b};
+    HOOK(hooks->openings(hooks->user, z, zn, W + L.off_local_values, W + L.off_next_values));
+  } else {
+    sb_openings_device(ctx, ctx->coeffs.as<u64>(), log_n, C, zeta, &zeta_next, d_tab_a, d_tab_b, d_open, d_open + C);
+    CUDA_CHECK(cudaMemcpyAsync(W + L.off_local_values, d_open, 16ull * C, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(W + L.off_next_values, d_open + C, 16ull * C, cudaMemcpyDeviceToHost, st));
+  }
   sb_openings_device(ctx, ctx->qcoeffs.as<u64>(), log_n, nq, zeta, nullptr, d_tab_a, d_tab_b, d_open + 2ull * C, nullptr);
-  CUDA_CHECK(cudaMemcpyAsync(W + L.off_local_values, d_open, 16ull * C, cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaMemcpyAsync(W + L.off_next_values, d_open + C, 16ull * C, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaMemcpyAsync(W + L.off_quotient_polys, d_open + 2ull * C, 16ull * nq, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaEventRecord(ev[5], st));
   CUDA_CHECK(cudaStreamSynchronize(st));
@@ -236,7 +259,12 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
   e2_t* d_apow = ar.take<e2_t>((size_t)C + nq);
   e2_t* d_partial = ar.take<e2_t>(partial_elems);
   e2_t* d_F = ar.take<e2_t>(2ull * n);
-  sb_combine_device(ctx, ctx->coeffs.as<u64>(), log_n, C, alpha, 0, d_apow, d_partial, partial_elems, d_F);
+  if (hooks) {
+    const u64 al[2] = {alpha.a, alpha.b};
+    HOOK(hooks->combine(hooks->user, al, (u64*)d_F));
+  } else {
+    sb_combine_device(ctx, ctx->coeffs.as<u64>(), log_n, C, alpha, 0, d_apow, d_partial, partial_elems, d_F);
+  }
   sb_combine_device(ctx, ctx->qcoeffs.as<u64>(), log_n, nq, alpha, C, d_apow, d_partial, partial_elems, d_F + n);
   std::vector<e2_t> hF(2ull * n);
   CUDA_CHECK(cudaMemcpyAsync(hF.data(), d_F, 32ull * n, cudaMemcpyDeviceToHost, st));
@@ -333,7 +361,14 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
   uint32_t* d_idx = ar.take<uint32_t>(2ull * nQ);
   u64* d_queries = ar.take<u64>(L.query_stride * nQ);
   CUDA_CHECK(cudaMemcpyAsync(d_idx, h_idx.data(), 8ull * nQ, cudaMemcpyHostToDevice, st));
-  sb_gather_leaf_device(ctx, d_queries, L.query_stride, L.q_off_trace_leaf, ctx->lde.as<u64>(), N, C, d_idx + nQ, nQ);
+  if (hooks) {
+    u64* d_rows = ar.take<u64>((size_t)nQ * C);
+    HOOK(hooks->query_rows(hooks->user, h_idx.data() + nQ, nQ, d_rows));
+    CUDA_CHECK(cudaMemcpy2DAsync(d_queries + L.q_off_trace_leaf, 8ull * L.query_stride, d_rows, 8ull * C, 8ull * C, nQ,
+                                 cudaMemcpyDeviceToDevice, st));
+  } else {
+    sb_gather_leaf_device(ctx, d_queries, L.query_stride, L.q_off_trace_leaf, ctx->lde.as<u64>(), N, C, d_idx + nQ, nQ);
+  }
   sb_gather_path_device(ctx, d_queries, L.query_stride, L.q_off_trace_path, ctx->tree.as<u64>(), N, L.trace_path_len, d_idx, 0, nQ);
   sb_gather_leaf_device(ctx, d_queries, L.query_stride, L.q_off_quot_leaf, ctx->qlde.as<u64>(), N, nq, d_idx + nQ, nQ);
   sb_gather_path_device(ctx, d_queries, L.query_stride, L.q_off_quot_path, ctx->qtree.as<u64>(), N, L.trace_path_len, d_idx, 0, nQ);
@@ -415,6 +450,85 @@ int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, con
     sb_proof_free(proof);
     return sb_fail(ctx, SbError{SB_EINVAL, e.what()});
   }
+}
+
+int sb_prove_sharded(sb_ctx* ctx, const sb_params* p, const sb_shard_hooks* hooks, const uint64_t* public_inputs, sb_proof** out) {
+  if (!ctx || !p || !out || !hooks || !hooks->commit || !hooks->quotient || !hooks->openings || !hooks->combine || !hooks->query_rows)
+    return SB_EINVAL;
+  sb_proof* proof = nullptr;
+  try {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (p->n_cols == 0 || p->log_n < 1 || p->log_n > 13 || p->rate_bits < 1 || p->rate_bits > 4 ||
+        p->cap_height > p->log_n + p->rate_bits)
+      SB_THROW(SB_EINVAL, "bad parameters (n_cols %u, log_n %u, rate_bits %u, cap_height %u)", p->n_cols, p->log_n, p->rate_bits, p->cap_height);
+    proof = new sb_proof();
+    memset(proof, 0, sizeof(*proof));
+    proof->layout = proof_layout(*p);
+    proof->words = (u64*)pinned_take(8ull * proof->layout.total_words);
+    prove_impl(ctx, p, nullptr, SB_TRACE_DEVICE_COLMAJOR_U64, public_inputs, proof, hooks);
+    *out = proof;
+    return SB_OK;
+  } catch (const SbError& e) {
+    cudaStreamSynchronize(ctx->stream);
+    sb_proof_free(proof);
+    return sb_fail(ctx, e);
+  } catch (const std::exception& e) {
+    cudaStreamSynchronize(ctx->stream);
+    sb_proof_free(proof);
+    return sb_fail(ctx, SbError{SB_EINVAL, e.what()});
+  }
+}
+
+// P_c(zeta) and P_c(g zeta) for a column slice of coefficients (this rank's share of StarkOpeningSet::new)
+int sb_openings_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_coeffs, uint32_t n_cols_local, const uint64_t* zeta,
+                            const uint64_t* zeta_next, uint64_t* local_out, uint64_t* next_out) {
+  if (!ctx || !p || !d_coeffs || !zeta || !zeta_next || !local_out || !next_out) return SB_EINVAL;
+  try {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (n_cols_local == 0) return SB_OK;
+    const uint32_t n = 1u << p->log_n;
+    ctx->scratch3.ensure(32ull * n + 32ull * n_cols_local + 1024);
+    Arena ar(ctx->scratch3.p, ctx->scratch3.cap);
+    e2_t* d_tab_a = ar.take<e2_t>(n);
+    e2_t* d_tab_b = ar.take<e2_t>(n);
+    e2_t* d_open = ar.take<e2_t>(2ull * n_cols_local);
+    const e2_t za = e2_make(zeta[0], zeta[1]), zb = e2_make(zeta_next[0], zeta_next[1]);
+    sb_openings_device(ctx, d_coeffs, p->log_n, n_cols_local, za, &zb, d_tab_a, d_tab_b, d_open, d_open + n_cols_local);
+    CUDA_CHECK(cudaMemcpyAsync(local_out, d_open, 16ull * n_cols_local, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(next_out, d_open + n_cols_local, 16ull * n_cols_local, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+
+// sum_c alpha^(first_col + c) coeffs_c over a column slice (this rank's share of the batch reduce in prove_openings)
+int sb_combine_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_coeffs, uint32_t n_cols_local, const uint64_t* alpha,
+                           uint32_t first_col, uint64_t* d_out) {
+  if (!ctx || !p || !d_coeffs || !alpha || !d_out) return SB_EINVAL;
+  try {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    const uint32_t n = 1u << p->log_n;
+    if (n_cols_local == 0) { CUDA_CHECK(cudaMemsetAsync(d_out, 0, 16ull * n, ctx->stream)); return SB_OK; }
+    const size_t partial_elems = (size_t)(ctx->sm_count * 16 + 8) * 128 + 2 * (size_t)n;
+    ctx->scratch3.ensure(16ull * (n_cols_local + 8) + 16ull * partial_elems + 1024);
+    Arena ar(ctx->scratch3.p, ctx->scratch3.cap);
+    e2_t* d_apow = ar.take<e2_t>((size_t)n_cols_local + 8);
+    e2_t* d_partial = ar.take<e2_t>(partial_elems);
+    sb_combine_device(ctx, d_coeffs, p->log_n, n_cols_local, e2_make(alpha[0], alpha[1]), first_col, d_apow, d_partial, partial_elems,
+                      (e2_t*)d_out);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+
+int sb_memcpy_device(sb_ctx* ctx, void* d_dst, const void* d_src, uint64_t bytes) {
+  if (!ctx || !d_dst || !d_src) return SB_EINVAL;
+  try {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    CUDA_CHECK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
 }
 
 void sb_proof_free(sb_proof* proof) {

@@ -11,6 +11,12 @@ PolynomialBatch::from_values as called by starky::prover::prove (aggregate_proof
                               lives on another rank when a block is shorter than one coset, so the ranks all-gather
                               their FIRST rows (C x 8 bytes each) and each picks its successor's; the 2 x N quotient
                               values (<= 0.5 MB) are all-gathered for the (small, unsharded) quotient commitment
+    tail     prove_sharded    every rank runs the library's proof orchestration (sb_prove_sharded: same transcript, same
+                              proof everywhere); the five distributed steps are hooks implemented here: the commitment
+                              and quotient above, the openings (column-sharded coefficient slices, all-gather of
+                              2 C/G extension values), the FRI batch combine (per-rank partial sums with the rank's
+                              alpha-power offset, all-gather of n extension values, added mod p) and the query rows
+                              (84 x C values, summed over the ranks that own them)
 
 The module is backend-agnostic plumbing (torch.distributed only): `backend` supplies the three kernels -- GpuBackend
 (libstarkyb200 through the C ABI, device pointers of torch CUDA tensors) in production, an oracle-backed CPU double in
@@ -59,27 +65,16 @@ def shard_plan(n_cols, log_n, rate_bits, world):
     return ShardPlan(n_cols, log_n, rate_bits, world, starts, counts, n_lde // world)
 
 
-def commit_sharded(backend, plan, rank, local_trace, group=None):
+def commit_sharded(backend, plan, rank, local_trace, group=None, comm=None):
     """Runs the sharded commitment on this rank.  local_trace: this rank's columns, [C_rank][n].
     Returns dict(cap=[2^cap_height][4] uint64 numpy, digests=[N][4] tensor in device position order, rows=tensor
     [C][N/world] (this rank's row block of the LDE, all columns))."""
     import torch
-    import torch.distributed as dist
+    comm = comm or TorchGroup(plan.world, rank, group)
     slabs = backend.lde_cols(plan, rank, local_trace)                       # [world][C_rank][rows] flattened
-    if plan.world == 1:
-        rows = slabs
-    else:
-        rows = torch.empty(plan.n_cols * plan.rows_per_rank, dtype=torch.int64, device=slabs.device)
-        dist.all_to_all_single(rows, slabs, output_split_sizes=plan.recv_splits(rank),
-                               input_split_sizes=plan.send_splits(rank), group=group)
-    rows = rows.view(plan.n_cols, plan.rows_per_rank)
+    rows = comm.all_to_all_rows(slabs, plan).view(plan.n_cols, plan.rows_per_rank)
     dig = backend.hash_rows(plan, rows)                                     # [rows][4], position order
-    if plan.world == 1:
-        digests = dig
-    else:
-        parts = [torch.empty_like(dig) for _ in range(plan.world)]
-        dist.all_gather(parts, dig, group=group)
-        digests = torch.cat(parts, dim=0)
+    digests = torch.cat(comm.all_gather(dig), dim=0)
     cap = backend.merkle_cap(plan, digests)
     return dict(cap=cap, digests=digests, rows=rows)
 
@@ -94,28 +89,200 @@ def successor_block(plan, rank):
     return nxt if nxt % blocks_per_coset else nxt - blocks_per_coset
 
 
-def quotient_sharded(backend, plan, rank, rows, cap, public_inputs, group=None):
+def quotient_sharded(backend, plan, rank, rows, cap, public_inputs, group=None, comm=None):
     """Row-sharded quotient evaluation (this rank's share of starky::prover::compute_quotient_polys, SURVEY a7 / 8e).
     rows: [C][N/world] from commit_sharded; cap: the trace cap every rank holds.  Returns dict(alphas, q = tensor
     [2][N] in device position order, gathered on every rank; q_local = this rank's [2][N/world])."""
     import torch
-    import torch.distributed as dist
+    comm = comm or TorchGroup(plan.world, rank, group)
     alphas = backend.alphas(cap)
     halo = None
     nb = successor_block(plan, rank)
     if nb is not None:
-        first = rows[:, 0].contiguous()
-        parts = [torch.empty_like(first) for _ in range(plan.world)]
-        dist.all_gather(parts, first, group=group)
-        halo = parts[nb]
+        halo = comm.all_gather(rows[:, 0].contiguous())[nb]
     q_local = backend.quotient_rows(plan, rank, rows, halo, public_inputs, alphas)          # [2][rows_per_rank]
-    if plan.world == 1:
-        q = q_local
-    else:
-        parts = [torch.empty_like(q_local) for _ in range(plan.world)]
-        dist.all_gather(parts, q_local, group=group)
-        q = torch.cat(parts, dim=1)
+    q = torch.cat(comm.all_gather(q_local), dim=1)
     return dict(alphas=alphas, q=q, q_local=q_local)
+
+
+P = 0xFFFFFFFF00000001
+
+
+def _addmod(a, b):
+    """(a + b) mod p on canonical uint64 numpy arrays."""
+    s = a + b
+    s = np.where(s < a, s + np.uint64(0xFFFFFFFF), s)          # wrapped: 2^64 = 2^32 - 1 (mod p); cannot wrap twice
+    return np.where(s >= np.uint64(P), s - np.uint64(P), s)
+
+
+class TorchGroup:
+    """The collectives of prove_sharded over torch.distributed (NCCL on the GPUs of one box, gloo in the CPU tests)."""
+
+    def __init__(self, world, rank, group=None):
+        self.world, self.rank, self.group = world, rank, group
+
+    def all_gather(self, t):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return [t]
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return parts
+
+    def sum_int64(self, t):
+        """Plain integer sum (used where exactly one rank contributes a non-zero value per element)."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_to_all_rows(self, slabs, plan):
+        """slab b of every rank -> rank b: [world][C_rank][rows] on every rank -> [C][rows] on every rank."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return slabs
+        rows = torch.empty(plan.n_cols * plan.rows_per_rank, dtype=torch.int64, device=slabs.device)
+        dist.all_to_all_single(rows, slabs, output_split_sizes=plan.recv_splits(self.rank),
+                               input_split_sizes=plan.send_splits(self.rank), group=self.group)
+        return rows
+
+
+class ThreadGroup:
+    """The same collectives between `world` host threads of ONE process (one sb_ctx per thread, all on one GPU): the
+    single-GPU test double of the NCCL group -- the control flow of every rank is exactly the multi-process one."""
+
+    class Shared:
+        def __init__(self, world):
+            import threading
+            self.world, self.barrier, self.box = world, threading.Barrier(world), [None] * world
+
+    def __init__(self, shared, rank):
+        self.sh, self.world, self.rank, self.group = shared, shared.world, rank, None
+
+    def _exchange(self, t):
+        import torch
+        torch.cuda.synchronize()
+        self.sh.box[self.rank] = t
+        self.sh.barrier.wait()
+        parts = list(self.sh.box)
+        self.sh.barrier.wait()
+        return parts
+
+    def all_gather(self, t):
+        return [x.clone() for x in self._exchange(t.contiguous())]
+
+    def sum_int64(self, t):
+        parts = self._exchange(t)
+        out = parts[0].clone()
+        for x in parts[1:]:
+            out += x
+        return out
+
+    def all_to_all_rows(self, slabs, plan):
+        import torch
+        parts = self._exchange(slabs)
+        mine = [parts[g].view(self.world, plan.col_count[g], plan.rows_per_rank)[self.rank].reshape(-1) for g in range(self.world)]
+        return torch.cat(mine)
+
+
+def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None):
+    """One proof with the trace sharded over plan.world GPUs: every rank calls this with its column slice
+    and gets the same proof.  backend: GpuBackend of this rank; comm: TorchGroup (default: the default process group)."""
+    import torch
+    from . import binding as B
+    C = B.C
+    comm = comm or TorchGroup(plan.world, rank)
+    p, ctx, lib = backend.p, backend.ctx, B.lib()
+    n = 1 << plan.log_n
+    c0, cg = plan.col_start[rank], plan.col_count[rank]
+    pis = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+    st = {}
+
+    def guard(fn):
+        def run(*a):
+            try:
+                fn(*a)
+                return 0
+            except B.SbError as e:
+                st["error"] = e
+                return e.code if e.code else -1
+            except Exception as e:                      # never unwind through the C frames
+                st["error"] = e
+                return -1
+        return run
+
+    def h_commit(_user, cap_out):
+        com = commit_sharded(backend, plan, rank, local_trace, comm=comm)
+        st["rows"], st["cap"] = com["rows"], com["cap"]
+        flat = np.ascontiguousarray(com["cap"], dtype=np.uint64).reshape(-1)
+        C.memmove(cap_out, flat.ctypes.data, flat.nbytes)
+
+    def h_quotient(_user, alphas, d_q_out):
+        al = np.array([alphas[0], alphas[1]], np.uint64)
+        halo, nb = None, successor_block(plan, rank)
+        if nb is not None:
+            halo = comm.all_gather(st["rows"][:, 0].contiguous())[nb]
+        q_local = backend.quotient_rows(plan, rank, st["rows"], halo, pis, al)
+        q = torch.cat(comm.all_gather(q_local), dim=1).contiguous()                    # [2][N], position order
+        backend._sync_torch()
+        ctx._check(lib.sb_memcpy_device(ctx._h, d_q_out, q.data_ptr(), 16 * plan.n_lde))
+
+    def h_openings(_user, zeta, zeta_next, local_out, next_out):
+        z = np.array([zeta[0], zeta[1]], np.uint64)
+        zn = np.array([zeta_next[0], zeta_next[1]], np.uint64)
+        mine = np.zeros((2, max(cg, 1), 2), np.uint64)
+        if cg:
+            ctx._check(lib.sb_openings_cols_device(ctx._h, C.byref(p), backend.coeffs.data_ptr(), cg, z.ctypes.data, zn.ctypes.data,
+                                                   mine[0].ctypes.data, mine[1].ctypes.data))
+        # ragged column counts: pad every slice to the largest, gather, cut
+        width = max(plan.col_count)
+        pad = np.zeros((2, width, 2), np.uint64)
+        pad[:, :cg] = mine[:, :cg]
+        parts = comm.all_gather(torch.from_numpy(pad.view(np.int64)).to(backend.device))
+        for g, t in enumerate(parts):
+            a = t.cpu().numpy().view(np.uint64)
+            k0, kc = plan.col_start[g], plan.col_count[g]
+            C.memmove(C.addressof(local_out.contents) + 16 * k0, np.ascontiguousarray(a[0, :kc]).ctypes.data, 16 * kc)
+            C.memmove(C.addressof(next_out.contents) + 16 * k0, np.ascontiguousarray(a[1, :kc]).ctypes.data, 16 * kc)
+
+    def h_combine(_user, alpha, d_out):
+        al = np.array([alpha[0], alpha[1]], np.uint64)
+        part = torch.zeros((n, 2), dtype=torch.int64, device=backend.device)
+        backend._sync_torch()
+        if cg:
+            ctx._check(lib.sb_combine_cols_device(ctx._h, C.byref(p), backend.coeffs.data_ptr(), cg, al.ctypes.data, c0, part.data_ptr()))
+        total = None
+        for t in comm.all_gather(part):
+            a = t.cpu().numpy().view(np.uint64)
+            total = a.copy() if total is None else _addmod(total, a)
+        dev = torch.from_numpy(total.view(np.int64)).to(backend.device)
+        backend._sync_torch()
+        ctx._check(lib.sb_memcpy_device(ctx._h, d_out, dev.data_ptr(), 16 * n))
+
+    def h_query_rows(_user, positions, count, d_rows_out):
+        pos = np.array([positions[i] for i in range(count)], np.int64)
+        R = plan.rows_per_rank
+        own = (pos // R) == rank
+        rows = torch.zeros((count, plan.n_cols), dtype=torch.int64, device=backend.device)
+        if own.any():
+            idx = torch.from_numpy(pos[own] - rank * R).to(backend.device)
+            rows[torch.from_numpy(np.nonzero(own)[0]).to(backend.device)] = st["rows"][:, idx].t()
+        rows = comm.sum_int64(rows).contiguous()   # exactly one rank holds each row, the others contribute zeros
+        backend._sync_torch()
+        ctx._check(lib.sb_memcpy_device(ctx._h, d_rows_out, rows.data_ptr(), 8 * count * plan.n_cols))
+
+    hooks = B.ShardHooks(None, B.HOOK_COMMIT(guard(h_commit)), B.HOOK_QUOTIENT(guard(h_quotient)),
+                         B.HOOK_OPENINGS(guard(h_openings)), B.HOOK_COMBINE(guard(h_combine)),
+                         B.HOOK_QUERY_ROWS(guard(h_query_rows)))
+    out = C.POINTER(B._CProof)()
+    rc = lib.sb_prove_sharded(ctx._h, C.byref(p), C.byref(hooks), pis.ctypes.data if pis.size else None, C.byref(out))
+    if rc:
+        if isinstance(st.get("error"), Exception) and not isinstance(st["error"], B.SbError):
+            raise st["error"]
+        ctx._check(rc)
+    return B.Proof(out)
 
 
 class GpuBackend:

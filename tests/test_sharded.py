@@ -198,3 +198,75 @@ def test_gpu_row_sharded_quotient_matches_unsharded(world):
             assert np.array_equal(got.cpu().numpy().view(np.uint64), want[:, h * rb:(h + 1) * rb]), h
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------- the whole proof, sharded (SURVEY 8e small collectives)
+def _prove_sharded_threads(world, p, trace, pis, airbin=None, stark_id=None):
+    """`world` host threads, one sb_ctx each on the one GPU, ThreadGroup collectives: the control flow of every rank is the
+    multi-process one.  Returns the proofs of all ranks."""
+    import threading
+    from starky_bls12_381_b200.sharded import GpuBackend, ThreadGroup, prove_sharded
+    plan = shard_plan(p.n_cols, p.log_n, p.rate_bits, world)
+    shared = ThreadGroup.Shared(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        ctx = sb.Context(0)
+        try:
+            if airbin:
+                ctx.air_load(stark_id, airbin)
+            be = GpuBackend(ctx, p)
+            c0, cg = plan.col_start[rank], plan.col_count[rank]
+            out[rank] = prove_sharded(be, plan, rank, trace[c0:c0 + cg], pis, comm=ThreadGroup(shared, rank))
+        except Exception as e:          # noqa: BLE001 -- a dead rank would hang the others at the barrier
+            errs.append(e)
+            shared.barrier.abort()
+        finally:
+            ctx.close()
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,log_n", [(1, 6), (2, 6), (4, 7), (8, 8)])
+def test_gpu_sharded_proof_of_a_valid_trace_equals_the_single_gpu_proof(world, log_n, tmp_path):
+    import toy_air
+    from helpers import to_oracle_params
+    air = toy_air.limbs(str(tmp_path), 4)
+    trace, pis = air["witness"](log_n)
+    p = sb.Params(205, log_n, air["n_cols"], air["n_pis"], air["degree"], air["rate_bits"], 4, 2, 16, 84, 4, 5, 0, 0, 0)
+    ctx = sb.Context(0)
+    try:
+        ctx.air_load(205, air["airbin"])
+        want = ctx.prove(p, trace, pis)
+    finally:
+        ctx.close()
+    proofs = _prove_sharded_threads(world, p, trace, pis, airbin=air["airbin"], stark_id=205)
+    for pr in proofs:
+        assert np.array_equal(pr.words, want.words)
+    assert O.verify(air["flat"], to_oracle_params(p), proofs[0].words) == 0, O.err()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,world,log_n", [("miller_loop", 4, 6), ("pairing_precomp", 2, 5), ("ecc_agg", 8, 7)])
+def test_gpu_sharded_proof_with_the_reference_constraint_programs(name, world, log_n):
+    """Ragged column slices (97330 = 2 x 24333 + 2 x 24332), the real constraint programs, random traces."""
+    from starky_bls12_381_b200 import airfiles
+    info = sb.STARKS[name]
+    airfiles.air_path(name, "airbin")
+    p = sb.standard_params(info.stark_id, log_n, flags=sb.Flags.ALLOW_INVALID_TRACE)
+    rng = np.random.default_rng(0xB2003000 + info.stark_id)
+    trace = random_trace(rng, info.columns, log_n)
+    pis = rng.integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
+    ctx = sb.Context(0)
+    try:
+        want = ctx.prove(p, trace, pis)
+    finally:
+        ctx.close()
+    for pr in _prove_sharded_threads(world, p, trace, pis):
+        assert np.array_equal(pr.words, want.words)
