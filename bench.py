@@ -160,7 +160,26 @@ def full_set_assignment(world):
     return out
 
 
-def run_full_set(sb, contexts, names, rank, timed):
+def full_set_plan(world):
+    """How the seven proofs are laid over `world` GPUs.  With a whole 8-GPU box the critical path (FinalExp, ~630 ms on one
+    GPU) is sharded over four GPUs (SURVEY 8e "proof-level parallelism on top") and the other six proofs share the rest;
+    otherwise whole proofs are assigned longest-first.  Returns (ranks of the sharded FinalExp proof or [], per-rank lists)."""
+    if world < 8:
+        return [], full_set_assignment(world)
+    rest = full_set_assignment_of([k for k in FULL_SET if k != "final_exp"], world - 4)
+    return [0, 1, 2, 3], [[] for _ in range(4)] + rest
+
+
+def full_set_assignment_of(names, world):
+    loads, out = [0.0] * world, [[] for _ in range(world)]
+    for name in sorted(names, key=lambda k: -FULL_SET_COST[k]):
+        g = min(range(world), key=lambda r: loads[r])
+        out[g].append(name)
+        loads[g] += FULL_SET_COST[name]
+    return out
+
+
+def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
     """Proves `names` on this rank's GPU, end to end from pinned host memory, with len(contexts) proofs in flight (one host
     thread per context, work queue in cost order).  Returns (seconds max over ranks, per-proof ms)."""
     import torch
@@ -182,6 +201,10 @@ def run_full_set(sb, contexts, names, rank, timed):
     phases = [([j for j in jobs if few(j)], contexts[:2]), ([j for j in jobs if not few(j)], contexts[:1])]
 
     def go():
+        if sharded_job is not None:
+            t0 = time.perf_counter()
+            sharded_job()
+            per.append(("final_exp(sharded)", 1e3 * (time.perf_counter() - t0)))
         for phase_jobs, phase_ctx in phases:
             queue = list(phase_jobs)
 
@@ -377,12 +400,27 @@ def main():
     if not args.no_full_set:
         for nm in set(FULL_SET):
             airfiles.air_path(nm, "airbin")
-        mine = full_set_assignment(world)[rank]
-        dt_full, per = run_full_set(sb, [ctx, ctx2], mine, rank, timed)
+        fe_ranks, per_rank = full_set_plan(world)
+        mine = per_rank[rank]
+        sharded_job = None
+        if fe_ranks:
+            grp = dist.new_group(ranks=fe_ranks)                      # collective: every rank calls it
+            if rank in fe_ranks:
+                fi = sb.STARKS["final_exp"]
+                sp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+                splan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, len(fe_ranks))
+                sr = fe_ranks.index(rank)
+                srng = np.random.Generator(np.random.PCG64(0xB2400000 + sr))
+                slocal = torch.from_numpy(srng.integers(0, 1 << 32, (splan.col_count[sr], fi.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
+                spis = np.random.Generator(np.random.PCG64(0xB2400099)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
+                sbackend, scomm = GpuBackend(ctx, sp), TorchGroup(len(fe_ranks), sr, grp)
+                sharded_job = lambda: prove_sharded(sbackend, splan, sr, slocal, spis, comm=scomm)
+        dt_full, per = run_full_set(sb, [ctx, ctx2], mine, rank, timed, sharded_job)
         full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
                             "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
-                "assignment": full_set_assignment(world), "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
-                "note": "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run two in "
+                "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
+                "note": "with 8 GPUs FinalExp is sharded over four (sb_prove_sharded) and the other six proofs share the rest; otherwise "
+                        "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run two in "
                         "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
     ctx2.close()
     clocks = sampler.stop() if rank == 0 else None

@@ -21,3 +21,12 @@ def test_workload_tables_are_consistent():
     import starky_bls12_381_b200 as sb
     assert set(bench.WORKLOADS) == set(sb.STARKS) == set(bench.K_CONSTRAINTS)
     assert set(bench.FULL_SET) == set(sb.STARKS)
+
+
+def test_full_set_plan_shards_final_exp_on_a_whole_box():
+    fe, per = bench.full_set_plan(8)
+    assert fe == [0, 1, 2, 3] and per[:4] == [[], [], [], []]
+    assert sorted(x for r in per for x in r) == sorted(k for k in bench.FULL_SET if k != "final_exp")
+    assert max(sum(bench.FULL_SET_COST[x] for x in r) for r in per) == bench.FULL_SET_COST["miller_loop"]
+    fe, per = bench.full_set_plan(4)
+    assert fe == [] and per == bench.full_set_assignment(4)
