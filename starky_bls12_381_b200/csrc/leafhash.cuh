@@ -270,6 +270,56 @@ __global__ void __launch_bounds__(LAYOUT == 2 ? 512 : 384) leaf_sponge_w12_kerne
 #include <type_traits>
 
 #include "poseidon_fast.h"
+// sum of 64x64 products as lo + hi 2^64 + top 2^128
+struct Acc192 { u64 lo, hi; u32 top; };
+__device__ __forceinline__ void acc192_mul(Acc192& a, u64 x, u64 y) {
+  const u64 pl = x * y, ph = __umul64hi(x, y);
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+      : "+l"(a.lo), "+l"(a.hi), "+r"(a.top) : "l"(pl), "l"(ph));
+}
+// (lo, hi, top) mod p -> lazy u64.   2^128 = -2^32 (mod p):  top * 2^128 = top * (p - 2^32) = top * (2^64 - 2^33 + 1)
+__device__ __forceinline__ u64 acc192_reduce(const Acc192& a) {
+  u64 lo = a.lo, hi = a.hi;
+  // t = top * (2^64 - 2^33 + 1) = (top - borrow) : (top - top 2^33), added to hi:lo; a wrap of 2^128 (at most one) is again
+  // worth 2^64 - 2^33 + 1, and after a wrap hi is tiny, so the second addition cannot wrap
+  asm("{\n\t"
+      ".reg .u64 t, sb, tlo, thi, c2, s2, ulo, uhi;\n\t"
+      "cvt.u64.u32 t, %2;\n\t"
+      "shl.b64 sb, t, 33;\n\t"
+      "sub.cc.u64 tlo, t, sb;\n\t"
+      "subc.u64 thi, t, 0;\n\t"
+      "add.cc.u64 %0, %0, tlo;\n\t"
+      "addc.cc.u64 %1, %1, thi;\n\t"
+      "addc.u64 c2, 0, 0;\n\t"
+      "shl.b64 s2, c2, 33;\n\t"
+      "sub.cc.u64 ulo, c2, s2;\n\t"
+      "subc.u64 uhi, c2, 0;\n\t"
+      "add.cc.u64 %0, %0, ulo;\n\t"
+      "addc.u64 %1, %1, uhi;\n\t"
+      "}"
+      : "+l"(lo), "+l"(hi) : "r"(a.top));
+  // fold the 128-bit value (x3:x2:x1:x0) exactly like gl_mul_lazy
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 nc, nb;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"
+      "subc.u32 %1, %4, 0;\n\t"
+      "add.cc.u32 %1, %1, %3;\n\t"
+      "addc.u32 nc, 0, 0;\n\t"
+      "neg.s32 nc, nc;\n\t"
+      "sub.cc.u32 %0, %0, %5;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 nb, 0, 0;\n\t"
+      "add.cc.u32 %0, %0, nc;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "sub.cc.u32 %0, %0, nb;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+  return ((u64)r1 << 32) | r0;
+}
+
 static __constant__ u64 c_fast_post[22] = POSEIDON_FAST_POST;
 static __constant__ u64 c_fast_what[22 * 11] = POSEIDON_FAST_WHAT;
 static __constant__ u64 c_fast_vs[22 * 11] = POSEIDON_FAST_VS;
@@ -332,17 +382,11 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         const u64 v = poseidon_sbox(s);
         xch[xb][wid][lane] = v; xch[xb][wid + 12][lane] = v;
         named_bar_sync(1, 384);
-        u64 acc = c_fast_k3[wid];
-        u32 cnt = 0;
+        // twelve unreduced 128-bit products into one 192-bit accumulator, one reduction (instead of twelve)
+        Acc192 acc = {c_fast_k3[wid], 0, 0};
 #pragma unroll
-        for (int i = 0; i < 12; i++) {
-          const u64 pr = gl_mul_lazy(c_fast_d3rot[12 * wid + i], xch[xb][wid + i][lane]);
-          acc += pr; cnt += (acc < pr);
-        }
-        const u64 tt = (u64)cnt * GL_EPS;    // every wrap of 2^64 is worth eps; cnt <= 12 so tt < 2^36
-        u64 r = acc + tt;
-        if (r < tt) r += GL_EPS;
-        s = gl_canon(r);
+        for (int i = 0; i < 12; i++) acc192_mul(acc, c_fast_d3rot[12 * wid + i], xch[xb][wid + i][lane]);
+        s = gl_canon(acc192_reduce(acc));
         xb ^= 1;
       }
     }
@@ -460,56 +504,6 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
 //   per round: y = x0^7 + a_r;   x0 = 25 y + sum_i w^_r[i] x_i (one 192-bit accumulator, one reduction);   x_i += v_r[i] y
 // ---------------------------------------------------------------------------------------------------------
 static __constant__ u64 c_fast_d3[12 * 12] = POSEIDON_FAST_D3;
-
-// sum of 64x64 products as lo + hi 2^64 + top 2^128
-struct Acc192 { u64 lo, hi; u32 top; };
-__device__ __forceinline__ void acc192_mul(Acc192& a, u64 x, u64 y) {
-  const u64 pl = x * y, ph = __umul64hi(x, y);
-  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
-      : "+l"(a.lo), "+l"(a.hi), "+r"(a.top) : "l"(pl), "l"(ph));
-}
-// (lo, hi, top) mod p -> lazy u64.   2^128 = -2^32 (mod p):  top * 2^128 = top * (p - 2^32) = top * (2^64 - 2^33 + 1)
-__device__ __forceinline__ u64 acc192_reduce(const Acc192& a) {
-  u64 lo = a.lo, hi = a.hi;
-  // t = top * (2^64 - 2^33 + 1) = (top - borrow) : (top - top 2^33), added to hi:lo; a wrap of 2^128 (at most one) is again
-  // worth 2^64 - 2^33 + 1, and after a wrap hi is tiny, so the second addition cannot wrap
-  asm("{\n\t"
-      ".reg .u64 t, sb, tlo, thi, c2, s2, ulo, uhi;\n\t"
-      "cvt.u64.u32 t, %2;\n\t"
-      "shl.b64 sb, t, 33;\n\t"
-      "sub.cc.u64 tlo, t, sb;\n\t"
-      "subc.u64 thi, t, 0;\n\t"
-      "add.cc.u64 %0, %0, tlo;\n\t"
-      "addc.cc.u64 %1, %1, thi;\n\t"
-      "addc.u64 c2, 0, 0;\n\t"
-      "shl.b64 s2, c2, 33;\n\t"
-      "sub.cc.u64 ulo, c2, s2;\n\t"
-      "subc.u64 uhi, c2, 0;\n\t"
-      "add.cc.u64 %0, %0, ulo;\n\t"
-      "addc.u64 %1, %1, uhi;\n\t"
-      "}"
-      : "+l"(lo), "+l"(hi) : "r"(a.top));
-  // fold the 128-bit value (x3:x2:x1:x0) exactly like gl_mul_lazy
-  u32 r0, r1;
-  asm("{\n\t"
-      ".reg .u32 nc, nb;\n\t"
-      "sub.cc.u32 %0, %2, %4;\n\t"
-      "subc.u32 %1, %4, 0;\n\t"
-      "add.cc.u32 %1, %1, %3;\n\t"
-      "addc.u32 nc, 0, 0;\n\t"
-      "neg.s32 nc, nc;\n\t"
-      "sub.cc.u32 %0, %0, %5;\n\t"
-      "subc.cc.u32 %1, %1, 0;\n\t"
-      "subc.u32 nb, 0, 0;\n\t"
-      "add.cc.u32 %0, %0, nc;\n\t"
-      "addc.u32 %1, %1, 0;\n\t"
-      "sub.cc.u32 %0, %0, nb;\n\t"
-      "subc.u32 %1, %1, 0;\n\t"
-      "}"
-      : "=&r"(r0), "=&r"(r1)
-      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
-  return ((u64)r1 << 32) | r0;
-}
 
 // full round on a register-resident state: s[i] holds the pre-S-box value (constant already added); `next` = the
 // constants of the coming round (folded into the MDS accumulators)
