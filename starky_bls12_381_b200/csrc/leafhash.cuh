@@ -320,6 +320,7 @@ __device__ __forceinline__ u64 acc192_reduce(const Acc192& a) {
   return ((u64)r1 << 32) | r0;
 }
 
+static __constant__ u32 c_opaque_zero = 0;     // a zero ptxas cannot see through
 static __constant__ u64 c_fast_post[22] = POSEIDON_FAST_POST;
 static __constant__ u64 c_fast_what[22 * 11] = POSEIDON_FAST_WHAT;
 static __constant__ u64 c_fast_vs[22 * 11] = POSEIDON_FAST_VS;
@@ -328,6 +329,12 @@ static __constant__ u64 c_fast_k3[12] = POSEIDON_FAST_K3;
 static __constant__ u64 c_fast_u[22] = POSEIDON_FAST_U;
 static __constant__ u64 c_fast_first[12] = POSEIDON_FAST_FIRST;
 
+#ifdef SP_TRACE
+__device__ long long* g_sp_trace;      // [64] clock64 stamps of block 0 / lane 0 of the word-0 warp, chunk 1 (lab only)
+#define SP_STAMP(i) do { if (blockIdx.x == 0 && lane == 0 && m == 1) g_sp_trace[(i)] = clock64(); } while (0)
+#else
+#define SP_STAMP(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                              uint32_t n_leaves, unsigned log_block,
                                                              u64* __restrict__ digests) {
@@ -358,6 +365,7 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         if (wid < 8 && c < leaf_len) nx = cols[(size_t)c * n_leaves + pos];
       }
       s = gl_add_lazy_canon(s, c_poseidon_rc[wid]);
+      if (crit) SP_STAMP(0);
 
       // full round rd: publish x^7, read the twelve words rotated, small-coefficient MDS row + constant `next`
       auto full_round = [&](u64 next) {
@@ -374,9 +382,10 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         xb ^= 1;
       };
 #pragma unroll 1
-      for (int rd = 0; rd < 3; rd++) full_round(c_poseidon_rc[12 * (rd + 1) + wid]);
+      for (int rd = 0; rd < 3; rd++) { full_round(c_poseidon_rc[12 * (rd + 1) + wid]); if (crit) SP_STAMP(1 + rd); }
       if (crit) {
         full_round(c_fast_first[0]);        // word 0 passes the initial matrix unchanged
+        SP_STAMP(4);
       } else {
         // round 3 with the dense initial matrix folded in: x_j = sum_i D3ROT[j][i] v_{(j+i) % 12} + K3[j]
         const u64 v = poseidon_sbox(s);
@@ -399,9 +408,13 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         const u64 x2 = gl_mul_lazy(x0, x0);
         const u64 x4 = gl_mul_lazy(x2, x2), x3 = gl_mul_lazy(x2, x0);
         const u64 x7 = gl_mul_lazy(x3, x4);
+        if (r < 8) SP_STAMP(8 + 4 * r);       // S-box issued
         // R needs y(r-1) for the look-ahead term and finishes Ebuf[q] ~200 cycles after it was published: waiting here,
         // behind the issue of the whole S-box, costs nothing unless R is late
-        named_bar_sync(8 + q, 64);
+        // the barrier id depends on x7 through a zero ptxas cannot fold: otherwise the S-box (pure register code) sinks
+        // below the volatile bar.sync and the wait for R no longer overlaps it
+        named_bar_sync(8 + q + ((u32)x7 & c_opaque_zero), 64);
+        if (r < 8) SP_STAMP(9 + 4 * r);       // past the barrier
         const ulonglong2 E = *(const ulonglong2*)&Ebuf[q][2 * lane];
         const u64 y = gl_add_lazy_canon(x7, post);
         ybuf[q][lane] = y;
@@ -411,6 +424,7 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         mac32(al0, al1, (u32)y, 25u);
         mac32(ah0, ah1, (u32)(y >> 32), 25u);
         x0 = mds_recombine(al0, al1, ah0, ah1);
+        if (r < 8) SP_STAMP(10 + 4 * r);      // x0 of the next round issued
       };
 #pragma unroll 1
       for (int r = 0; r < 21; r += 3) {
@@ -418,6 +432,7 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
       }
       body(21, std::integral_constant<int, 0>());
       s = x0;
+      SP_STAMP(5);
     } else if (!reducer) {
       u64 x = s;                               // lazy
       const u64* what = c_fast_what + (wid - 1);
@@ -491,6 +506,9 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
       }
     }
   }
+#ifdef SP_TRACE
+  // (the chunk loop variable is out of scope here; the end-of-permutation stamp is taken inside the loop)
+#endif
   if (live && !reducer && wid < 4) digests[4ull * leaf_index_of(pos, log_block) + wid] = gl_canon(s);
 }
 

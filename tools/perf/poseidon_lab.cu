@@ -9,6 +9,9 @@
 
 #include <vector>
 
+#ifdef LAB_TRACE
+#define SP_TRACE 1
+#endif
 #include "leafhash.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
@@ -134,6 +137,28 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
   printf("device %s, %d SMs, %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
 
+#ifdef LAB_TRACE
+  if (argc > 1 && !strcmp(argv[1], "trace")) {   // clock64 timeline of the word-0 warp of the sp kernel (one permutation)
+    uint32_t nl = 4096, ll = 256;
+    size_t cells = (size_t)nl * ll;
+    u64 *d_cols, *d_dig; long long* d_tr;
+    CK(cudaMalloc(&d_cols, 8 * cells)); CK(cudaMalloc(&d_dig, 32ull * nl)); CK(cudaMalloc(&d_tr, 64 * 8));
+    CK(cudaMemset(d_tr, 0, 64 * 8));
+    CK(cudaMemcpyToSymbol(g_sp_trace, &d_tr, sizeof(d_tr)));
+    fill_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_cols, cells);
+    for (int rep = 0; rep < 2; rep++) leaf_sponge_sp_kernel<<<(nl + 31) / 32, 416>>>(d_cols, ll, nl, 0, d_dig);
+    CK(cudaDeviceSynchronize());
+    long long h[64]; CK(cudaMemcpy(h, d_tr, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("perm start %lld\n", 0ll);
+    for (int i = 1; i <= 4; i++) printf("full round %d done  +%lld (d %lld)\n", i - 1, h[i] - h[0], h[i] - h[i - 1]);
+    for (int r = 0; r < 8; r++)
+      printf("partial %d: sbox issued +%lld | barrier passed +%lld (wait %lld) | x0 issued +%lld   round total %lld\n", r, h[8 + 4 * r] - h[0],
+             h[9 + 4 * r] - h[0], h[9 + 4 * r] - h[8 + 4 * r], h[10 + 4 * r] - h[0], r ? h[10 + 4 * r] - h[10 + 4 * (r - 1)] : h[10] - h[4]);
+    printf("partial rounds done +%lld  (22 rounds: %lld, avg %lld)\n", h[5] - h[0], h[5] - h[4], (h[5] - h[4]) / 22);
+    for (int i = 0; i < 4; i++) printf("full round %d done +%lld (d %lld)\n", 26 + i, h[40 + i] - h[0], h[40 + i] - (i ? h[40 + i - 1] : h[5]));
+    return 0;
+  }
+#endif
   if (argc > 4 && !strcmp(argv[1], "one")) {   // one variant, one shape (for ncu): one <wps> <n_leaves> <leaf_len>
     int wps = atoi(argv[2]); uint32_t nl = atoi(argv[3]), ll = atoi(argv[4]);
     size_t cells = (size_t)nl * ll;
