@@ -371,7 +371,9 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
       auto full_round = [&](u64 next) {
         const u64 v = poseidon_sbox(s);
         xch[xb][wid][lane] = v; xch[xb][wid + 12][lane] = v;
+        if (crit) SP_STAMP(50);
         named_bar_sync(1, 384);
+        if (crit) SP_STAMP(51);
         u64 t[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) t[i] = xch[xb][wid + i][lane];
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         if (wid == 0) { mac32(al0, al1, (u32)t[0], 8u); mac32(ah0, ah1, (u32)(t[0] >> 32), 8u); }   // DIAG[0] = 8
         s = mds_recombine(al0, al1, ah0, ah1);
         xb ^= 1;
+        if (crit) SP_STAMP(52);
       };
 #pragma unroll 1
       for (int rd = 0; rd < 3; rd++) { full_round(c_poseidon_rc[12 * (rd + 1) + wid]); if (crit) SP_STAMP(1 + rd); }

@@ -150,6 +150,8 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     long long h[64]; CK(cudaMemcpy(h, d_tr, sizeof(h), cudaMemcpyDeviceToHost));
     printf("perm start %lld\n", 0ll);
+    printf("last full round of the first four (stamps of the crit warp): sbox+store issued at +%lld, barrier passed +%lld (wait %lld), mds+recombine issued +%lld; previous round ended +%lld\n",
+           h[50] - h[0], h[51] - h[0], h[51] - h[50], h[52] - h[0], h[3] - h[0]);
     for (int i = 1; i <= 4; i++) printf("full round %d done  +%lld (d %lld)\n", i - 1, h[i] - h[0], h[i] - h[i - 1]);
     for (int r = 0; r < 8; r++)
       printf("partial %d: sbox issued +%lld | barrier passed +%lld (wait %lld) | x0 issued +%lld   round total %lld\n", r, h[8 + 4 * r] - h[0],
