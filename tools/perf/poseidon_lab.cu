@@ -106,6 +106,69 @@ __global__ void mul_tput_kernel(u64* out, u64 a, int iters) {
   for (int j = 0; j < ILP; j++) acc ^= x[j];
   if (acc == 0x1234567) out[0] = acc;
 }
+// ---- alternative Goldilocks multiply formulations (lab only) ----
+// v2: the fold's x2 * eps + (x1:x0) as ONE multiply-add with carry out (mad.lo.cc / madc.hi.cc fuse into IMAD.WIDE),
+//     then - x3 and the two eps repairs.
+__device__ __forceinline__ u64 gl_mul_lazy_v2(u64 a, u64 b) {
+  const u64 lo = a * b, hi = __umul64hi(a, b);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 c1, b1;\n\t"
+      "mad.lo.cc.u32 %0, %4, 0xFFFFFFFF, %2;\n\t"     // (x1:x0) + x2 * eps, carry c1
+      "madc.hi.cc.u32 %1, %4, 0xFFFFFFFF, %3;\n\t"
+      "addc.u32 c1, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, %5;\n\t"                     // - x3, borrow b1
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 b1, 0, 0;\n\t"                         // 0 or 0xFFFFFFFF
+      "neg.s32 c1, c1;\n\t"                            // 0 or 0xFFFFFFFF = c1 * eps
+      "add.cc.u32 %0, %0, c1;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "sub.cc.u32 %0, %0, b1;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+  return ((u64)r1 << 32) | r0;
+}
+template <int V> __device__ __forceinline__ u64 mulv(u64 a, u64 b) { return V == 2 ? gl_mul_lazy_v2(a, b) : gl_mul_lazy(a, b); }
+template <int V> __device__ __forceinline__ u64 sboxv(u64 x) {
+  const u64 x2 = mulv<V>(x, x), x4 = mulv<V>(x2, x2), x3 = mulv<V>(x2, x);
+  return mulv<V>(x3, x4);
+}
+template <int V>
+__global__ void sbox_variant_kernel(u64* out, u64 a, int iters, int busy, long long* cycles) {
+  const unsigned warp = threadIdx.x >> 5;
+  u64 x = a + threadIdx.x;
+  if (warp == 0 || busy) {
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) x = gl_add_lazy_canon(sboxv<V>(x), 0x123456789ULL);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+// S-box latency in the shape of the sp kernel: `warps` warps per block, warp 0 runs a dependent chain of S-boxes
+// (x <- x^7 + c), the other warps either wait at a barrier (busy == 0) or run their own chains (busy == 1)
+__global__ void sbox_latency_kernel(u64* out, u64 a, int iters, int busy, long long* cycles) {
+  const unsigned warp = threadIdx.x >> 5;
+  u64 x = a + threadIdx.x;
+  if (warp == 0 || busy) {
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) x = gl_add_lazy_canon(poseidon_sbox(x), 0x123456789ULL);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
 __global__ void perm_latency_kernel(u64* out, int iters, long long* cycles) {
   u64 s[12];
 #pragma unroll
@@ -202,6 +265,30 @@ int main(int argc, char** argv) {
     float ms8 = time_ms([&] { mul_tput_kernel<8><<<grid, block>>>(d_out, 3, iters / 8); });
     double muls = (double)grid * block * iters * 4;
     printf("gl_mul_lazy throughput: ILP1 %.1f  ILP4 %.1f  ILP8 %.1f Gmul/s\n", muls / ms1 / 1e6, muls / ms4 / 1e6, muls / ms8 / 1e6);
+  }
+
+  {  // S-box latency in situ
+    u64* d_out; long long* d_cyc; CK(cudaMalloc(&d_out, 8 * 416 * 148)); CK(cudaMalloc(&d_cyc, 8 * 148));
+    const int iters = 256;
+    for (int warps : {1, 4, 13}) for (int busy : {0, 1}) for (int blocks : {1, 128}) {
+      sbox_latency_kernel<<<blocks, 32 * warps>>>(d_out, 3, iters, busy, d_cyc);
+      CK(cudaDeviceSynchronize());
+      long long c; CK(cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost));
+      printf("S-box chain latency: %2d warps/block, others %s, %3d blocks: %.1f cycles per S-box\n", warps, busy ? "busy" : "idle", blocks,
+             (double)c / (iters * 4));
+    }
+    u64 h1[32], h2[32];
+    for (int busy : {0, 1}) {
+      sbox_variant_kernel<1><<<1, 416>>>(d_out, 3, iters, busy, d_cyc); CK(cudaDeviceSynchronize());
+      long long c1; CK(cudaMemcpy(&c1, d_cyc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h1, d_out, sizeof(h1), cudaMemcpyDeviceToHost));
+      sbox_variant_kernel<2><<<1, 416>>>(d_out, 3, iters, busy, d_cyc); CK(cudaDeviceSynchronize());
+      long long c2; CK(cudaMemcpy(&c2, d_cyc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h2, d_out, sizeof(h2), cudaMemcpyDeviceToHost));
+      bool same = true;
+      for (int i = 0; i < 32; i++) same = same && ((h1[i] % GL_P) == (h2[i] % GL_P));
+      printf("S-box variants, 13 warps, others %s: current fold %.1f, multiply-add fold %.1f cycles per S-box  (%s)\n", busy ? "busy" : "idle",
+             (double)c1 / (iters * 4), (double)c2 / (iters * 4), same ? "same values" : "VALUES DIFFER");
+    }
+    cudaFree(d_out); cudaFree(d_cyc);
   }
 
   // ---- leaf sponge variants ----
