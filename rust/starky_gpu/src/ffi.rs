@@ -42,6 +42,18 @@ pub struct sb_proof {
 #[repr(C)]
 pub struct sb_ctx { _private: [u8; 0] }
 
+/// Binary-identical to `sb_shard_hooks`: five collective callbacks of a sharded proof.
+#[repr(C)]
+pub struct sb_shard_hooks {
+    pub user: *mut c_void,
+    pub commit: Option<unsafe extern "C" fn(user: *mut c_void, cap_out: *mut u64) -> c_int>,
+    pub quotient: Option<unsafe extern "C" fn(user: *mut c_void, alphas: *const u64, d_q_out: *mut u64) -> c_int>,
+    pub openings: Option<unsafe extern "C" fn(user: *mut c_void, zeta: *const u64, zeta_next: *const u64,
+                                              local_out: *mut u64, next_out: *mut u64) -> c_int>,
+    pub combine: Option<unsafe extern "C" fn(user: *mut c_void, alpha: *const u64, d_out: *mut u64) -> c_int>,
+    pub query_rows: Option<unsafe extern "C" fn(user: *mut c_void, positions: *const u32, count: u32, d_rows_out: *mut u64) -> c_int>,
+}
+
 extern "C" {
     pub fn sb_init(devices: *const c_int, n_devices: c_int, out: *mut *mut sb_ctx) -> c_int;
     pub fn sb_destroy(ctx: *mut sb_ctx);
@@ -50,6 +62,22 @@ extern "C" {
     pub fn sb_prove(ctx: *mut sb_ctx, p: *const sb_params, trace: *const c_void, layout: c_int,
                     public_inputs: *const u64, out: *mut *mut sb_proof) -> c_int;
     pub fn sb_proof_free(proof: *mut sb_proof);
+    // one proof sharded over the GPUs of a box (include/starky_b200.h: sb_shard_hooks); the hooks are collective and
+    // are implemented by the host with ncclSend/ncclRecv (the Python harness does them with torch.distributed)
+    pub fn sb_prove_sharded(ctx: *mut sb_ctx, p: *const sb_params, hooks: *const sb_shard_hooks,
+                            public_inputs: *const u64, out: *mut *mut sb_proof) -> c_int;
+    pub fn sb_lde_cols_device(ctx: *mut sb_ctx, p: *const sb_params, d_trace: *const u64, n_cols_local: u32,
+                              n_row_blocks: u32, d_coeffs_out: *mut u64, d_lde_out: *mut u64) -> c_int;
+    pub fn sb_hash_rows_device(ctx: *mut sb_ctx, d_cols: *const u64, leaf_len: u32, n_leaves: u32, d_digests: *mut u64) -> c_int;
+    pub fn sb_merkle_from_position_digests(ctx: *mut sb_ctx, p: *const sb_params, d_digests_pos: *const u64, cap_out: *mut u64) -> c_int;
+    pub fn sb_transcript_alphas(trace_cap: *const u64, cap_len: u32, num_challenges: u32, alphas_out: *mut u64) -> c_int;
+    pub fn sb_quotient_rows_device(ctx: *mut sb_ctx, p: *const sb_params, d_rows: *const u64, rows_per_block: u32,
+                                   block_index: u32, d_halo_next_row: *const u64, public_inputs: *const u64,
+                                   alphas: *const u64, d_out: *mut u64) -> c_int;
+    pub fn sb_openings_cols_device(ctx: *mut sb_ctx, p: *const sb_params, d_coeffs: *const u64, n_cols_local: u32,
+                                   zeta: *const u64, zeta_next: *const u64, local_out: *mut u64, next_out: *mut u64) -> c_int;
+    pub fn sb_combine_cols_device(ctx: *mut sb_ctx, p: *const sb_params, d_coeffs: *const u64, n_cols_local: u32,
+                                  alpha: *const u64, first_col: u32, d_out: *mut u64) -> c_int;
     pub fn sb_fri_step_path_len(l: *const sb_proof_layout, round: u32) -> u32;
     pub fn sb_fri_step_offset(l: *const sb_proof_layout, round: u32) -> u64;
 }
