@@ -4,7 +4,9 @@
 // PARITY UNPINNED at proof-byte level: the reference's prove() lives in un-vendored Rust git dependencies (plonky2 @
 // 666f315) and cannot be built here; this restatement follows SURVEY.md Appendix A.  Pinned: Poseidon-12 (plonky2's
 // published KATs), Goldilocks constants, the five starks' constraint counts / fingerprints (tests/test_oracle_kat.py,
-// tests/test_air_programs.py, tests/golden/).
+// tests/test_air_programs.py, tests/golden/); the constraint programs it interprets, by the reference's own witness
+// logic: every constraint vanishes on every row of generated traces of all five starks, and the BLS12-381 arithmetic
+// under those generators passes the reference's KATs (tests/test_witness.py, tests/golden/bls_kats.json).
 #include "prover.h"
 #include <map>
 #include <memory>
