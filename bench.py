@@ -161,13 +161,14 @@ def full_set_assignment(world):
 
 
 def full_set_plan(world):
-    """How the seven proofs are laid over `world` GPUs.  With a whole 8-GPU box the critical path (FinalExp, ~630 ms on one
-    GPU) is sharded over four GPUs (SURVEY 8e "proof-level parallelism on top") and the other six proofs share the rest;
-    otherwise whole proofs are assigned longest-first.  Returns (ranks of the sharded FinalExp proof or [], per-rank lists)."""
-    if world < 8:
+    """How the seven proofs are laid over `world` GPUs.  From four GPUs on, the critical path (FinalExp, ~630 ms on one GPU)
+    is sharded over half of them (SURVEY 8e "proof-level parallelism on top") and the other six proofs share the rest;
+    below that whole proofs are assigned longest-first.  Returns (ranks of the sharded FinalExp proof or [], per-rank lists)."""
+    if world < 4:
         return [], full_set_assignment(world)
-    rest = full_set_assignment_of([k for k in FULL_SET if k != "final_exp"], world - 4)
-    return [0, 1, 2, 3], [[] for _ in range(4)] + rest
+    k = world // 2
+    rest = full_set_assignment_of([x for x in FULL_SET if x != "final_exp"], world - k)
+    return list(range(k)), [[] for _ in range(k)] + rest
 
 
 def full_set_assignment_of(names, world):
@@ -419,7 +420,7 @@ def main():
         full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
                             "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
                 "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
-                "note": "with 8 GPUs FinalExp is sharded over four (sb_prove_sharded) and the other six proofs share the rest; otherwise "
+                "note": "from 4 GPUs on FinalExp is sharded over half of them (sb_prove_sharded) and the other six proofs share the rest; otherwise "
                         "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run two in "
                         "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
     ctx2.close()

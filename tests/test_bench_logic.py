@@ -29,4 +29,7 @@ def test_full_set_plan_shards_final_exp_on_a_whole_box():
     assert sorted(x for r in per for x in r) == sorted(k for k in bench.FULL_SET if k != "final_exp")
     assert max(sum(bench.FULL_SET_COST[x] for x in r) for r in per) == bench.FULL_SET_COST["miller_loop"]
     fe, per = bench.full_set_plan(4)
-    assert fe == [] and per == bench.full_set_assignment(4)
+    assert fe == [0, 1] and per[:2] == [[], []]
+    assert sorted(x for r in per for x in r) == sorted(k for k in bench.FULL_SET if k != "final_exp")
+    fe, per = bench.full_set_plan(2)
+    assert fe == [] and per == bench.full_set_assignment(2)
