@@ -187,6 +187,47 @@ class ThreadGroup:
         return torch.cat(mine)
 
 
+# ---- the three "small collectives" of the tail as plain data movement (tested under gloo on CPU) ----
+def gather_openings(comm, plan, rank, mine, device=None):
+    """mine: uint64 [2][C_rank][2] = (P_c(zeta), P_c(g zeta)) of this rank's columns.  Returns uint64 [2][C][2] on every
+    rank (ragged column counts: every slice is padded to the widest before the all-gather, then cut)."""
+    import torch
+    cg, width = plan.col_count[rank], max(plan.col_count)
+    pad = np.zeros((2, width, 2), np.uint64)
+    pad[:, :cg] = mine[:, :cg]
+    t = torch.from_numpy(pad.view(np.int64))
+    parts = comm.all_gather(t.to(device) if device is not None else t)
+    out = np.empty((2, plan.n_cols, 2), np.uint64)
+    for g, part in enumerate(parts):
+        a = part.cpu().numpy().view(np.uint64)
+        out[:, plan.col_start[g]:plan.col_start[g] + plan.col_count[g]] = a[:, :plan.col_count[g]]
+    return out
+
+
+def combine_partials(comm, part):
+    """part: int64 tensor [n][2], this rank's sum_c alpha^c coeffs_c over its columns (canonical field elements).
+    Returns the sum over all ranks mod p as uint64 numpy [n][2] (NCCL has no modular reduction: all-gather, add here)."""
+    total = None
+    for t in comm.all_gather(part):
+        a = t.cpu().numpy().view(np.uint64)
+        total = a.copy() if total is None else _addmod(total, a)
+    return total
+
+
+def gather_query_rows(comm, plan, rank, rows, positions):
+    """rows: int64 tensor [C][N/world] (this rank's row block); positions: device LDE positions of the queries.
+    Returns int64 tensor [len(positions)][C]: every row comes from the rank that owns it, the others contribute zeros."""
+    import torch
+    pos = np.asarray(positions, np.int64)
+    R = plan.rows_per_rank
+    own = (pos // R) == rank
+    out = torch.zeros((len(pos), plan.n_cols), dtype=torch.int64, device=rows.device)
+    if own.any():
+        idx = torch.from_numpy(pos[own] - rank * R).to(rows.device)
+        out[torch.from_numpy(np.nonzero(own)[0]).to(rows.device)] = rows[:, idx].t()
+    return comm.sum_int64(out).contiguous()
+
+
 def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None):
     """One proof with the trace sharded over plan.world GPUs: every rank calls this with its column slice
     and gets the same proof.  backend: GpuBackend of this rank; comm: TorchGroup (default: the default process group)."""
@@ -236,16 +277,9 @@ def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None):
         if cg:
             ctx._check(lib.sb_openings_cols_device(ctx._h, C.byref(p), backend.coeffs.data_ptr(), cg, z.ctypes.data, zn.ctypes.data,
                                                    mine[0].ctypes.data, mine[1].ctypes.data))
-        # ragged column counts: pad every slice to the largest, gather, cut
-        width = max(plan.col_count)
-        pad = np.zeros((2, width, 2), np.uint64)
-        pad[:, :cg] = mine[:, :cg]
-        parts = comm.all_gather(torch.from_numpy(pad.view(np.int64)).to(backend.device))
-        for g, t in enumerate(parts):
-            a = t.cpu().numpy().view(np.uint64)
-            k0, kc = plan.col_start[g], plan.col_count[g]
-            C.memmove(C.addressof(local_out.contents) + 16 * k0, np.ascontiguousarray(a[0, :kc]).ctypes.data, 16 * kc)
-            C.memmove(C.addressof(next_out.contents) + 16 * k0, np.ascontiguousarray(a[1, :kc]).ctypes.data, 16 * kc)
+        allv = gather_openings(comm, plan, rank, mine, backend.device)
+        C.memmove(local_out, np.ascontiguousarray(allv[0]).ctypes.data, 16 * plan.n_cols)
+        C.memmove(next_out, np.ascontiguousarray(allv[1]).ctypes.data, 16 * plan.n_cols)
 
     def h_combine(_user, alpha, d_out):
         al = np.array([alpha[0], alpha[1]], np.uint64)
@@ -253,23 +287,13 @@ def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None):
         backend._sync_torch()
         if cg:
             ctx._check(lib.sb_combine_cols_device(ctx._h, C.byref(p), backend.coeffs.data_ptr(), cg, al.ctypes.data, c0, part.data_ptr()))
-        total = None
-        for t in comm.all_gather(part):
-            a = t.cpu().numpy().view(np.uint64)
-            total = a.copy() if total is None else _addmod(total, a)
+        total = combine_partials(comm, part)
         dev = torch.from_numpy(total.view(np.int64)).to(backend.device)
         backend._sync_torch()
         ctx._check(lib.sb_memcpy_device(ctx._h, d_out, dev.data_ptr(), 16 * n))
 
     def h_query_rows(_user, positions, count, d_rows_out):
-        pos = np.array([positions[i] for i in range(count)], np.int64)
-        R = plan.rows_per_rank
-        own = (pos // R) == rank
-        rows = torch.zeros((count, plan.n_cols), dtype=torch.int64, device=backend.device)
-        if own.any():
-            idx = torch.from_numpy(pos[own] - rank * R).to(backend.device)
-            rows[torch.from_numpy(np.nonzero(own)[0]).to(backend.device)] = st["rows"][:, idx].t()
-        rows = comm.sum_int64(rows).contiguous()   # exactly one rank holds each row, the others contribute zeros
+        rows = gather_query_rows(comm, plan, rank, st["rows"], [positions[i] for i in range(count)])
         backend._sync_torch()
         ctx._check(lib.sb_memcpy_device(ctx._h, d_rows_out, rows.data_ptr(), 8 * count * plan.n_cols))
 

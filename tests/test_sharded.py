@@ -270,3 +270,65 @@ def test_gpu_sharded_proof_with_the_reference_constraint_programs(name, world, l
         ctx.close()
     for pr in _prove_sharded_threads(world, p, trace, pis):
         assert np.array_equal(pr.words, want.words)
+
+
+# ---------------------------------------------------------------- the tail's small collectives under gloo (CPU)
+def _tail_worker(rank, world, init_file, n_cols, log_n, rate_bits, q):
+    from starky_bls12_381_b200.sharded import TorchGroup, combine_partials, gather_openings, gather_query_rows
+    dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
+    try:
+        plan = shard_plan(n_cols, log_n, rate_bits, world)
+        comm = TorchGroup(world, rank)
+        c0, cg = plan.col_start[rank], plan.col_count[rank]
+        # openings: value of global column c is a function of c only
+        cols = np.arange(c0, c0 + cg, dtype=np.uint64)
+        mine = np.stack([np.stack([cols * np.uint64(3) + np.uint64(1), cols * np.uint64(5) + np.uint64(2)], axis=1),
+                         np.stack([cols * np.uint64(7) + np.uint64(3), cols * np.uint64(11) + np.uint64(4)], axis=1)])
+        op = gather_openings(comm, plan, rank, mine)
+        # combine: partial sums near p so that the modular addition wraps
+        n = 1 << log_n
+        part = (np.arange(2 * n, dtype=np.uint64).reshape(n, 2) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(rank * 77)) % np.uint64(P)
+        part[0, 0] = P - 1 - rank
+        tot = combine_partials(comm, torch.from_numpy(part.view(np.int64)))
+        # query rows: this rank's row block of a global [C][N] table whose entry is a function of (c, pos)
+        R = plan.rows_per_rank
+        cc, pp = np.meshgrid(np.arange(n_cols, dtype=np.int64), np.arange(rank * R, (rank + 1) * R, dtype=np.int64), indexing="ij")
+        rows = torch.from_numpy(cc * 1000003 + pp)
+        positions = [0, plan.n_lde - 1, R - 1, R % plan.n_lde, 5, plan.n_lde // 2 + 3, 5]
+        qr = gather_query_rows(comm, plan, rank, rows, positions)
+        q.put((rank, op, tot, qr.numpy().copy(), part))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_cols", [(2, 13), (4, 9), (4, 3)])
+def test_tail_collectives_over_gloo(world, n_cols):
+    log_n, rate_bits = 6, 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        procs = [ctx.Process(target=_tail_worker, args=(r, world, os.path.join(d, "rv"), n_cols, log_n, rate_bits, q)) for r in range(world)]
+        for pr in procs:
+            pr.start()
+        res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+        for pr in procs:
+            pr.join(timeout=60)
+            assert pr.exitcode == 0
+    cols = np.arange(n_cols, dtype=np.uint64)
+    want_op = np.stack([np.stack([cols * np.uint64(3) + np.uint64(1), cols * np.uint64(5) + np.uint64(2)], axis=1),
+                        np.stack([cols * np.uint64(7) + np.uint64(3), cols * np.uint64(11) + np.uint64(4)], axis=1)])
+    want_tot = np.zeros_like(res[0][4])
+    acc = [[0, 0] for _ in range(want_tot.shape[0])]
+    for _, _, _, _, part in res:
+        for i in range(part.shape[0]):
+            for j in range(2):
+                acc[i][j] = (acc[i][j] + int(part[i, j])) % P
+    want_tot = np.array(acc, dtype=np.uint64)
+    N = 1 << (log_n + rate_bits)
+    positions = [0, N - 1, N // world - 1, (N // world) % N, 5, N // 2 + 3, 5]
+    want_rows = np.array([[c * 1000003 + p for c in range(n_cols)] for p in positions], dtype=np.int64)
+    for rank, op, tot, qr, _ in res:
+        assert np.array_equal(op, want_op)
+        assert np.array_equal(tot, want_tot)
+        assert np.array_equal(qr, want_rows)
