@@ -168,6 +168,13 @@ int sb_coeffs_download(sb_ctx* ctx, uint64_t* coeffs_out);
  *        position-ordered digests of all ranks are gathered and the tree is built to the cap (K3). ---- */
 int sb_lde_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_trace, uint32_t n_cols_local,
                        uint32_t n_row_blocks, uint64_t* d_coeffs_out /* optional */, uint64_t* d_lde_out);
+/*      K1 fused with the exchange ("P2P stores fused into the K1 epilogue"): the same transform, but every LDE
+ *        value is stored straight into the row buffer of the rank that owns its row block -- peer_rows[b] (host array of
+ *        n_row_blocks device pointers, peer-mapped over NVLink) = rank b's [n_cols total][N / n_row_blocks] buffer; this
+ *        rank's columns are first_col .. first_col + n_cols_local - 1.  There is no all-to-all afterwards. */
+int sb_lde_cols_peer_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_trace, uint32_t n_cols_local,
+                            uint32_t n_row_blocks, uint32_t first_col, uint64_t* d_coeffs_out /* optional */,
+                            const uint64_t* peer_rows);
 int sb_hash_rows_device(sb_ctx* ctx, const uint64_t* d_cols, uint32_t leaf_len, uint32_t n_leaves, uint64_t* d_digests);
 int sb_merkle_from_position_digests(sb_ctx* ctx, const sb_params* p, const uint64_t* d_digests_pos, uint64_t* cap_out);
 /*      Phase 2 continued: the quotient values q_j(x) (j < 2) of this rank's row block: d_rows = [n_cols][rows_per_block]

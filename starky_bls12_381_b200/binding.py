@@ -111,6 +111,8 @@ def lib():
         L.sb_synchronize.argtypes = [C.c_void_p]
         L.sb_lde_cols_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.sb_hash_rows_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.sb_lde_cols_peer_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_void_p]
         L.sb_merkle_from_position_digests.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
         L.sb_quotient_rows_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p]

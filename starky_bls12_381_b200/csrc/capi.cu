@@ -78,7 +78,7 @@ void sb_destroy(sb_ctx* ctx) {
   for (auto& kv : ctx->coset_scale) kv.second.release();
   for (auto& kv : ctx->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
   DevBuf* bufs[] = {&ctx->trace, &ctx->staging, &ctx->coeffs, &ctx->lde, &ctx->tree, &ctx->qvals, &ctx->qcoeffs, &ctx->qlde,
-                    &ctx->qtree, &ctx->pis, &ctx->weights, &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3};
+                    &ctx->qtree, &ctx->pis, &ctx->weights, &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->peer_tab};
   for (DevBuf* b : bufs) b->release();
   air_release_all(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -330,6 +330,31 @@ int sb_lde_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_trace,
   stage_begin(ctx, "lde");
   sb_lde_trace(ctx, d_trace, d_coeffs_out, d_lde_out, n_cols_local, p->log_n, p->rate_bits, log_blocks);
   stage_end(ctx, "lde");
+  return SB_OK;
+  SB_CATCH(ctx)
+}
+
+// K1 fused with the exchange: the LDE of this rank's column slice is stored straight into the row buffers of the ranks
+// that own the row blocks (peer memory over NVLink for the other ranks' blocks), peer_rows[b] = device pointer of rank b's
+// [n_cols_total][N / n_row_blocks] buffer.  No all-to-all pass follows; the caller barriers before reading its rows.
+int sb_lde_cols_peer_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_trace, uint32_t n_cols_local, uint32_t n_row_blocks,
+                            uint32_t first_col, uint64_t* d_coeffs_out, const uint64_t* peer_rows) {
+  if (!ctx || !d_trace || !peer_rows) return SB_EINVAL;
+  SB_TRY(ctx)
+  check_params(p);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  unsigned log_blocks = ilog2(n_row_blocks);
+  if (n_row_blocks == 0 || n_row_blocks > 64 || (1u << log_blocks) != n_row_blocks || p->log_n + p->rate_bits < log_blocks + 5)
+    SB_THROW(SB_EINVAL, "n_row_blocks %u must be a power of two <= 64 leaving >= 32 positions per block", n_row_blocks);
+  if ((uint64_t)first_col + n_cols_local > p->n_cols) SB_THROW(SB_EINVAL, "column slice [%u, +%u) outside %u columns", first_col, n_cols_local, p->n_cols);
+  if (n_cols_local == 0) return SB_OK;
+  ctx->peer_tab.ensure(8ull * 64);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->peer_tab.p, peer_rows, 8ull * n_row_blocks, cudaMemcpyHostToDevice, ctx->stream));
+  stage_begin(ctx, "lde");
+  sb_lde_trace(ctx, d_trace, d_coeffs_out, nullptr, n_cols_local, p->log_n, p->rate_bits, log_blocks, (u64* const*)ctx->peer_tab.p, first_col);
+  stage_end(ctx, "lde");
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  stage_collect(ctx);
   return SB_OK;
   SB_CATCH(ctx)
 }

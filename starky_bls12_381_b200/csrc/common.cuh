@@ -83,7 +83,7 @@ struct sb_ctx {
   DevBuf qtree;
   DevBuf pis;          // public inputs
   DevBuf weights;      // alpha powers
-  DevBuf scratch0, scratch1, scratch2, scratch3;
+  DevBuf scratch0, scratch1, scratch2, scratch3, peer_tab;
   void* pinned = nullptr; size_t pinned_cap = 0;
 };
 
@@ -118,7 +118,7 @@ static inline unsigned ilog2(uint64_t x) { unsigned b = 0; while ((uint64_t(1) <
 // ---- stage functions implemented across the .cu files ----
 // ntt.cu
 void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, uint32_t n_cols, unsigned log_n, unsigned rate_bits,
-                  unsigned log_row_blocks = 0);
+                  unsigned log_row_blocks = 0, u64* const* d_dst_tab = nullptr, uint32_t col0 = 0);
 void sb_ntt_device(sb_ctx* ctx, u64* d_data, unsigned log_size, uint32_t count, bool inverse, bool dif);
 void sb_transpose_rows_to_cols(sb_ctx* ctx, const void* d_rows, u64* d_cols, uint32_t n_rows, uint32_t n_cols, bool is_u32);
 // merkle.cu

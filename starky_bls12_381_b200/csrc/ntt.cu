@@ -110,11 +110,22 @@ __device__ __forceinline__ void dit_stages(u64* buf, unsigned log_n, unsigned lo
 // K1: fused iNTT -> (n^-1, coset shift) scaling -> 2^r coset NTTs, one pass over the trace.
 // Algorithmic HBM bytes per column: 8n read + 8n (coefficients, kept for openings/FRI) + 8N written.
 // ---------------------------------------------------------------------------------------------------------
+// Where LDE value (column col, position pos) goes.  Local output: [row block][column][position in block] (one block =
+// the plain [column][N] layout).  Peer output ("P2P stores fused into the K1 epilogue"): dst_tab[b] is the row
+// buffer [C_total][2^log_rb] of the rank that owns row block b -- this GPU's or, over NVLink, a peer's -- so the
+// column-sharded LDE lands row-sharded without a separate all-to-all pass.
+__device__ __forceinline__ u64* lde_slot(u64* lde, u64* const* dst_tab, uint32_t col0, uint32_t n_cols, uint32_t col, size_t pos,
+                                         unsigned log_rb) {
+  const size_t blk = pos >> log_rb, r = pos & (((size_t)1 << log_rb) - 1);
+  if (dst_tab) return dst_tab[blk] + (((size_t)(col0 + col)) << log_rb) + r;
+  return lde + (((blk * n_cols) + col) << log_rb) + r;
+}
+
 template <int EPT>
 __global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* __restrict__ values, u64* __restrict__ coeffs, u64* __restrict__ lde,
                            uint32_t n_cols, unsigned log_n, unsigned rate_bits, unsigned cpb,
                            const u64* __restrict__ tw_fwd, const u64* __restrict__ tw_inv,
-                           const u64* __restrict__ scale, u64 n_inv, unsigned log_rb) {
+                           const u64* __restrict__ scale, u64 n_inv, unsigned log_rb, u64* const* __restrict__ dst_tab, uint32_t dst_col0) {
   extern __shared__ u64 buf[];
   const unsigned T = blockDim.x;
   const uint32_t n = 1u << log_n;
@@ -147,7 +158,7 @@ __global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* _
       // output order [row block][column][position in block], blocks of 2^log_rb positions: one block (log_rb = log N) is
       // the plain column-major [C][N]; G blocks make every destination rank's slab contiguous for the all-to-all (8e)
       const size_t pos = ((size_t)J << log_n) + (e & (n - 1));
-      if (col < n_cols) lde[((((pos >> log_rb) * n_cols) + col) << log_rb) + (pos & (((size_t)1 << log_rb) - 1))] = buf[e];
+      if (col < n_cols) *lde_slot(lde, dst_tab, dst_col0, n_cols, col, pos, log_rb) = buf[e];
     }
   }
   if (coeffs) {
@@ -238,7 +249,7 @@ __device__ __forceinline__ void smem_pass(u64* b, unsigned t, unsigned log_n, un
 __global__ void __launch_bounds__(1024) lde8_kernel(const u64* __restrict__ values, u64* __restrict__ coeffs, u64* __restrict__ lde,
                                                    uint32_t n_cols, unsigned log_n, unsigned rate_bits, unsigned log_cpb,
                                                    const u64* __restrict__ tw_fwd, const u64* __restrict__ tw_inv,
-                                                   const u64* __restrict__ scale, u64 n_inv, unsigned log_rb) {
+                                                   const u64* __restrict__ scale, u64 n_inv, unsigned log_rb, u64* const* __restrict__ dst_tab, uint32_t dst_col0) {
   extern __shared__ u64 buf[];
   const uint32_t n = 1u << log_n, unit = n >> 3;
   const unsigned lc = threadIdx.x >> (log_n - 3), t = threadIdx.x & (unit - 1);
@@ -290,14 +301,14 @@ __global__ void __launch_bounds__(1024) lde8_kernel(const u64* __restrict__ valu
 #pragma unroll
       for (int m = 0; m < 8; m++) {
         const size_t pos = ((size_t)J << log_n) + t + (size_t)m * unit;
-        lde[((((pos >> log_rb) * n_cols) + col) << log_rb) + (pos & (((size_t)1 << log_rb) - 1))] = x[m];
+        *lde_slot(lde, dst_tab, dst_col0, n_cols, col, pos, log_rb) = x[m];
       }
     }
   }
 }
 
 void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, uint32_t n_cols, unsigned log_n,
-                  unsigned rate_bits, unsigned log_row_blocks) {
+                  unsigned rate_bits, unsigned log_row_blocks, u64* const* d_dst_tab, uint32_t col0) {
   const unsigned log_rb = log_n + rate_bits - log_row_blocks;
   if (log_n < 1 || log_n > 13) SB_THROW(SB_EINVAL, "trace height 2^%u unsupported (1 <= log_n <= 13)", log_n);
   const Twiddles& tw = sb_twiddles(ctx, log_n);
@@ -312,7 +323,7 @@ void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, u
     static bool attr_set = false;
     if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(lde8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 256))); attr_set = true; }
     LAUNCH(ctx, lde8_kernel, (n_cols + (1u << log_cpb) - 1) >> log_cpb, T, smem8, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits,
-           log_cpb, tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb);
+           log_cpb, tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb, d_dst_tab, col0);
     return;
   }
   // block shape: EPT elements per thread, cpb columns per block so that a block has >= 128 threads
@@ -325,11 +336,11 @@ void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, u
   if (ept == 8) {
     CUDA_CHECK(cudaFuncSetAttribute(lde_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH(ctx, lde_kernel<8>, grid, T, smem, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits, cpb,
-           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb);
+           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb, d_dst_tab, col0);
   } else {
     CUDA_CHECK(cudaFuncSetAttribute(lde_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH(ctx, lde_kernel<4>, grid, T, smem, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits, cpb,
-           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb);
+           tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb, d_dst_tab, col0);
   }
 }
 

@@ -4,6 +4,10 @@ PolynomialBatch::from_values as called by starky::prover::prove (aggregate_proof
     phase 1  column-sharded   rank g owns columns [c0_g, c0_g + C_g): K1 (iNTT + coset LDE) on its slice, written as
                               `world` slabs [b][c][N / world] so that every destination's slab is contiguous
     exchange all-to-all       slab b of every rank -> rank b (NCCL over NVLink; LDE bytes x (G-1)/G cross the fabric)
+             or FUSED         (commit_sharded(fused=True)) K1 stores every LDE value straight into the row buffer of the
+                              rank that owns its row block -- symmetric memory, peer pointers over NVLink
+                              (sb_lde_cols_peer_device) -- so the transfer overlaps the transform and the all-to-all
+                              pass disappears; two barriers replace it
     phase 2  row-sharded      rank g holds all C columns of its N / world positions: K2 leaf sponge, row-local
     gather   all-gather       N x 32-byte digests (<= 1 MB); K3 tree to the cap, redundantly on every rank
     phase 2' row-sharded      K4 quotient values of the rank's positions (quotient_sharded): the alphas come from the
@@ -65,14 +69,25 @@ def shard_plan(n_cols, log_n, rate_bits, world):
     return ShardPlan(n_cols, log_n, rate_bits, world, starts, counts, n_lde // world)
 
 
-def commit_sharded(backend, plan, rank, local_trace, group=None, comm=None):
+def commit_sharded(backend, plan, rank, local_trace, group=None, comm=None, fused=False):
     """Runs the sharded commitment on this rank.  local_trace: this rank's columns, [C_rank][n].
     Returns dict(cap=[2^cap_height][4] uint64 numpy, digests=[N][4] tensor in device position order, rows=tensor
-    [C][N/world] (this rank's row block of the LDE, all columns))."""
+    [C][N/world] (this rank's row block of the LDE, all columns)).  fused: K1 writes into the peers' row buffers
+    (no all-to-all); needs a GpuBackend and a comm with symmetric_rows()."""
     import torch
     comm = comm or TorchGroup(plan.world, rank, group)
-    slabs = backend.lde_cols(plan, rank, local_trace)                       # [world][C_rank][rows] flattened
-    rows = comm.all_to_all_rows(slabs, plan).view(plan.n_cols, plan.rows_per_rank)
+    if fused and plan.world > 1:
+        sym = getattr(backend, "_sym", None)
+        if sym is None or sym[0] != (plan.n_cols, plan.rows_per_rank, plan.world):
+            sym = backend._sym = ((plan.n_cols, plan.rows_per_rank, plan.world),) + tuple(comm.symmetric_rows(plan, backend.device))
+        _, rows, peer_ptrs, barrier = sym
+        barrier()                                   # every rank is done reading its rows of the previous proof
+        backend.lde_cols_peer(plan, rank, local_trace, peer_ptrs)
+        barrier()                                   # every rank has written its columns into my rows
+    else:
+        slabs = backend.lde_cols(plan, rank, local_trace)                   # [world][C_rank][rows] flattened
+        rows = comm.all_to_all_rows(slabs, plan)
+    rows = rows.view(plan.n_cols, plan.rows_per_rank)
     dig = backend.hash_rows(plan, rows)                                     # [rows][4], position order
     digests = torch.cat(comm.all_gather(dig), dim=0)
     cap = backend.merkle_cap(plan, digests)
@@ -149,6 +164,22 @@ class TorchGroup:
         return rows
 
 
+    def symmetric_rows(self, plan, device):
+        """This rank's row buffer [C][N/world] in symmetric memory + the peer-mapped pointers of every rank's buffer.
+        Returns (rows tensor, [device pointers by rank], barrier function)."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        rows = symm_mem.empty(plan.n_cols * plan.rows_per_rank, dtype=torch.int64, device=device)
+        hdl = symm_mem.rendezvous(rows, self.group if self.group is not None else dist.group.WORLD)
+
+        def barrier():
+            torch.cuda.synchronize()
+            hdl.barrier()
+            torch.cuda.synchronize()
+        return rows, [int(x) for x in hdl.buffer_ptrs], barrier
+
+
 class ThreadGroup:
     """The same collectives between `world` host threads of ONE process (one sb_ctx per thread, all on one GPU): the
     single-GPU test double of the NCCL group -- the control flow of every rank is exactly the multi-process one."""
@@ -179,6 +210,17 @@ class ThreadGroup:
         for x in parts[1:]:
             out += x
         return out
+
+    def symmetric_rows(self, plan, device):
+        import torch
+        rows = torch.empty(plan.n_cols * plan.rows_per_rank, dtype=torch.int64, device=device)
+        ptrs = [int(t.data_ptr()) for t in self._exchange(rows)]
+        self._keep = rows
+
+        def barrier():
+            torch.cuda.synchronize()
+            self.sh.barrier.wait()
+        return rows, ptrs, barrier
 
     def all_to_all_rows(self, slabs, plan):
         import torch
@@ -228,7 +270,7 @@ def gather_query_rows(comm, plan, rank, rows, positions):
     return comm.sum_int64(out).contiguous()
 
 
-def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None):
+def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None, fused=False):
     """One proof with the trace sharded over plan.world GPUs: every rank calls this with its column slice
     and gets the same proof.  backend: GpuBackend of this rank; comm: TorchGroup (default: the default process group)."""
     import torch
@@ -255,7 +297,7 @@ def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None):
         return run
 
     def h_commit(_user, cap_out):
-        com = commit_sharded(backend, plan, rank, local_trace, comm=comm)
+        com = commit_sharded(backend, plan, rank, local_trace, comm=comm, fused=fused)
         st["rows"], st["cap"] = com["rows"], com["cap"]
         flat = np.ascontiguousarray(com["cap"], dtype=np.uint64).reshape(-1)
         C.memmove(cap_out, flat.ctypes.data, flat.nbytes)
@@ -335,6 +377,19 @@ class GpuBackend:
                                                       self.coeffs.data_ptr(), out.data_ptr()))
         self.ctx.synchronize()
         return out
+
+    def lde_cols_peer(self, plan, rank, local_trace, peer_ptrs):
+        t = self.torch
+        cg, n = plan.col_count[rank], 1 << plan.log_n
+        if not isinstance(local_trace, t.Tensor):
+            local_trace = t.from_numpy(np.ascontiguousarray(local_trace, dtype=np.uint64).view(np.int64))
+        d_trace = local_trace.to(self.device, non_blocking=False).contiguous()
+        assert d_trace.numel() == cg * n and len(peer_ptrs) == plan.world
+        self.coeffs = t.empty(cg * n, dtype=t.int64, device=self.device)
+        ptrs = np.array(peer_ptrs, dtype=np.uint64)
+        self._sync_torch()
+        self.ctx._check(self.B.lib().sb_lde_cols_peer_device(self.ctx._h, self.B.C.byref(self.p), d_trace.data_ptr(), cg, plan.world,
+                                                           plan.col_start[rank], self.coeffs.data_ptr(), ptrs.ctypes.data))
 
     def hash_rows(self, plan, rows):
         t = self.torch

@@ -201,7 +201,7 @@ def test_gpu_row_sharded_quotient_matches_unsharded(world):
 
 
 # ---------------------------------------------------------------- the whole proof, sharded (SURVEY 8e small collectives)
-def _prove_sharded_threads(world, p, trace, pis, airbin=None, stark_id=None):
+def _prove_sharded_threads(world, p, trace, pis, airbin=None, stark_id=None, fused=False):
     """`world` host threads, one sb_ctx each on the one GPU, ThreadGroup collectives: the control flow of every rank is the
     multi-process one.  Returns the proofs of all ranks."""
     import threading
@@ -217,7 +217,7 @@ def _prove_sharded_threads(world, p, trace, pis, airbin=None, stark_id=None):
                 ctx.air_load(stark_id, airbin)
             be = GpuBackend(ctx, p)
             c0, cg = plan.col_start[rank], plan.col_count[rank]
-            out[rank] = prove_sharded(be, plan, rank, trace[c0:c0 + cg], pis, comm=ThreadGroup(shared, rank))
+            out[rank] = prove_sharded(be, plan, rank, trace[c0:c0 + cg], pis, comm=ThreadGroup(shared, rank), fused=fused)
         except Exception as e:          # noqa: BLE001 -- a dead rank would hang the others at the barrier
             errs.append(e)
             shared.barrier.abort()
@@ -332,3 +332,24 @@ def test_tail_collectives_over_gloo(world, n_cols):
         assert np.array_equal(op, want_op)
         assert np.array_equal(tot, want_tot)
         assert np.array_equal(qr, want_rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,world,log_n", [("miller_loop", 4, 6), ("ecc_agg", 8, 7), ("pairing_precomp", 2, 8)])
+def test_gpu_sharded_proof_with_k1_storing_into_peer_row_buffers(name, world, log_n):
+    """fused=True: K1 writes the LDE straight into the row buffers of the owning ranks (sb_lde_cols_peer_device; here the
+    'peers' are buffers of the other host threads on the same GPU), no all-to-all: same proof."""
+    from starky_bls12_381_b200 import airfiles
+    info = sb.STARKS[name]
+    airfiles.air_path(name, "airbin")
+    p = sb.standard_params(info.stark_id, log_n, flags=sb.Flags.ALLOW_INVALID_TRACE)
+    rng = np.random.default_rng(0xB2004000 + info.stark_id)
+    trace = random_trace(rng, info.columns, log_n)
+    pis = rng.integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
+    ctx = sb.Context(0)
+    try:
+        want = ctx.prove(p, trace, pis)
+    finally:
+        ctx.close()
+    for pr in _prove_sharded_threads(world, p, trace, pis, fused=True):
+        assert np.array_equal(pr.words, want.words)
