@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded-stark", default="final_exp",
                     help="shape of the second sharded trace commitment (column slices drawn per rank); '' to skip")
+    ap.add_argument("--no-fused", action="store_true", help="sharded legs: NCCL all-to-all after K1 instead of K1 storing into peer memory")
     ap.add_argument("--no-full-set", action="store_true", help="skip the 7-proof BLS set (BASELINE configs[4])")
     ap.add_argument("--also", default="miller_loop,final_exp",
                     help="N=1 only: further starks proved once each after the headline workload (reported under 'also')")
@@ -343,8 +344,10 @@ def main():
         airfiles.air_path(args.sharded_stark, "airbin")
         fpis = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
 
+        fused = world > 1 and not args.no_fused
+
         def ffn():
-            out = commit_sharded(fbackend, fplan, rank, flocal)
+            out = commit_sharded(fbackend, fplan, rank, flocal, fused=fused)
             qq = quotient_sharded(fbackend, fplan, rank, out["rows"], out["cap"], fpis)
             return out["cap"], qq["q"][:, :4]
         ffn()
@@ -354,15 +357,15 @@ def main():
         fe = {"workload": WORKLOADS[args.sharded_stark], "ranks": world, "ms": ms_fe,
               "lde_merkle_gbs": 8.0 * fi.columns * fN / (ms_fe * 1e-3) / 1e9, "a2a_bytes_out_per_rank": fplan.a2a_bytes_out(0),
               "leaf_hash_ms_rank0": ctx.stage_ms("leaf_hash"), "lde_ms_rank0": ctx.stage_ms("lde"),
-              "quotient_ms_rank0": ctx.stage_ms("quotient"),
-              "note": "column-sharded LDE -> all-to-all -> row-sharded leaf hashing -> digest all-gather -> tree -> alphas -> "
+              "quotient_ms_rank0": ctx.stage_ms("quotient"), "k1_stores_into_peer_memory": fused,
+              "note": "column-sharded LDE -> all-to-all (or, fused: K1 stores into the owners' row buffers over NVLink) -> row-sharded leaf hashing -> digest all-gather -> tree -> alphas -> "
                       "halo row exchange -> row-sharded quotient -> all-gather of the 2 x N quotient values"}
         # the WHOLE proof of that sharded trace: sb_prove_sharded on every rank, the five distributed steps (commitment,
         # quotient, openings, FRI batch combine, query rows) as NCCL collectives; every rank ends with the same proof
         fp_inv = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
         pbackend = GpuBackend(ctx, fp_inv)
         comm = TorchGroup(world, rank)
-        pfn = lambda: prove_sharded(pbackend, fplan, rank, flocal, fpis, comm=comm)
+        pfn = lambda: prove_sharded(pbackend, fplan, rank, flocal, fpis, comm=comm, fused=fused)
         pfn()
         dt_fp, fproofs = timed(pfn, max(1, args.steps - 1))
         caps = torch.from_numpy(fproofs[-1].words[:64].view(np.int64).copy()).cuda()
@@ -372,7 +375,8 @@ def main():
             dist.all_gather(allc, caps)
             same = all(bool(torch.equal(allc[0], c)) for c in allc)
         fe["sharded_proof"] = {"ms": 1e3 * dt_fp / max(1, args.steps - 1), "ranks": world, "proof_words": int(fproofs[-1].layout.total_words),
-                               "same_proof_on_every_rank": same,
+                               "same_proof_on_every_rank": same, "hook_ms_rank0": {k: round(v, 2) for k, v in fproofs[-1].hook_ms.items()},
+                               "library_stage_ms_rank0": {k: round(float(v), 2) for k, v in fproofs[-1].timings.items()},
                                "note": "one FinalExp-shaped proof, trace sharded over all ranks (sb_prove_sharded): commitment + quotient as "
                                        "above, openings from column-sharded coefficient slices (all-gather), FRI batch combine (per-rank "
                                        "partial sums, all-gather + add), query rows from their owners; quotient commitment, transcript, "

@@ -283,10 +283,15 @@ def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None, fu
     pis = np.ascontiguousarray(public_inputs, dtype=np.uint64)
     st = {}
 
+    import time
+    st["hook_ms"] = {}
+
     def guard(fn):
         def run(*a):
             try:
+                t0 = time.perf_counter()
                 fn(*a)
+                st["hook_ms"][fn.__name__] = 1e3 * (time.perf_counter() - t0)
                 return 0
             except B.SbError as e:
                 st["error"] = e
@@ -348,7 +353,9 @@ def prove_sharded(backend, plan, rank, local_trace, public_inputs, comm=None, fu
         if isinstance(st.get("error"), Exception) and not isinstance(st["error"], B.SbError):
             raise st["error"]
         ctx._check(rc)
-    return B.Proof(out)
+    proof = B.Proof(out)
+    proof.hook_ms = st["hook_ms"]          # wall milliseconds spent in each collective hook (includes waiting for peers)
+    return proof
 
 
 class GpuBackend:
