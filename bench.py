@@ -207,19 +207,16 @@ def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
             sharded_job()
             per.append(("final_exp(sharded)", 1e3 * (time.perf_counter() - t0)))
         for phase_jobs, phase_ctx in phases:
-            queue = list(phase_jobs)
-
-            def worker(c):
-                while True:
-                    with lock:
-                        if not queue:
-                            return
-                        name, p, host, pis = queue.pop(0)
+            # job i of a phase always runs on context i % len(contexts): the warm-up pass then sizes exactly the device
+            # buffers (and loads the constraint programs) the timed pass needs -- with a shared work queue a context can
+            # meet its largest shape for the first time inside the timed pass and pay a multi-GB cudaMalloc there
+            def worker(k, c):
+                for name, p, host, pis in phase_jobs[k::len(phase_ctx)]:
                     t0 = time.perf_counter()
                     c.prove(p, host.data_ptr(), pis, sb.TraceLayout.COLMAJOR_U64)
                     with lock:
                         per.append((name, 1e3 * (time.perf_counter() - t0)))
-            ts = [threading.Thread(target=worker, args=(c,)) for c in phase_ctx[:max(1, len(queue))]]
+            ts = [threading.Thread(target=worker, args=(k, c)) for k, c in enumerate(phase_ctx)]
             for t in ts:
                 t.start()
             for t in ts:

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 
 #include "poseidon.cuh"
 #include "prover.cuh"
@@ -398,29 +399,50 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
   stage_collect(ctx);
 }
 
-// Pinned host buffers for proofs are expensive to create (cudaMallocHost of tens of MB); sb_proof_free parks them
-// here and the next sb_prove of a fitting size takes one back.
+// Pinned host buffers for proofs are expensive to create (cudaMallocHost of tens of MB) and cudaMallocHost / cudaFreeHost
+// synchronise the whole device: with two proofs in flight a proof that allocates its buffer waits for the OTHER proof's
+// kernels (measured: a 120 ms proof intermittently taking 450 ms).  sb_proof_free parks the buffers here, the next
+// sb_prove takes the smallest one that fits, and nothing is freed until the pool holds 16 of them.
 #include <mutex>
 static std::mutex g_pool_mu;
 static std::vector<std::pair<size_t, void*>> g_pool;
-static void* pinned_take(size_t bytes) {
+static std::map<void*, size_t> g_pinned_cap;     // capacity of every buffer handed out
+static void* pinned_take(size_t bytes, size_t* got) {
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t best = g_pool.size();
     for (size_t i = 0; i < g_pool.size(); i++)
-      if (g_pool[i].first >= bytes && g_pool[i].first <= 2 * bytes + 4096) {
-        void* p = g_pool[i].second;
-        g_pool.erase(g_pool.begin() + i);
-        return p;
-      }
+      if (g_pool[i].first >= bytes && (best == g_pool.size() || g_pool[i].first < g_pool[best].first)) best = i;
+    if (best != g_pool.size()) {
+      void* p = g_pool[best].second;
+      *got = g_pool[best].first;
+      g_pool.erase(g_pool.begin() + best);
+      return p;
+    }
   }
   void* p = nullptr;
   cudaError_t e = cudaMallocHost(&p, bytes);
   if (e != cudaSuccess) SB_THROW(SB_ENOMEM, "cudaMallocHost(proof, %zu bytes): %s", bytes, cudaGetErrorString(e));
+  *got = bytes;
+  return p;
+}
+static void* pinned_take(size_t bytes) {
+  size_t got = 0;
+  void* p = pinned_take(bytes, &got);
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pinned_cap[p] = got;
   return p;
 }
 static void pinned_give(void* p, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
-  if (g_pool.size() >= 4) { cudaFreeHost(g_pool.front().second); g_pool.erase(g_pool.begin()); }
+  auto it = g_pinned_cap.find(p);
+  if (it != g_pinned_cap.end()) { bytes = it->second; g_pinned_cap.erase(it); }
+  if (g_pool.size() >= 16) {
+    size_t small = 0;
+    for (size_t i = 1; i < g_pool.size(); i++) if (g_pool[i].first < g_pool[small].first) small = i;
+    cudaFreeHost(g_pool[small].second);
+    g_pool.erase(g_pool.begin() + small);
+  }
   g_pool.push_back({bytes, p});
 }
 
