@@ -194,12 +194,12 @@ def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
         jobs.append((name, p, host, pis))
     lock, per = threading.Lock(), []
     # Phase A: the latency-bound proofs (few leaves: MillerLoop, PairingPrecomp, FP12Mul -- the leaf sponge is a long
-    # sequential chain, the host transcript is a large share) two in flight, so that the transcript of one overlaps the
+    # sequential chain, the host transcript is a large share) up to four in flight, so that the transcript of one overlaps the
     # kernels of the other; phase B: the throughput-bound ones (FinalExp, ECCAgg: 32768 leaves fill the GPU) one at a
     # time.  Measured alternatives: FinalExp next to MillerLoop slows the latter to 937 ms (from 225); five latency-bound
     # proofs in flight serialise on the one-block-per-SM leaf sponge (893 ms for the phase instead of ~500).
     few = lambda j: (sb.STARKS[j[0]].num_rows << sb.STARKS[j[0]].rate_bits) <= 64 * 148
-    phases = [([j for j in jobs if few(j)], contexts[:2]), ([j for j in jobs if not few(j)], contexts[:1])]
+    phases = [([j for j in jobs if few(j)], contexts), ([j for j in jobs if not few(j)], contexts[:1])]
 
     def go():
         if sharded_job is not None:
@@ -210,8 +210,18 @@ def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
             # job i of a phase always runs on context i % len(contexts): the warm-up pass then sizes exactly the device
             # buffers (and loads the constraint programs) the timed pass needs -- with a shared work queue a context can
             # meet its largest shape for the first time inside the timed pass and pay a multi-GB cudaMalloc there
+            lanes = full_set_assignment_of([j[0] for j in phase_jobs], len(phase_ctx))     # longest-first over the contexts
+            pool = list(phase_jobs)
+            mine_jobs = []
+            for lane in lanes:
+                got = []
+                for nm in lane:
+                    i = next(i for i, j in enumerate(pool) if j[0] == nm)
+                    got.append(pool.pop(i))
+                mine_jobs.append(got)
+
             def worker(k, c):
-                for name, p, host, pis in phase_jobs[k::len(phase_ctx)]:
+                for name, p, host, pis in mine_jobs[k]:
                     t0 = time.perf_counter()
                     c.prove(p, host.data_ptr(), pis, sb.TraceLayout.COLMAJOR_U64)
                     with lock:
@@ -380,23 +390,28 @@ def main():
                                        "FRI rounds and proof of work redundantly on every rank"}
         del flocal, fbackend, pbackend, fproofs
         torch.cuda.empty_cache()
-    # ---- two proofs in flight on one GPU (two contexts, two host threads): the host transcript of one proof (a strictly
-    # sequential sponge, ~1 us per permutation) overlaps the kernels of the other, as a scheduler for the reference's seven
-    # independent proofs would run them ----
+    # ---- several proofs in flight on one GPU (one context and one host thread per proof): the leaf sponge of these shapes
+    # is latency-bound (one 32-leaf group per SM) and the host transcript is a strictly sequential sponge (~1 us per
+    # permutation), so concurrent proofs fill each other's gaps -- how a scheduler for the reference's seven independent
+    # proofs runs them.  End to end: every proof is taken from pinned host memory. ----
     ctx2 = sb.Context(local_rank)
-    ctx2.trace_upload(p, host_ptr)
-    ctx2.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64)
+    more = [sb.Context(local_rank) for _ in range(2)]
+    for c in [ctx2] + more:
+        c.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
 
-    def two_in_flight():
-        def worker(c):
-            for _ in range(args.steps):
-                c.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64)
-        ts = [threading.Thread(target=worker, args=(c,)) for c in (ctx, ctx2)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-    dt_pipe, _ = timed(two_in_flight, 1)
+    def in_flight(contexts):
+        def run():
+            def worker(c):
+                for _ in range(args.steps):
+                    c.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
+            ts = [threading.Thread(target=worker, args=(c,)) for c in contexts]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        return run
+    dt_pipe2, _ = timed(in_flight([ctx, ctx2]), 1)
+    dt_pipe4, _ = timed(in_flight([ctx, ctx2] + more), 1)
     # ---- BASELINE configs[4]: the seven proofs of one BLS signature verification over all ranks, two in flight per GPU ----
     full = None
     if not args.no_full_set:
@@ -417,14 +432,16 @@ def main():
                 spis = np.random.Generator(np.random.PCG64(0xB2400099)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
                 sbackend, scomm = GpuBackend(ctx, sp), TorchGroup(len(fe_ranks), sr, grp)
                 sharded_job = lambda: prove_sharded(sbackend, splan, sr, slocal, spis, comm=scomm)
-        dt_full, per = run_full_set(sb, [ctx, ctx2], mine, rank, timed, sharded_job)
+        dt_full, per = run_full_set(sb, [ctx, ctx2] + more, mine, rank, timed, sharded_job)
         full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
                             "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
                 "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
                 "note": "from 4 GPUs on FinalExp is sharded over half of them (sb_prove_sharded) and the other six proofs share the rest; otherwise "
-                        "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run two in "
+                        "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run up to four in "
                         "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
     ctx2.close()
+    for c in more:
+        c.close()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = 1e3 * dt / args.steps
     ms_e2e = 1e3 * dt_e2e / args.steps
@@ -503,8 +520,9 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "stage_ms": stage, "kernel_ms": kern, "sharded_commit": sharded, "sharded_commit_scaling_shape": fe, "also": also,
             "full_bls_set": full,
-            "two_in_flight": {"ms_per_proof": 1e3 * dt_pipe / (2 * args.steps) / world, "proofs": 2 * args.steps * world,
-                              "note": "two contexts per GPU, one host thread each: transcript of one proof overlaps kernels of the other"},
+            "in_flight": {"2": {"ms_per_proof": 1e3 * dt_pipe2 / (2 * args.steps) / world}, "4": {"ms_per_proof": 1e3 * dt_pipe4 / (4 * args.steps) / world},
+                          "note": "k contexts per GPU, one host thread each, end to end from pinned host memory: the latency-bound leaf "
+                                  "sponge and the sequential host transcript of one proof overlap the kernels of the others"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
