@@ -461,8 +461,8 @@ def main():
             "achieved": perms * U32_MACS_PER_PERM / t_hash / 1e9, "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
             "frac": perms * U32_MACS_PER_PERM / t_hash / 1e9 / imad["mad_lo_u32_gops"],
             # dram__bytes_read.sum + dram__bytes_write.sum of the leaf sponge from the committed ncu --set full capture
-            # (profiles/r1_top_kernels_pairing_precomp.txt); algorithmic = 8 C N = 962.6 MB
-            "traffic": 973794304 if args.stark == "pairing_precomp" else None,
+            # (profiles/r1_top_kernels_pairing_precomp_final.txt); algorithmic = 8 C N = 962.6 MB
+            "traffic": 975198208 if args.stark == "pairing_precomp" else None,
             "peak_source": "sb_measure_imad_peak: dependent-free mad.lo.u32, measured in this run",
             "share_of_step": (kern["leaf_hash"] + kern["merkle"]) / ms_step,
             "stages": {
