@@ -237,6 +237,18 @@ def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
     return dt, per
 
 
+def optional(leg, world):
+    """Runs a secondary leg of the bench.  On one GPU a failure there (e.g. out of memory on a smaller part) must not cost the
+    headline line; with several ranks an exception is re-raised (a rank that skips a collective would hang the others)."""
+    try:
+        return leg()
+    except Exception as e:          # noqa: BLE001
+        if world > 1:
+            raise
+        print("bench: secondary leg %s failed: %r" % (leg.__name__, e), file=sys.stderr, flush=True)
+        return {"error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,57 +351,75 @@ def main():
     torch.cuda.empty_cache()
     # ---- the same sharded commitment on the FinalExp shape (BASELINE configs[3]; throughput-bound, the shape that scales):
     # every rank draws its own column slice (seed + rank), so no 4.8 GB trace is replicated on the host ----
-    fe = None
-    if args.sharded_stark and args.sharded_stark != args.stark:
-        fi = sb.STARKS[args.sharded_stark]
-        fp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1)
-        fplan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, world)
-        fcg = fplan.col_count[rank]
-        frng = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id + 1000 * rank))
-        flocal = torch.from_numpy(frng.integers(0, 1 << 32, (fcg, fi.num_rows), dtype=np.uint64).view(np.int64)).cuda()
-        fbackend = GpuBackend(ctx, fp)
-        airfiles.air_path(args.sharded_stark, "airbin")
-        fpis = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
+    def fe_leg():
+        fe = None
+        if args.sharded_stark and args.sharded_stark != args.stark:
+            fi = sb.STARKS[args.sharded_stark]
+            fp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1)
+            fplan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, world)
+            fcg = fplan.col_count[rank]
+            frng = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id + 1000 * rank))
+            flocal = torch.from_numpy(frng.integers(0, 1 << 32, (fcg, fi.num_rows), dtype=np.uint64).view(np.int64)).cuda()
+            fbackend = GpuBackend(ctx, fp)
+            airfiles.air_path(args.sharded_stark, "airbin")
+            fpis = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
 
-        fused = world > 1 and not args.no_fused
+            fused = world > 1 and not args.no_fused
+            if fused:
+                # symmetric memory needs peer access between the GPUs of the box; probe it once and let every rank agree, so
+                # that a box without it falls back to the NCCL all-to-all instead of losing the bench line
+                ok = 1
+                try:
+                    probe = TorchGroup(world, rank).symmetric_rows(shard_plan(8, 5, 1, world), torch.device("cuda", local_rank))
+                    probe[2]()
+                    del probe
+                except Exception as e:          # noqa: BLE001
+                    ok = 0
+                    print("symmetric memory unavailable on rank %d: %r" % (rank, e), file=sys.stderr, flush=True)
+                flag = torch.tensor([ok], device="cuda")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                fused = bool(flag.item())
 
-        def ffn():
-            out = commit_sharded(fbackend, fplan, rank, flocal, fused=fused)
-            qq = quotient_sharded(fbackend, fplan, rank, out["rows"], out["cap"], fpis)
-            return out["cap"], qq["q"][:, :4]
-        ffn()
-        dt_fe, _ = timed(ffn, max(1, args.steps - 1))
-        fN = fi.num_rows << fi.rate_bits
-        ms_fe = 1e3 * dt_fe / max(1, args.steps - 1)
-        fe = {"workload": WORKLOADS[args.sharded_stark], "ranks": world, "ms": ms_fe,
-              "lde_merkle_gbs": 8.0 * fi.columns * fN / (ms_fe * 1e-3) / 1e9, "a2a_bytes_out_per_rank": fplan.a2a_bytes_out(0),
-              "leaf_hash_ms_rank0": ctx.stage_ms("leaf_hash"), "lde_ms_rank0": ctx.stage_ms("lde"),
-              "quotient_ms_rank0": ctx.stage_ms("quotient"), "k1_stores_into_peer_memory": fused,
-              "note": "column-sharded LDE -> all-to-all (or, fused: K1 stores into the owners' row buffers over NVLink) -> row-sharded leaf hashing -> digest all-gather -> tree -> alphas -> "
-                      "halo row exchange -> row-sharded quotient -> all-gather of the 2 x N quotient values"}
-        # the WHOLE proof of that sharded trace: sb_prove_sharded on every rank, the five distributed steps (commitment,
-        # quotient, openings, FRI batch combine, query rows) as NCCL collectives; every rank ends with the same proof
-        fp_inv = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-        pbackend = GpuBackend(ctx, fp_inv)
-        comm = TorchGroup(world, rank)
-        pfn = lambda: prove_sharded(pbackend, fplan, rank, flocal, fpis, comm=comm, fused=fused)
-        pfn()
-        dt_fp, fproofs = timed(pfn, max(1, args.steps - 1))
-        caps = torch.from_numpy(fproofs[-1].words[:64].view(np.int64).copy()).cuda()
-        same = True
-        if world > 1:
-            allc = [torch.empty_like(caps) for _ in range(world)]
-            dist.all_gather(allc, caps)
-            same = all(bool(torch.equal(allc[0], c)) for c in allc)
-        fe["sharded_proof"] = {"ms": 1e3 * dt_fp / max(1, args.steps - 1), "ranks": world, "proof_words": int(fproofs[-1].layout.total_words),
-                               "same_proof_on_every_rank": same, "hook_ms_rank0": {k: round(v, 2) for k, v in fproofs[-1].hook_ms.items()},
-                               "library_stage_ms_rank0": {k: round(float(v), 2) for k, v in fproofs[-1].timings.items()},
-                               "note": "one FinalExp-shaped proof, trace sharded over all ranks (sb_prove_sharded): commitment + quotient as "
-                                       "above, openings from column-sharded coefficient slices (all-gather), FRI batch combine (per-rank "
-                                       "partial sums, all-gather + add), query rows from their owners; quotient commitment, transcript, "
-                                       "FRI rounds and proof of work redundantly on every rank"}
-        del flocal, fbackend, pbackend, fproofs
-        torch.cuda.empty_cache()
+            def ffn():
+                out = commit_sharded(fbackend, fplan, rank, flocal, fused=fused)
+                qq = quotient_sharded(fbackend, fplan, rank, out["rows"], out["cap"], fpis)
+                return out["cap"], qq["q"][:, :4]
+            ffn()
+            dt_fe, _ = timed(ffn, max(1, args.steps - 1))
+            fN = fi.num_rows << fi.rate_bits
+            ms_fe = 1e3 * dt_fe / max(1, args.steps - 1)
+            fe = {"workload": WORKLOADS[args.sharded_stark], "ranks": world, "ms": ms_fe,
+                  "lde_merkle_gbs": 8.0 * fi.columns * fN / (ms_fe * 1e-3) / 1e9, "a2a_bytes_out_per_rank": fplan.a2a_bytes_out(0),
+                  "leaf_hash_ms_rank0": ctx.stage_ms("leaf_hash"), "lde_ms_rank0": ctx.stage_ms("lde"),
+                  "quotient_ms_rank0": ctx.stage_ms("quotient"), "k1_stores_into_peer_memory": fused,
+                  "note": "column-sharded LDE -> all-to-all (or, fused: K1 stores into the owners' row buffers over NVLink) -> row-sharded leaf hashing -> digest all-gather -> tree -> alphas -> "
+                          "halo row exchange -> row-sharded quotient -> all-gather of the 2 x N quotient values"}
+            # the WHOLE proof of that sharded trace: sb_prove_sharded on every rank, the five distributed steps (commitment,
+            # quotient, openings, FRI batch combine, query rows) as NCCL collectives; every rank ends with the same proof
+            fp_inv = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+            pbackend = GpuBackend(ctx, fp_inv)
+            comm = TorchGroup(world, rank)
+            pfn = lambda: prove_sharded(pbackend, fplan, rank, flocal, fpis, comm=comm, fused=fused)
+            pfn()
+            dt_fp, fproofs = timed(pfn, max(1, args.steps - 1))
+            caps = torch.from_numpy(fproofs[-1].words[:64].view(np.int64).copy()).cuda()
+            same = True
+            if world > 1:
+                allc = [torch.empty_like(caps) for _ in range(world)]
+                dist.all_gather(allc, caps)
+                same = all(bool(torch.equal(allc[0], c)) for c in allc)
+            fe["sharded_proof"] = {"ms": 1e3 * dt_fp / max(1, args.steps - 1), "ranks": world, "proof_words": int(fproofs[-1].layout.total_words),
+                                   "same_proof_on_every_rank": same, "hook_ms_rank0": {k: round(v, 2) for k, v in fproofs[-1].hook_ms.items()},
+                                   "library_stage_ms_rank0": {k: round(float(v), 2) for k, v in fproofs[-1].timings.items()},
+                                   "note": "one FinalExp-shaped proof, trace sharded over all ranks (sb_prove_sharded): commitment + quotient as "
+                                           "above, openings from column-sharded coefficient slices (all-gather), FRI batch combine (per-rank "
+                                           "partial sums, all-gather + add), query rows from their owners; quotient commitment, transcript, "
+                                           "FRI rounds and proof of work redundantly on every rank"}
+            del flocal, fbackend, pbackend, fproofs
+            torch.cuda.empty_cache()
+        return fe
+
+    fe = optional(fe_leg, world)
     # ---- several proofs in flight on one GPU (one context and one host thread per proof): the leaf sponge of these shapes
     # is latency-bound (one 32-leaf group per SM) and the host transcript is a strictly sequential sponge (~1 us per
     # permutation), so concurrent proofs fill each other's gaps -- how a scheduler for the reference's seven independent
@@ -413,32 +443,36 @@ def main():
     dt_pipe2, _ = timed(in_flight([ctx, ctx2]), 1)
     dt_pipe4, _ = timed(in_flight([ctx, ctx2] + more), 1)
     # ---- BASELINE configs[4]: the seven proofs of one BLS signature verification over all ranks, two in flight per GPU ----
-    full = None
-    if not args.no_full_set:
-        for nm in set(FULL_SET):
-            airfiles.air_path(nm, "airbin")
-        fe_ranks, per_rank = full_set_plan(world)
-        mine = per_rank[rank]
-        sharded_job = None
-        if fe_ranks:
-            grp = dist.new_group(ranks=fe_ranks)                      # collective: every rank calls it
-            if rank in fe_ranks:
-                fi = sb.STARKS["final_exp"]
-                sp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-                splan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, len(fe_ranks))
-                sr = fe_ranks.index(rank)
-                srng = np.random.Generator(np.random.PCG64(0xB2400000 + sr))
-                slocal = torch.from_numpy(srng.integers(0, 1 << 32, (splan.col_count[sr], fi.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
-                spis = np.random.Generator(np.random.PCG64(0xB2400099)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
-                sbackend, scomm = GpuBackend(ctx, sp), TorchGroup(len(fe_ranks), sr, grp)
-                sharded_job = lambda: prove_sharded(sbackend, splan, sr, slocal, spis, comm=scomm)
-        dt_full, per = run_full_set(sb, [ctx, ctx2] + more, mine, rank, timed, sharded_job)
-        full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
-                            "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
-                "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
-                "note": "from 4 GPUs on FinalExp is sharded over half of them (sb_prove_sharded) and the other six proofs share the rest; otherwise "
-                        "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run up to four in "
-                        "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
+    def full_leg():
+        full = None
+        if not args.no_full_set:
+            for nm in set(FULL_SET):
+                airfiles.air_path(nm, "airbin")
+            fe_ranks, per_rank = full_set_plan(world)
+            mine = per_rank[rank]
+            sharded_job = None
+            if fe_ranks:
+                grp = dist.new_group(ranks=fe_ranks)                      # collective: every rank calls it
+                if rank in fe_ranks:
+                    fi = sb.STARKS["final_exp"]
+                    sp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+                    splan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, len(fe_ranks))
+                    sr = fe_ranks.index(rank)
+                    srng = np.random.Generator(np.random.PCG64(0xB2400000 + sr))
+                    slocal = torch.from_numpy(srng.integers(0, 1 << 32, (splan.col_count[sr], fi.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
+                    spis = np.random.Generator(np.random.PCG64(0xB2400099)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
+                    sbackend, scomm = GpuBackend(ctx, sp), TorchGroup(len(fe_ranks), sr, grp)
+                    sharded_job = lambda: prove_sharded(sbackend, splan, sr, slocal, spis, comm=scomm)
+            dt_full, per = run_full_set(sb, [ctx, ctx2] + more, mine, rank, timed, sharded_job)
+            full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
+                                "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
+                    "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
+                    "note": "from 4 GPUs on FinalExp is sharded over half of them (sb_prove_sharded) and the other six proofs share the rest; otherwise "
+                            "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run up to four in "
+                            "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
+        return full
+
+    full = optional(full_leg, world)
     ctx2.close()
     for c in more:
         c.close()
