@@ -73,6 +73,20 @@ def make():
     out["toy_limbs4"] = {"log_n": log_n, "sha_trace": sha(trace), "sha_quotient_values": sha(q),
                          "trace_cap0": [int(v) for v in words[lay.off_trace_cap:lay.off_trace_cap + 4]],
                          "pow_witness": int(words[lay.off_pow]), "total_words": int(words.size), "sha_proof": sha(words)}
+    # a REAL stark at the size the reference instantiates it with: FP12MulStark 60285 x 16 on a VALID trace from the witness
+    # generator (seeded Fp12 operands): trace, public inputs and the whole proof
+    from starky_bls12_381_b200 import airfiles, witness as W
+    wr = np.random.default_rng(0xB2005000)
+    x, y = W.random_fp12(wr), W.random_fp12(wr)
+    trace, pis = W.fp12_mul_trace(x, y)
+    flat = airfiles.air_path("fp12_mul", "air")
+    p = O.make_params(stark_id=0, log_n=4, n_cols=trace.shape[0], n_pis=pis.size, degree=3, rate_bits=1)
+    rc, words = O.prove(flat, p, trace, pis)
+    assert rc == 0 and O.verify(flat, p, words) == 0
+    lay = O.layout(p)
+    out["fp12_mul_valid"] = {"seed": 0xB2005000, "sha_trace": sha(trace), "sha_public_inputs": sha(pis),
+                             "trace_cap0": [int(v) for v in words[lay.off_trace_cap:lay.off_trace_cap + 4]],
+                             "pow_witness": int(words[lay.off_pow]), "total_words": int(words.size), "sha_proof": sha(words)}
     return out
 
 
