@@ -407,7 +407,8 @@ void sb_quotient_rows(sb_ctx* ctx, const sb_params* p, const u64* d_rows, size_t
   if ((uint64_t)stride * 8 >= (1ull << 32)) SB_THROW(SB_EINVAL, "row stride %zu too large", stride);
   const unsigned block = n_local < 128 ? n_local : 128;
   const uint32_t xtiles = (n_local + block - 1) / block;
-  build_chunks(ctx, a, (uint32_t)((ctx->sm_count * 64 + xtiles - 1) / xtiles));
+  static const int chunk_mul = [] { const char* e = getenv("SB_QUOTIENT_CHUNK_MUL"); return e ? atoi(e) : 128; }();   // 16: 3.84 / 92.8, 64: 3.39 / 81.4, 128: 3.36 / 79.7, 256: 3.43 / 78.9 ms (PairingPrecomp / FinalExp)
+  build_chunks(ctx, a, (uint32_t)((ctx->sm_count * chunk_mul + xtiles - 1) / xtiles));
   a->pw.ensure(16ull * a->K);
   a->wt.ensure(16ull * a->n_slots + 16);
   a->part.ensure(16ull * a->n_chunks * n_local);
