@@ -82,6 +82,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def probe_plan(world):
+    """Smallest shard plan that shard_plan accepts at every power-of-two world size up to 64: the symmetric-memory probe only
+    needs *a* valid plan, and a plan the planner itself rejects (fewer than 32 LDE positions per rank) would read as
+    'no symmetric memory' and silently demote the fused K1 to the all-to-all."""
+    from starky_bls12_381_b200.sharded import shard_plan
+    return shard_plan(8, 10, 1, world)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -370,7 +378,7 @@ def main():
                 # that a box without it falls back to the NCCL all-to-all instead of losing the bench line
                 ok = 1
                 try:
-                    probe = TorchGroup(world, rank).symmetric_rows(shard_plan(8, 5, 1, world), torch.device("cuda", local_rank))
+                    probe = TorchGroup(world, rank).symmetric_rows(probe_plan(world), torch.device("cuda", local_rank))
                     probe[2]()
                     del probe
                 except Exception as e:          # noqa: BLE001
@@ -450,7 +458,7 @@ def main():
                 airfiles.air_path(nm, "airbin")
             fe_ranks, per_rank = full_set_plan(world)
             mine = per_rank[rank]
-            sharded_job = None
+            sharded_job, fe_fused = None, None
             if fe_ranks:
                 grp = dist.new_group(ranks=fe_ranks)                      # collective: every rank calls it
                 if rank in fe_ranks:
@@ -462,11 +470,25 @@ def main():
                     slocal = torch.from_numpy(srng.integers(0, 1 << 32, (splan.col_count[sr], fi.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
                     spis = np.random.Generator(np.random.PCG64(0xB2400099)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
                     sbackend, scomm = GpuBackend(ctx, sp), TorchGroup(len(fe_ranks), sr, grp)
-                    sharded_job = lambda: prove_sharded(sbackend, splan, sr, slocal, spis, comm=scomm)
+                    fs_fused = 0 if args.no_fused else 1
+                    if fs_fused:
+                        # same probe as the sharded legs, agreed inside the FinalExp sub-group only
+                        try:
+                            probe = scomm.symmetric_rows(probe_plan(len(fe_ranks)), torch.device("cuda", local_rank))
+                            probe[2]()
+                            del probe
+                        except Exception as e:          # noqa: BLE001
+                            fs_fused = 0
+                            print("symmetric memory unavailable in the FinalExp sub-group on rank %d: %r" % (rank, e), file=sys.stderr, flush=True)
+                        flag = torch.tensor([fs_fused], device="cuda")
+                        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=grp)
+                        fs_fused = int(flag.item())
+                    fe_fused = bool(fs_fused)
+                    sharded_job = lambda: prove_sharded(sbackend, splan, sr, slocal, spis, comm=scomm, fused=fe_fused)
             dt_full, per = run_full_set(sb, [ctx, ctx2] + more, mine, rank, timed, sharded_job)
             full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
                                 "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
-                    "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
+                    "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "final_exp_k1_stores_into_peer_memory": fe_fused, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
                     "note": "from 4 GPUs on FinalExp is sharded over half of them (sb_prove_sharded) and the other six proofs share the rest; otherwise "
                             "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run up to four in "
                             "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}

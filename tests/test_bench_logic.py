@@ -33,3 +33,12 @@ def test_full_set_plan_shards_final_exp_on_a_whole_box():
     assert sorted(x for r in per for x in r) == sorted(k for k in bench.FULL_SET if k != "final_exp")
     fe, per = bench.full_set_plan(2)
     assert fe == [] and per == bench.full_set_assignment(2)
+
+
+def test_symmetric_memory_probe_plan_is_valid_at_every_world_size():
+    """The probe that decides fused K1 vs all-to-all must never fail on its own plan: with a 64-position plan it was rejected
+    by shard_plan at 4 and 8 ranks and the sharded legs fell back to the all-to-all without anyone asking them to."""
+    import bench
+    for world in (1, 2, 4, 8, 16, 32, 64):
+        plan = bench.probe_plan(world)
+        assert plan.world == world and plan.rows_per_rank >= 32 and sum(plan.col_count) == plan.n_cols
