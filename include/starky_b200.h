@@ -128,7 +128,8 @@ const char* sb_last_error(sb_ctx* ctx); /* ctx may be NULL: last error of this t
 
 /* ---- constraint programs ("AIR") ---- */
 /* Load a compiled constraint program (tools/airgen output) and bind it to a stark id on this ctx.
- * The five standard ids are auto-loaded from $SB_AIR_DIR (default: <library dir>/../air) on first use. */
+ * The five standard programs are linked into the library (csrc/air_blobs.S) and bound on first use; when $SB_AIR_DIR
+ * is set, <dir>/<name>.airbin (fp12_mul, pairing_precomp, miller_loop, final_exp, ecc_agg) is read instead. */
 int sb_air_load(sb_ctx* ctx, uint32_t stark_id, const char* path);
 
 /* ---- the hot path: replaces starky::prover::prove ---- */

@@ -57,7 +57,9 @@ void orc_challenger_run(const uint64_t* obs, size_t n_obs, uint64_t* out, size_t
   for (size_t i = 0; i < n_out; i++) out[i] = ch.challenge();
 }
 
-void orc_layout(const Params* p, Layout* out) { *out = layout_for(*p); }
+int orc_layout(const Params* p, Layout* out) {
+  try { *out = layout_for(*p); return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
 
 // PolynomialBatch::from_values.  leaves_out [N][C] (plonky2 leaf order), digests_out [N][4], cap_out [2^cap][4];
 // coeffs_out [C][n].  Any output may be NULL.

@@ -40,7 +40,12 @@ static inline unsigned log2_ceil_u(unsigned x) { unsigned b = 0; while ((1u << b
 static inline std::vector<unsigned> fri_arities(const Params& p) {
   std::vector<unsigned> r;
   unsigned db = p.log_n;
-  while (db > p.fri_final_poly_bits && db + p.rate_bits - p.fri_arity_bits >= p.cap_height) {
+  if (p.fri_arity_bits == 0) throw std::invalid_argument("fri_arity_bits is 0");
+  while (db > p.fri_final_poly_bits) {
+    // plonky2: `degree_bits + rate_bits - arity_bits >= cap_height` in usize (a negative difference panics or wraps to
+    // "true"), then assert!(degree_bits >= arity_bits) inside the loop
+    if (db + p.rate_bits >= p.fri_arity_bits && db + p.rate_bits - p.fri_arity_bits < p.cap_height) break;
+    if (db < p.fri_arity_bits) throw std::invalid_argument("FRI reduction: degree_bits < arity_bits");
     r.push_back(p.fri_arity_bits); db -= p.fri_arity_bits;
   }
   return r;

@@ -162,13 +162,20 @@ const u64* ingest_trace(sb_ctx* ctx, const sb_params* p, const void* trace, int 
   return ctx->trace.as<u64>();
 }
 
-static void check_params(const sb_params* p) {
+// The one parameter check of every entry point (sb_prove, sb_prove_sharded, the stage functions, the layout helper).
+void check_params(const sb_params* p) {
   if (!p) SB_THROW(SB_EINVAL, "params is NULL");
-  if (p->n_cols == 0) SB_THROW(SB_EINVAL, "n_cols is 0");
+  if (p->n_cols == 0 || p->n_cols >= (1u << 18)) SB_THROW(SB_EINVAL, "n_cols %u out of range [1, 2^18)", p->n_cols);
   if (p->log_n < 1 || p->log_n > 13) SB_THROW(SB_EINVAL, "log_n %u out of range [1,13]", p->log_n);
   if (p->rate_bits < 1 || p->rate_bits > 4) SB_THROW(SB_EINVAL, "rate_bits %u out of range [1,4]", p->rate_bits);
-  if (p->cap_height > p->log_n + p->rate_bits) SB_THROW(SB_EINVAL, "cap_height larger than the tree");
-  if (p->num_challenges < 1 || p->num_challenges > 4) SB_THROW(SB_EINVAL, "num_challenges %u out of range", p->num_challenges);
+  if (p->cap_height > p->log_n + p->rate_bits) SB_THROW(SB_EINVAL, "cap_height %u larger than the tree", p->cap_height);
+  if (p->num_challenges < 1 || p->num_challenges > 4) SB_THROW(SB_EINVAL, "num_challenges %u out of range [1,4]", p->num_challenges);
+  if (p->constraint_degree < 1 || p->constraint_degree > 17) SB_THROW(SB_EINVAL, "constraint_degree %u out of range [1,17]", p->constraint_degree);
+  if (p->pow_bits > 32) SB_THROW(SB_EINVAL, "pow_bits %u out of range [0,32]", p->pow_bits);
+  if (p->num_query_rounds < 1 || p->num_query_rounds > 1024) SB_THROW(SB_EINVAL, "num_query_rounds %u out of range [1,1024]", p->num_query_rounds);
+  if (p->fri_arity_bits < 1 || p->fri_arity_bits > 9) SB_THROW(SB_EINVAL, "fri_arity_bits %u out of range [1,9]", p->fri_arity_bits);
+  if (p->fri_final_poly_bits > 13) SB_THROW(SB_EINVAL, "fri_final_poly_bits %u out of range [0,13]", p->fri_final_poly_bits);
+  (void)fri_arities(*p);   // throws SB_EINVAL where plonky2's reduction strategy would assert
 }
 
 // from_values on the device: ctx->trace -> ctx->coeffs, ctx->lde, ctx->tree.

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(EPT == 8 ? 1024 : 512) lde_kernel(const u64* _
   for (int m = 0; m < EPT; m++) {
     unsigned e = threadIdx.x + m * T;
     uint32_t col = col0 + (e >> log_n);
-    buf[e] = col < n_cols ? values[(size_t)col * n + (e & (n - 1))] : 0;
+    buf[e] = col < n_cols ? gl_canon(values[(size_t)col * n + (e & (n - 1))]) : 0;
   }
   __syncthreads();
   dif_stages<EPT>(buf, log_n, log_n, tw_inv, T);
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(1024) lde8_kernel(const u64* __restrict__ valu
   // ---- inverse transform, decimation in frequency ----
   const u64* vin = values + (size_t)col * n + t;
 #pragma unroll
-  for (int m = 0; m < 8; m++) x[m] = live ? vin[(size_t)m * unit] : 0;
+  for (int m = 0; m < 8; m++) x[m] = live ? gl_canon(vin[(size_t)m * unit]) : 0;   // plonky2 fields may hold [p, 2^64)
   dif_group<3>(x, t, log_n - 3, log_n, tw_inv);
 #pragma unroll
   for (int m = 0; m < 8; m++) b[padi(t + m * unit)] = x[m];
@@ -320,8 +320,8 @@ void sb_lde_trace(sb_ctx* ctx, const u64* d_values, u64* d_coeffs, u64* d_lde, u
     while (((n >> 3) << log_cpb) < 256) log_cpb++;
     const unsigned T = (n >> 3) << log_cpb;
     const size_t smem8 = 8ull * ((size_t)(n + (n >> 5)) << log_cpb);
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(lde8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 256))); attr_set = true; }
+    // per device (function attributes are per context): a cheap host call, so no process-wide "done" flag
+    CUDA_CHECK(cudaFuncSetAttribute(lde8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 256)));
     LAUNCH(ctx, lde8_kernel, (n_cols + (1u << log_cpb) - 1) >> log_cpb, T, smem8, d_values, d_coeffs, d_lde, n_cols, log_n, rate_bits,
            log_cpb, tw.fwd.as<u64>(), tw.inv.as<u64>(), scale, gl_inv((u64)n), log_rb, d_dst_tab, col0);
     return;
@@ -446,7 +446,7 @@ __global__ void transpose_kernel(const T* __restrict__ rows, u64* __restrict__ c
   uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     uint32_t r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < n_rows && c < n_cols) ? (u64)rows[(size_t)r * n_cols + c] : 0;
+    tile[i][threadIdx.x] = (r < n_rows && c < n_cols) ? gl_canon((u64)rows[(size_t)r * n_cols + c]) : 0;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {

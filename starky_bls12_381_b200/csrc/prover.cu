@@ -35,9 +35,17 @@ void sb_tail_nonzero_device(sb_ctx* ctx, const u64* d, unsigned log_size, uint32
 // ---------------------------------------------------------------------------------------------------------
 std::vector<unsigned> fri_arities(const sb_params& p) {
   // FriReductionStrategy::ConstantArityBits(arity_bits, final_poly_bits)
+  // (plonky2 asserts degree_bits >= arity_bits inside the loop and would underflow in usize otherwise: SB_EINVAL here)
   std::vector<unsigned> r;
   unsigned db = p.log_n;
-  while (db > p.fri_final_poly_bits && db + p.rate_bits - p.fri_arity_bits >= p.cap_height) {
+  if (p.fri_arity_bits == 0) SB_THROW(SB_EINVAL, "fri_arity_bits is 0");
+  while (db > p.fri_final_poly_bits) {
+    // `degree_bits + rate_bits - arity_bits >= cap_height` in usize: a negative difference panics (debug) or wraps to "true"
+    // and then trips the assert (release) -- an error either way, never "stop here"
+    if (db + p.rate_bits >= p.fri_arity_bits && db + p.rate_bits - p.fri_arity_bits < p.cap_height) break;
+    if (db < p.fri_arity_bits)
+      SB_THROW(SB_EINVAL, "FRI reduction: degree_bits %u < arity_bits %u (log_n %u, final_poly_bits %u, cap_height %u)", db,
+               p.fri_arity_bits, p.log_n, p.fri_final_poly_bits, p.cap_height);
     r.push_back(p.fri_arity_bits);
     db -= p.fri_arity_bits;
   }
@@ -53,7 +61,7 @@ uint64_t fri_step_offset(const sb_proof_layout& l, uint32_t round) {
   return o;
 }
 sb_proof_layout proof_layout(const sb_params& p) {
-  if (p.fri_arity_bits == 0) SB_THROW(SB_EINVAL, "fri_arity_bits is 0");
+  check_params(&p);
   sb_proof_layout l = {};
   std::vector<unsigned> ar = fri_arities(p);
   l.log_n = p.log_n; l.log_lde = p.log_n + p.rate_bits; l.n_cols = p.n_cols;
@@ -446,6 +454,12 @@ static void pinned_give(void* p, size_t bytes) {
   g_pool.push_back({bytes, p});
 }
 
+// error path: nothing of this proof may still be reading the caller's trace buffer or writing the proof buffer
+static void quiesce(sb_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+}
+
 extern "C" {
 
 int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, const uint64_t* public_inputs, sb_proof** out) {
@@ -453,9 +467,7 @@ int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, con
   sb_proof* proof = nullptr;
   try {
     CUDA_CHECK(cudaSetDevice(ctx->device));
-    if (p->n_cols == 0 || p->log_n < 1 || p->log_n > 13 || p->rate_bits < 1 || p->rate_bits > 4 ||
-        p->cap_height > p->log_n + p->rate_bits)
-      SB_THROW(SB_EINVAL, "bad parameters (n_cols %u, log_n %u, rate_bits %u, cap_height %u)", p->n_cols, p->log_n, p->rate_bits, p->cap_height);
+    check_params(p);
     proof = new sb_proof();
     memset(proof, 0, sizeof(*proof));
     proof->layout = proof_layout(*p);
@@ -464,11 +476,11 @@ int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, con
     *out = proof;
     return SB_OK;
   } catch (const SbError& e) {
-    cudaStreamSynchronize(ctx->stream);
+    quiesce(ctx);
     sb_proof_free(proof);
     return sb_fail(ctx, e);
   } catch (const std::exception& e) {
-    cudaStreamSynchronize(ctx->stream);
+    quiesce(ctx);
     sb_proof_free(proof);
     return sb_fail(ctx, SbError{SB_EINVAL, e.what()});
   }
@@ -480,9 +492,7 @@ int sb_prove_sharded(sb_ctx* ctx, const sb_params* p, const sb_shard_hooks* hook
   sb_proof* proof = nullptr;
   try {
     CUDA_CHECK(cudaSetDevice(ctx->device));
-    if (p->n_cols == 0 || p->log_n < 1 || p->log_n > 13 || p->rate_bits < 1 || p->rate_bits > 4 ||
-        p->cap_height > p->log_n + p->rate_bits)
-      SB_THROW(SB_EINVAL, "bad parameters (n_cols %u, log_n %u, rate_bits %u, cap_height %u)", p->n_cols, p->log_n, p->rate_bits, p->cap_height);
+    check_params(p);
     proof = new sb_proof();
     memset(proof, 0, sizeof(*proof));
     proof->layout = proof_layout(*p);
@@ -491,11 +501,11 @@ int sb_prove_sharded(sb_ctx* ctx, const sb_params* p, const sb_shard_hooks* hook
     *out = proof;
     return SB_OK;
   } catch (const SbError& e) {
-    cudaStreamSynchronize(ctx->stream);
+    quiesce(ctx);
     sb_proof_free(proof);
     return sb_fail(ctx, e);
   } catch (const std::exception& e) {
-    cudaStreamSynchronize(ctx->stream);
+    quiesce(ctx);
     sb_proof_free(proof);
     return sb_fail(ctx, SbError{SB_EINVAL, e.what()});
   }

@@ -10,6 +10,7 @@ std::vector<unsigned> fri_arities(const sb_params& p);
 static inline unsigned quotient_degree_factor(const sb_params& p) { return p.constraint_degree > 1 ? p.constraint_degree - 1 : 1; }
 
 // capi.cu
+void check_params(const sb_params* p);
 int sb_fail(sb_ctx* ctx, const SbError& e);
 const u64* ingest_trace(sb_ctx* ctx, const sb_params* p, const void* trace, int layout);
 void commit_trace(sb_ctx* ctx, const sb_params* p, const u64* d_values);

@@ -38,24 +38,34 @@ void air_release_all(sb_ctx* ctx) {
   ctx->airs.clear();
 }
 
-static void air_load_file(sb_ctx* ctx, uint32_t stark_id, const char* path) {
-  FILE* f = fopen(path, "rb");
-  if (!f) SB_THROW(SB_EAIR, "cannot open constraint program %s", path);
-  struct { char magic[8]; uint32_t v[12]; } h;
+// Parses one SBAIRBN1 image (tools/airgen/compile.py: write_airbin) from memory and binds it to `stark_id` on this ctx.
+// `what` names the source in error messages (a path, or "embedded:<name>").
+static void air_load_image(sb_ctx* ctx, uint32_t stark_id, const unsigned char* img, size_t img_len, const char* path) {
+  struct Hdr { char magic[8]; uint32_t v[12]; } h;
   std::vector<u64> code, consts;
   std::vector<uint32_t> slot_off, slot_ks, gpc, gslot;
-  bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "SBAIRBN1", 8) == 0;
+  size_t off = 0;
+  auto rd = [&](void* p, size_t sz, size_t n) {
+    if (n == 0) return true;
+    if (off + sz * n > img_len) return false;
+    memcpy(p, img + off, sz * n);
+    off += sz * n;
+    return true;
+  };
+  bool ok = rd(&h, sizeof(h), 1) && memcmp(h.magic, "SBAIRBN1", 8) == 0;
   AirProgram* a = new AirProgram();
   if (ok) {
     a->n_cols = h.v[0]; a->n_pis = h.v[1]; a->degree = h.v[2]; a->K = h.v[3]; a->n_code = h.v[4]; a->n_consts = h.v[5];
     a->n_slots = h.v[6]; a->n_groups = h.v[7];
+    ok = (uint64_t)a->n_code * 8 <= img_len && (uint64_t)a->n_consts * 8 <= img_len && (uint64_t)a->n_slots * 4 <= img_len &&
+         (uint64_t)a->K * 4 <= img_len && (uint64_t)a->n_groups * 4 <= img_len;
+  }
+  if (ok) {
     code.resize(a->n_code + 1); consts.resize(a->n_consts + 1); /* consts.back(): spare slot */ slot_off.resize(a->n_slots + 1); slot_ks.resize(a->K);
     gpc.resize(a->n_groups + 1); gslot.resize(a->n_groups + 1);
-    auto rd = [&](void* p, size_t sz, size_t n) { return n == 0 || fread(p, sz, n, f) == n; };
     ok = rd(code.data(), 8, a->n_code) && rd(consts.data(), 8, a->n_consts) && rd(slot_off.data(), 4, a->n_slots + 1) &&
          rd(slot_ks.data(), 4, a->K) && rd(gpc.data(), 4, a->n_groups + 1) && rd(gslot.data(), 4, a->n_groups + 1);
   }
-  fclose(f);
   if (!ok) { delete a; SB_THROW(SB_EAIR, "malformed constraint program %s", path); }
   // validate: every variable index in range, group table consistent
   const uint32_t n_vars = 2 * a->n_cols + a->n_pis;
@@ -117,16 +127,26 @@ static void air_load_file(sb_ctx* ctx, uint32_t stark_id, const char* path) {
   ctx->airs[stark_id] = a;
 }
 
-static std::string default_air_dir() {
-  const char* env = getenv("SB_AIR_DIR");
-  if (env && *env) return env;
-  Dl_info info;
-  if (dladdr((void*)&air_release_all, &info) && info.dli_fname) {
-    std::string p = info.dli_fname;
-    size_t s = p.find_last_of('/');
-    return (s == std::string::npos ? std::string(".") : p.substr(0, s)) + "/air/_unpacked";
-  }
-  return "air/_unpacked";
+static void air_load_file(sb_ctx* ctx, uint32_t stark_id, const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) SB_THROW(SB_EAIR, "cannot open constraint program %s", path);
+  std::vector<unsigned char> img;
+  unsigned char buf[1 << 16];
+  size_t got;
+  while ((got = fread(buf, 1, sizeof(buf), f)) > 0) img.insert(img.end(), buf, buf + got);
+  fclose(f);
+  air_load_image(ctx, stark_id, img.data(), img.size(), path);
+}
+
+// The five standard programs are linked into the library (air_blobs.S: .incbin of the images the Makefile unpacks from
+// starky_bls12_381_b200/air/*.airbin.xz), so sb_prove needs no file at run time.  $SB_AIR_DIR, when set, names a
+// directory of <name>.airbin files that take precedence (regenerated programs, experiments).
+extern "C" {
+extern const unsigned char sb_airbin_fp12_mul[], sb_airbin_fp12_mul_end[];
+extern const unsigned char sb_airbin_pairing_precomp[], sb_airbin_pairing_precomp_end[];
+extern const unsigned char sb_airbin_miller_loop[], sb_airbin_miller_loop_end[];
+extern const unsigned char sb_airbin_final_exp[], sb_airbin_final_exp_end[];
+extern const unsigned char sb_airbin_ecc_agg[], sb_airbin_ecc_agg_end[];
 }
 
 AirProgram* air_get(sb_ctx* ctx, const sb_params* p) {
@@ -134,8 +154,17 @@ AirProgram* air_get(sb_ctx* ctx, const sb_params* p) {
   if (it == ctx->airs.end()) {
     static const char* names[] = {"fp12_mul", "pairing_precomp", "miller_loop", "final_exp", "ecc_agg"};
     if (p->stark_id > SB_STARK_ECC_AGG) SB_THROW(SB_EAIR, "no constraint program loaded for stark id %u (sb_air_load)", p->stark_id);
-    std::string path = default_air_dir() + "/" + names[p->stark_id] + ".airbin";
-    air_load_file(ctx, p->stark_id, path.c_str());
+    const char* env = getenv("SB_AIR_DIR");
+    if (env && *env) {
+      std::string path = std::string(env) + "/" + names[p->stark_id] + ".airbin";
+      air_load_file(ctx, p->stark_id, path.c_str());
+    } else {
+      const unsigned char* b[5] = {sb_airbin_fp12_mul, sb_airbin_pairing_precomp, sb_airbin_miller_loop, sb_airbin_final_exp, sb_airbin_ecc_agg};
+      const unsigned char* e[5] = {sb_airbin_fp12_mul_end, sb_airbin_pairing_precomp_end, sb_airbin_miller_loop_end, sb_airbin_final_exp_end,
+                                   sb_airbin_ecc_agg_end};
+      const std::string what = std::string("embedded:") + names[p->stark_id];
+      air_load_image(ctx, p->stark_id, b[p->stark_id], (size_t)(e[p->stark_id] - b[p->stark_id]), what.c_str());
+    }
     it = ctx->airs.find(p->stark_id);
   }
   AirProgram* a = it->second;

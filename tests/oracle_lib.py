@@ -114,7 +114,8 @@ def challenger_run(obs, n_out):
 
 def layout(p):
     l = Layout()
-    lib().orc_layout(C.byref(p), C.byref(l))
+    if lib().orc_layout(C.byref(p), C.byref(l)):
+        raise RuntimeError("oracle: " + err())
     return l
 
 

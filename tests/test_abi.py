@@ -84,3 +84,51 @@ def test_host_transcript_permutation_variants_match_oracle():
             assert np.array_equal(got, want), (variant, st)
             ran += 1
     assert ran >= len(states)          # at least the scalar path
+
+
+def test_bad_fri_parameters_are_rejected_not_looped_on():
+    """plonky2 asserts degree_bits >= arity_bits inside ConstantArityBits and would underflow in usize; the C ABI answers
+    SB_EINVAL from the one check_params every entry point shares (no 2^30-entry loop, no UB shift)."""
+    L = sb.lib()
+    l = sb.ProofLayout()
+    base = sb.standard_params(sb.StarkId.CUSTOM, 5)
+    base.n_cols, base.constraint_degree = 8, 3
+
+    def rc(**kw):
+        p = base.copy()
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return L.sb_proof_layout_for(C.byref(p), C.byref(l))
+    assert rc() == 0
+    assert rc(rate_bits=1, fri_arity_bits=4, fri_final_poly_bits=0, cap_height=2) == -1      # 5 -> 1 -> (1 < 4)
+    assert b"arity_bits" in L.sb_last_error(None)
+    assert rc(pow_bits=64) == -1
+    assert rc(fri_arity_bits=0) == -1
+    assert rc(fri_arity_bits=10) == -1
+    assert rc(num_query_rounds=0) == -1
+    assert rc(num_query_rounds=1 << 20) == -1
+    assert rc(fri_final_poly_bits=40) == -1
+    assert rc(cap_height=9) == -1
+    assert rc(n_cols=0) == -1
+    # the oracle applies the same rule instead of wrapping around
+    op = to_oracle_params(base)
+    op.rate_bits, op.fri_arity_bits, op.fri_final_poly_bits, op.cap_height = 1, 4, 0, 2
+    import pytest
+    with pytest.raises(RuntimeError):
+        O.layout(op)
+
+
+def test_standard_constraint_programs_are_linked_into_the_library():
+    """sb_prove must not depend on files that only the Python harness unpacks: the five programs are .incbin'ed into
+    libstarkyb200.so (csrc/air_blobs.S) and equal the committed air/<name>.airbin.xz byte for byte."""
+    import lzma
+    import os
+    from starky_bls12_381_b200 import airfiles
+    L = sb.lib()
+    for name in airfiles.NAMES.values():
+        b = C.c_ubyte.in_dll(L, "sb_airbin_" + name)
+        e = C.c_ubyte.in_dll(L, "sb_airbin_%s_end" % name)
+        n = C.addressof(e) - C.addressof(b)
+        img = C.string_at(C.addressof(b), n)
+        want = lzma.decompress(open(os.path.join(airfiles.AIR_DIR, name + ".airbin.xz"), "rb").read())
+        assert img == want, name
