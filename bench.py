@@ -1,15 +1,21 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark: starky prove ms/STARK on B200 (BASELINE.json metric), one process per GPU.
+"""bench.py -- headline benchmark: starky prove ms/STARK (MillerLoop, FinalExp) on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--stark pairing_precomp] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--stark miller_loop] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full proof (sb_prove: trace LDE -> Poseidon Merkle -> quotient -> FRI -> proof in host memory) of one
-synthetic trace of the workload stark.  At N GPUs every rank proves its own trace (the reference's seven proofs are
-independent, SURVEY 8e "proof-level parallelism"), so scaling is weak and `value` = wall ms per step / N.
-  value : trace already resident in HBM when the timed region starts (layout DEVICE_COLMAJOR_U64)
-  e2e   : through the plugin call with the trace in pinned HOST memory (H2D of the trace and D2H of the proof inside)
-  --impl reference : the CPU restatement of the reference's prover (oracle/, all host threads) on the same workload.
+synthetic trace of the workload stark (default MillerLoopStark 97330 x 1024, BASELINE configs[2]).
+  N = 1  value : ms per proof, trace already resident in HBM when the timed region starts (DEVICE_COLMAJOR_U64)
+         e2e   : ms per proof through the plugin call with the trace in pinned HOST memory (H2D of the trace and D2H of
+                 the proof inside); `e2e_pageable_cols` is the same from 97 330 separately allocated pageable columns,
+                 the Vec<PolynomialValues<F>> the reference hands to prove() (aggregate_proof.rs:57-59)
+         also  : FinalExponentiateStark 73527 x 8192 (BASELINE configs[3]) with its own value / e2e / roofline / CPU sample
+  N > 1  value : ms of ONE proof of the same stark with the trace SHARDED over the N GPUs (column-sharded LDE -> NVLink
+                 exchange -> row-sharded leaf hashing + quotient -> small collectives): strong scaling.
+                 `replicas` (one independent proof per GPU, weak) and the FinalExp-shaped sharded proof are extras.
+  --impl reference : the CPU restatement of the reference's prover (oracle/, all host threads) on the same stark; each
+                 step is a bounded sample (the same AIR and all columns on 1/8 of the rows, time x 8).
 """
 import argparse
 import ctypes
@@ -36,6 +42,17 @@ WORKLOADS = {
     "ecc_agg": "ECCAggStark 3339 cols x 8192 rows, rate_bits 2 (BASELINE configs[4] member)",
 }
 K_CONSTRAINTS = {"fp12_mul": 82560, "pairing_precomp": 113634, "miller_loop": 145574, "final_exp": 360800, "ecc_agg": 20013}
+# rows of the CPU sample: the same AIR and all columns on 2^-shift of the rows, time x 2^shift (leaf hashing, quotient
+# and openings are linear in the rows; the NTTs lose a log factor, so the scaled figure slightly favours the CPU)
+CPU_SAMPLE_SHIFT = {"fp12_mul": 0, "pairing_precomp": 2, "miller_loop": 3, "final_exp": 4, "ecc_agg": 2}
+
+
+def config_for(stark, world):
+    """The `config` object of the JSON line: a function of (stark, world) only, so both arms print the same dict."""
+    return {"workload": WORKLOADS[stark], "trace": "synthetic: uniform u32 cells and public inputs, seeded PCG64",
+            "parallelism": "one proof on one GPU" if world == 1 else
+                           "one proof, trace sharded over %d GPUs (columns for the LDE, rows for leaf hashing and quotient)" % world,
+            "l2": "inputs larger than L2 (the trace alone is 0.8 GB for MillerLoop, 4.8 GB for FinalExp)"}
 
 
 def synthetic(info, seed):
@@ -83,9 +100,8 @@ class ClockSampler(threading.Thread):
 
 
 def probe_plan(world):
-    """Smallest shard plan that shard_plan accepts at every power-of-two world size up to 64: the symmetric-memory probe only
-    needs *a* valid plan, and a plan the planner itself rejects (fewer than 32 LDE positions per rank) would read as
-    'no symmetric memory' and silently demote the fused K1 to the all-to-all."""
+    """Smallest shard plan that shard_plan accepts at every power-of-two world size up to 64 (used by callers that only
+    need *a* valid plan, e.g. to probe peer access)."""
     from starky_bls12_381_b200.sharded import shard_plan
     return shard_plan(8, 10, 1, world)
 
@@ -97,59 +113,147 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference(args, info, rank, world):
-    """CPU arm: the oracle restatement of starky::prover::prove, all host threads, same stark and shape."""
+def measured_traffic(stark, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on `stark`, from the committed `ncu --set full`
+    capture of this round (profiles/r2_dram_traffic.json, written by tools/perf/summarize_ncu.py); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    try:
+        return json.load(open(path)).get(stark, {}).get(kernel)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of starky::prover::prove, all host threads
+# ---------------------------------------------------------------------------------------------------------------------
+def oracle_all_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 for nproc > 1: the CPU arm must still use every host core."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    import oracle_lib as O
+    O.build()
+    O.lib().orc_set_num_threads(n)
+    return O, int(O.lib().orc_num_threads())
+
+
+def cpu_sample(O, sb, stark, seed, shift=None):
+    """One proof by the CPU port of the same AIR and all columns on num_rows >> shift rows.  Returns (ms scaled to the
+    full height, description)."""
+    from starky_bls12_381_b200 import airfiles
+    info = sb.STARKS[stark]
+    shift = CPU_SAMPLE_SHIFT[stark] if shift is None else shift
+    rows = info.num_rows >> shift
+    flat = airfiles.air_path(stark, "air")
+    rng = np.random.Generator(np.random.PCG64(seed))
+    trace = rng.integers(0, 1 << 32, (info.columns, rows), dtype=np.uint64)
+    pis = rng.integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
+    p = O.make_params(stark_id=info.stark_id, log_n=rows.bit_length() - 1, n_cols=info.columns, n_pis=info.public_inputs,
+                      degree=info.constraint_degree, rate_bits=info.rate_bits, flags=1)
+    t0 = time.perf_counter()
+    rc, _ = O.prove(flat, p, trace, pis)
+    dt = time.perf_counter() - t0
+    assert rc == 0, O.err()
+    what = ("one full proof" if shift == 0 else
+            "one proof of the same AIR and all %d columns on %d of the %d rows, time x %d" % (info.columns, rows, info.num_rows, 1 << shift))
+    return 1e3 * dt * (1 << shift), what
+
+
+def run_reference(args, rank, world):
     if rank != 0:
         return
-    import oracle_lib as O
-    from starky_bls12_381_b200 import airfiles
-    O.build()
-    flat = airfiles.air_path(args.stark, "air")
-    trace, pis = synthetic(info, 0xB2000000 + info.stark_id)
-    p = O.make_params(stark_id=info.stark_id, log_n=info.num_rows.bit_length() - 1, n_cols=info.columns,
-                      n_pis=info.public_inputs, degree=info.constraint_degree, rate_bits=info.rate_bits, flags=1)
-    cores = O.lib().orc_num_threads()
-    times = []
+    import starky_bls12_381_b200 as sb
+    O, cores = oracle_all_threads()
+    times, what = [], ""
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        rc, _ = O.prove(flat, p, trace, pis)
-        assert rc == 0, O.err()
+        ms, what = cpu_sample(O, sb, args.stark, 0xB2000000 + it)
         if it >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(times) / len(times)
+            times.append(ms)
+    ms = float(np.mean(times))
     line = {"impl": "reference", "metric": "starky_prove_ms_per_stark", "value": ms, "unit": "ms", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.stark], "trace": "uniform u32 cells, seeded PCG64",
-                       "note": "CPU restatement of the reference algorithm (oracle/), not the Rust binary: no cargo in the image"},
-            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": "one full proof per step"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
+            "config": config_for(args.stark, world),
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": what,
+                             "note": "CPU restatement of the reference algorithm (oracle/), not the Rust binary: no cargo in the image"},
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def run_also(ctx, sb, name):
-    """One further stark of BASELINE.json's metric (MillerLoop, FinalExp), proved after the headline workload: 1 warm-up +
-    2 timed proofs with the trace resident, 1 end to end from pinned host memory."""
-    import torch
-    info = sb.STARKS[name]
-    p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-    trace, pis = synthetic(info, 0xB2000000 + info.stark_id)
-    host = torch.from_numpy(trace.view(np.int64)).pin_memory()
-    del trace
-    ctx.trace_upload(p, host.data_ptr())
-    ctx.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    proofs = [ctx.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64) for _ in range(2)]
-    ms = 1e3 * (time.perf_counter() - t0) / 2
-    t0 = time.perf_counter()
-    ctx.prove(p, host.data_ptr(), pis, sb.TraceLayout.COLMAJOR_U64)
-    ms_e2e = 1e3 * (time.perf_counter() - t0)
+# ---------------------------------------------------------------------------------------------------------------------
+# one stark on one GPU: resident / end-to-end timings, stage breakdown, roofline blocks
+# ---------------------------------------------------------------------------------------------------------------------
+def roofline_for(stark, info, kern, ms_step, imad, hbm_peak, peak_src):
     C, n, N = info.columns, info.num_rows, info.num_rows << info.rate_bits
+    perms = -(-C // 8) * N + (N - 16)
+    t_hash = (kern["leaf_hash"] + kern["merkle"]) * 1e-3
+    t_lde, t_q = kern["lde"] * 1e-3, kern["quotient"] * 1e-3
+    lde_bytes = 8.0 * C * (n + n + N)           # trace read + coefficients kept + LDE written
+    k2 = "leaf_sponge_sp_kernel" if N <= 64 * 148 else "leaf_sponge_dp_kernel"
+    return {
+        # dominant kernel of the step: the Poseidon leaf sponge (integer-pipe bound, SURVEY 8d)
+        "kernel": k2 + "+merkle_level_kernel", "bound": "imad",
+        "achieved": perms * U32_MACS_PER_PERM / t_hash / 1e9, "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
+        "frac": perms * U32_MACS_PER_PERM / t_hash / 1e9 / imad["mad_lo_u32_gops"],
+        "traffic": measured_traffic(stark, k2), "algorithmic_bytes": 8 * C * N,
+        "peak_source": "sb_measure_imad_peak: dependent-free mad.lo.u32, measured in this run",
+        "share_of_step": (kern["leaf_hash"] + kern["merkle"]) / ms_step,
+        "stages": {
+            "lde": {"bound": "hbm", "achieved": lde_bytes / t_lde / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": lde_bytes / t_lde / 1e9 / hbm_peak, "ms": kern["lde"], "peak_source": peak_src,
+                    "traffic": measured_traffic(stark, "lde8_kernel"), "algorithmic_bytes": lde_bytes},
+            "merkle_hbm_view": {"bound": "hbm", "achieved": 8.0 * C * N / t_hash / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": 8.0 * C * N / t_hash / 1e9 / hbm_peak, "ms": kern["leaf_hash"] + kern["merkle"]},
+            "quotient": {"bound": "imad", "achieved": K_CONSTRAINTS[stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9,
+                         "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
+                         "frac": K_CONSTRAINTS[stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9 / imad["mad_lo_u32_gops"],
+                         "ms": kern["quotient"], "traffic": measured_traffic(stark, "quotient_kernel"), "algorithmic_bytes": 8 * C * N},
+            "lde_quotient_merkle": {"ms": kern["lde"] + kern["quotient"] + kern["leaf_hash"] + kern["merkle"],
+                                    "lde_merkle_gbs": 8.0 * C * N / ((kern["lde"] + kern["leaf_hash"] + kern["merkle"]) * 1e-3) / 1e9},
+        },
+    }
+
+
+def pageable_columns(trace):
+    """The reference's Vec<PolynomialValues<F>>: one separately allocated (pageable) buffer per column + the pointer array."""
+    cols = [np.array(trace[c], dtype=np.uint64, copy=True) for c in range(trace.shape[0])]
+    ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    return cols, ptrs
+
+
+def measure_stark(ctx, sb, stark, steps, warmup, timed, seed, pageable_leg=True):
+    """value / e2e / stage breakdown of `stark` on this rank's GPU.  Returns (dict, trace, pis, last proof)."""
+    import torch
+    info = sb.STARKS[stark]
+    p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+    trace, pis = synthetic(info, seed)
+    host = torch.from_numpy(trace.view(np.int64)).pin_memory()
+    host_ptr = host.data_ptr()
+    ctx.trace_upload(p, host_ptr)
+    resident = lambda: ctx.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64)
+    e2e_fn = lambda: ctx.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
+    for _ in range(warmup):
+        resident()
+    l0 = ctx.kernel_launches()
+    dt, proofs = timed(resident, steps)
+    launches = ctx.kernel_launches() - l0
+    stage = {k: float(np.mean([pr.timings[k] for pr in proofs])) for k in proofs[0].timings}
     kern = {k: ctx.stage_ms(k) for k in ("lde", "leaf_hash", "merkle", "quotient")}
-    return {"workload": WORKLOADS[name], "ms": ms, "ms_e2e": ms_e2e, "stage_ms": {k: float(v) for k, v in proofs[-1].timings.items()},
-            "kernel_ms": kern, "lde_merkle_gbs": 8.0 * C * N / ((kern["lde"] + kern["leaf_hash"] + kern["merkle"]) * 1e-3) / 1e9,
-            "leaf_hash_mperm_s": (-(-C // 8) * N) / (kern["leaf_hash"] * 1e-3) / 1e6, "h2d_bytes": 8 * C * n}
+    e2e_fn()
+    dt_e2e, _ = timed(e2e_fn, steps)
+    out = {"ms": 1e3 * dt / steps, "ms_e2e": 1e3 * dt_e2e / steps, "stage_ms": stage, "kernel_ms": kern, "launches": int(launches),
+           "h2d_bytes": 8 * info.columns * info.num_rows + 8 * info.public_inputs,
+           "d2h_bytes": int(proofs[0].layout.total_words) * 8,
+           "leaf_hash_mperm_s": (-(-info.columns // 8) * (info.num_rows << info.rate_bits)) / (kern["leaf_hash"] * 1e-3) / 1e6}
+    if pageable_leg:
+        cols, ptrs = pageable_columns(trace)
+        pg = lambda: ctx.prove(p, ctypes.addressof(ptrs), pis, sb.TraceLayout.COLS_U64_PTRS)
+        pg()
+        k = max(1, min(steps, 3))
+        dt_pg, _ = timed(pg, k)
+        out["ms_e2e_pageable_cols"] = 1e3 * dt_pg / k
+        del cols, ptrs
+    del host
+    return out, trace, pis, proofs[-1], p
 
 
 FULL_SET = ["final_exp", "miller_loop", "miller_loop", "pairing_precomp", "pairing_precomp", "ecc_agg", "fp12_mul"]
@@ -160,12 +264,7 @@ def full_set_assignment(world):
     """BASELINE configs[4]: the seven starky proofs of one BLS signature verification (aggregate_proof.rs:279-370 proves
     them one after the other; they are independent once the native inputs are known).  Longest-processing-time-first
     onto `world` GPUs; returns one list of stark names per rank."""
-    loads, out = [0.0] * world, [[] for _ in range(world)]
-    for name in sorted(FULL_SET, key=lambda k: -FULL_SET_COST[k]):
-        g = min(range(world), key=lambda r: loads[r])
-        out[g].append(name)
-        loads[g] += FULL_SET_COST[name]
-    return out
+    return full_set_assignment_of(FULL_SET, world)
 
 
 def full_set_plan(world):
@@ -216,8 +315,8 @@ def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
             per.append(("final_exp(sharded)", 1e3 * (time.perf_counter() - t0)))
         for phase_jobs, phase_ctx in phases:
             # job i of a phase always runs on context i % len(contexts): the warm-up pass then sizes exactly the device
-            # buffers (and loads the constraint programs) the timed pass needs -- with a shared work queue a context can
-            # meet its largest shape for the first time inside the timed pass and pay a multi-GB cudaMalloc there
+            # buffers the timed pass needs -- with a shared work queue a context can meet its largest shape for the first time
+            # inside the timed pass and pay a multi-GB cudaMalloc there
             lanes = full_set_assignment_of([j[0] for j in phase_jobs], len(phase_ctx))     # longest-first over the contexts
             pool = list(phase_jobs)
             mine_jobs = []
@@ -239,7 +338,7 @@ def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
                 t.start()
             for t in ts:
                 t.join()
-    go()                 # warm-up: buffers of every shape allocated, constraint programs loaded
+    go()                 # warm-up: buffers of every shape allocated, constraint programs bound
     per.clear()
     dt, _ = timed(go, 1)
     return dt, per
@@ -262,41 +361,31 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--stark", default="pairing_precomp", choices=sorted(WORKLOADS))
+    ap.add_argument("--stark", default="miller_loop", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharded-stark", default="final_exp",
-                    help="shape of the second sharded trace commitment (column slices drawn per rank); '' to skip")
     ap.add_argument("--no-fused", action="store_true", help="sharded legs: NCCL all-to-all after K1 instead of K1 storing into peer memory")
     ap.add_argument("--no-full-set", action="store_true", help="skip the 7-proof BLS set (BASELINE configs[4])")
-    ap.add_argument("--also", default="miller_loop,final_exp",
-                    help="N=1 only: further starks proved once each after the headline workload (reported under 'also')")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only (no 'also', sharded FinalExp, in-flight, full set)")
+    ap.add_argument("--also", default="final_exp",
+                    help="further starks measured after the headline workload (N=1: whole proofs; N>1: sharded proofs)")
     args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)            # timing rules: at least three warm-up steps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
-    import starky_bls12_381_b200 as sb
-    info = sb.STARKS[args.stark]
     if args.impl == "reference":
-        return run_reference(args, info, rank, world)
+        return run_reference(args, rank, world)
 
     import torch
     import torch.distributed as dist
-    from starky_bls12_381_b200 import airfiles
+    import starky_bls12_381_b200 as sb
+    info = sb.STARKS[args.stark]
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    airfiles.air_path(args.stark, "airbin")
     ctx = sb.Context(local_rank)
-    p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-    trace, pis = synthetic(info, 0xB2000000 + info.stark_id + 1000 * rank)
-    # pinned host copy for the end-to-end leg; resident device copy for the kernel leg
-    host = torch.from_numpy(trace.view(np.int64)).pin_memory()
-    host_ptr = host.data_ptr()
-    ctx.trace_upload(p, host_ptr)
-    C, n, N = info.columns, info.num_rows, info.num_rows << info.rate_bits
 
     def barrier():
         torch.cuda.synchronize()
@@ -316,270 +405,220 @@ def main():
             dt = float(t.item())
         return dt, out
 
-    resident = lambda: ctx.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64)
-    e2e_fn = lambda: ctx.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
-    for _ in range(args.warmup):
-        resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ctx.kernel_launches()
-    dt, proofs = timed(resident, args.steps)
-    launches = ctx.kernel_launches() - l0
-    stage = {k: float(np.mean([pr.timings[k] for pr in proofs])) for k in proofs[0].timings}
-    kern = {k: ctx.stage_ms(k) for k in ("lde", "leaf_hash", "merkle", "quotient")}
-    e2e_fn()
-    dt_e2e, proofs_e2e = timed(e2e_fn, args.steps)
-    # ---- ONE trace commitment sharded over all ranks (column-sharded LDE -> all-to-all -> row-sharded leaf
-    # hashing -> digest all-gather -> tree), the LDE+Merkle GB/s half of BASELINE.json's metric ----
-    from starky_bls12_381_b200.sharded import GpuBackend, TorchGroup, commit_sharded, prove_sharded, quotient_sharded, shard_plan
-    plan = shard_plan(C, info.num_rows.bit_length() - 1, info.rate_bits, world)
-    base_trace = trace if rank == 0 else synthetic(info, 0xB2000000 + info.stark_id)[0]
-    c0, cg = plan.col_start[rank], plan.col_count[rank]
-    local = torch.from_numpy(np.ascontiguousarray(base_trace[c0:c0 + cg]).view(np.int64)).cuda()
-    backend = GpuBackend(ctx, p)
-    pis0 = pis if rank == 0 else np.random.Generator(np.random.PCG64(7)).integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
-    if world > 1:                      # every rank must evaluate with rank 0's public inputs
-        t_pis = torch.from_numpy(pis0.view(np.int64).copy()).cuda()
-        dist.broadcast(t_pis, 0)
-        pis0 = t_pis.cpu().numpy().view(np.uint64).copy()
+    extras = not args.no_extras
+    also_names = [x for x in args.also.split(",") if x and x != args.stark] if extras else []
+    C, n, N = info.columns, info.num_rows, info.num_rows << info.rate_bits
+    line = {}
 
-    def sharded_fn():
-        out = commit_sharded(backend, plan, rank, local)
-        out["quotient"] = quotient_sharded(backend, plan, rank, out["rows"], out["cap"], pis0)
-        return out
-    for _ in range(args.warmup):
-        sh = sharded_fn()
-    dt_sh, sh_out = timed(sharded_fn, args.steps)
-    sh_cap = sh_out[-1]["cap"]
-    sh_q = sh_out[-1]["quotient"]["q"].cpu().numpy().view(np.uint64).copy()
-    sh_q_ms = ctx.stage_ms("quotient")
-    sh_out_alphas = sh_out[-1]["quotient"]["alphas"]
-    del sh_out, sh, local
-    torch.cuda.empty_cache()
-    # ---- the same sharded commitment on the FinalExp shape (BASELINE configs[3]; throughput-bound, the shape that scales):
-    # every rank draws its own column slice (seed + rank), so no 4.8 GB trace is replicated on the host ----
-    def fe_leg():
-        fe = None
-        if args.sharded_stark and args.sharded_stark != args.stark:
-            fi = sb.STARKS[args.sharded_stark]
-            fp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1)
-            fplan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, world)
-            fcg = fplan.col_count[rank]
-            frng = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id + 1000 * rank))
-            flocal = torch.from_numpy(frng.integers(0, 1 << 32, (fcg, fi.num_rows), dtype=np.uint64).view(np.int64)).cuda()
-            fbackend = GpuBackend(ctx, fp)
-            airfiles.air_path(args.sharded_stark, "airbin")
-            fpis = np.random.Generator(np.random.PCG64(0xB2100000 + fi.stark_id)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
+    if world == 1:
+        # ---------------- N = 1: whole proofs on one GPU ----------------
+        m, trace, pis, last, p = measure_stark(ctx, sb, args.stark, args.steps, args.warmup, timed, 0xB2000000 + info.stark_id)
+        clocks = sampler.stop()
+        hbm_peak, peak_src = peaks()
+        imad = ctx.measure_imad_peak()
+        cpu = None
+        if not args.no_cpu_baseline:
+            O, cores = oracle_all_threads()
+            from starky_bls12_381_b200 import airfiles
+            op = O.Params.from_buffer_copy(bytes(p))
+            t0 = time.perf_counter()
+            rc, words = O.prove(airfiles.air_path(args.stark, "air"), op, trace, pis)
+            cpu_ms = 1e3 * (time.perf_counter() - t0)
+            cpu = {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port",
+                   "sample": "one full proof of the same trace (whole workload, no scaling)",
+                   "proof_bit_identical_to_gpu": bool(rc == 0 and np.array_equal(words, last.words))}
+        del trace
+        line = {
+            "metric": "starky_prove_ms_per_stark", "value": m["ms"], "unit": "ms", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks)", "data": "synthetic", "config": config_for(args.stark, 1),
+            "e2e": {"value": m["ms_e2e"], "unit": "ms", "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"]},
+            "e2e_pageable_cols": {"value": m.get("ms_e2e_pageable_cols"), "unit": "ms",
+                                  "note": "trace handed over as %d separately allocated pageable columns (SB_TRACE_COLS_U64_PTRS, the "
+                                          "reference's Vec<PolynomialValues<F>>): gathered into pinned staging slabs inside the call" % C},
+            "gpu_launches": m["launches"], "clocks": clocks,
+            "roofline": roofline_for(args.stark, info, m["kernel_ms"], m["ms"], imad, hbm_peak, peak_src),
+            "cpu_baseline": cpu, "stage_ms": m["stage_ms"], "kernel_ms": m["kernel_ms"], "leaf_hash_mperm_s": m["leaf_hash_mperm_s"],
+        }
+        also = {}
+        for name in also_names:
+            def leg(name=name):
+                ai = sb.STARKS[name]
+                am, atrace, _, _, _ = measure_stark(ctx, sb, name, 2, 1, timed, 0xB2000000 + ai.stark_id, pageable_leg=False)
+                del atrace
+                out = {"workload": WORKLOADS[name], "value": am["ms"], "unit": "ms",
+                       "e2e": {"value": am["ms_e2e"], "unit": "ms", "h2d_bytes_per_step": am["h2d_bytes"], "d2h_bytes_per_step": am["d2h_bytes"]},
+                       "stage_ms": am["stage_ms"], "kernel_ms": am["kernel_ms"], "leaf_hash_mperm_s": am["leaf_hash_mperm_s"],
+                       "roofline": roofline_for(name, ai, am["kernel_ms"], am["ms"], imad, hbm_peak, peak_src)}
+                if not args.no_cpu_baseline:
+                    O, cores = oracle_all_threads()
+                    ms, what = cpu_sample(O, sb, name, 0xB2500000 + ai.stark_id)
+                    out["cpu_baseline"] = {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": what}
+                return out
+            leg.__name__ = "also_" + name
+            also[name] = optional(leg, world)
+        line["also"] = also
+    else:
+        # ---------------- N > 1: ONE proof sharded over all ranks (strong scaling) ----------------
+        from starky_bls12_381_b200 import multi
+        group = multi.Group.from_torch(ctx, rank, world, local_rank)       # NCCL communicator + peer row buffers inside the library
+        p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+        trace, pis = synthetic(info, 0xB2000000 + info.stark_id)           # same seed on every rank: one trace, sliced
+        c0, cg = group.column_slice(p)
+        local_host = torch.from_numpy(np.ascontiguousarray(trace[c0:c0 + cg]).view(np.int64)).pin_memory()
+        local_dev = local_host.cuda()
+        del trace
+        fused = not args.no_fused
+        res_fn = lambda: group.prove(p, local_dev.data_ptr(), pis, on_device=True, fused=fused)
+        e2e_fn = lambda: group.prove(p, local_host.data_ptr(), pis, on_device=False, fused=fused)
+        for _ in range(args.warmup):
+            res_fn()
+        l0 = ctx.kernel_launches()
+        dt, proofs = timed(res_fn, args.steps)
+        launches = ctx.kernel_launches() - l0
+        kern = {k: ctx.stage_ms(k) for k in ("lde", "leaf_hash", "merkle", "quotient")}
+        e2e_fn()
+        dt_e2e, _ = timed(e2e_fn, args.steps)
+        same = multi.same_on_every_rank(proofs[-1].words)
+        clocks = sampler.stop() if rank == 0 else None
+        ms, ms_e2e = 1e3 * dt / args.steps, 1e3 * dt_e2e / args.steps
+        hbm_peak, peak_src = peaks()
+        imad = ctx.measure_imad_peak()
+        line = {
+            "metric": "starky_prove_ms_per_stark", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks)", "data": "synthetic", "config": config_for(args.stark, world),
+            "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": 8 * cg * n + 8 * info.public_inputs,
+                    "d2h_bytes_per_step": int(proofs[-1].layout.total_words) * 8,
+                    "note": "every rank copies its column slice from pinned host memory inside the call; bytes are rank 0's"},
+            "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None,
+            "roofline": {"kernel": "leaf_sponge (this rank's %d of %d leaves)" % (N // world, N), "bound": "imad",
+                         "achieved": (-(-C // 8) * (N // world)) * U32_MACS_PER_PERM / (kern["leaf_hash"] * 1e-3) / 1e9,
+                         "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
+                         "frac": (-(-C // 8) * (N // world)) * U32_MACS_PER_PERM / (kern["leaf_hash"] * 1e-3) / 1e9 / imad["mad_lo_u32_gops"],
+                         "traffic": None, "share_of_step": kern["leaf_hash"] / ms,
+                         "peak_source": "sb_measure_imad_peak: dependent-free mad.lo.u32, measured in this run"},
+            "sharded_proof": {"ranks": world, "same_proof_on_every_rank": same, "k1_stores_into_peer_memory": bool(group.fused_ok and fused),
+                              "phase_ms_rank0": proofs[-1].phase_ms, "library_stage_ms_rank0": {k: round(float(v), 2) for k, v in proofs[-1].timings.items()},
+                              "kernel_ms_rank0": kern,
+                              "note": "sb_prove on a multi-GPU group: column-sharded LDE storing into the owners' row buffers over NVLink, "
+                                      "row-sharded leaf hashing and quotient, digests / halo rows / quotient values / openings / FRI "
+                                      "combine partials / query rows exchanged with NCCL inside libstarkyb200; quotient commitment, "
+                                      "transcript, FRI rounds and proof of work redundantly on every rank"},
+        }
+        del local_host, local_dev
+        torch.cuda.empty_cache()
+        if extras:
+            # replicas: one independent proof per GPU (the reference's seven proofs are independent), weak scaling
+            def replicas():
+                rm, rtrace, _, _, _ = measure_stark(ctx, sb, args.stark, max(1, args.steps // 2), 1, timed, 0xB2000000 + info.stark_id + 1000 * rank,
+                                                    pageable_leg=False)
+                del rtrace
+                return {"ms_per_proof_per_gpu": rm["ms"], "ms_per_proof_whole_box": rm["ms"] / world, "e2e_ms_per_proof_whole_box": rm["ms_e2e"] / world,
+                        "scaling": "weak", "note": "every rank proves its own trace, no data-path collective"}
+            line["replicas"] = optional(replicas, world)
+            also = {}
+            for name in also_names:
+                def leg(name=name):
+                    ai = sb.STARKS[name]
+                    ap_ = sb.standard_params(ai.stark_id, ai.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+                    a0, ag = group.column_slice(ap_)
+                    # every rank draws its own column slice (seed + rank): no 4.8 GB trace is replicated on the host
+                    arng = np.random.Generator(np.random.PCG64(0xB2100000 + ai.stark_id + 1000 * rank))
+                    ahost = torch.from_numpy(arng.integers(0, 1 << 32, (ag, ai.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
+                    adev = ahost.cuda()
+                    apis = np.random.Generator(np.random.PCG64(0xB2100000 + ai.stark_id)).integers(0, 1 << 32, ai.public_inputs, dtype=np.uint64)
+                    fn = lambda: group.prove(ap_, adev.data_ptr(), apis, on_device=True, fused=fused)
+                    fn()
+                    k = max(1, min(args.steps, 3))
+                    adt, aproofs = timed(fn, k)
+                    akern = {kk: ctx.stage_ms(kk) for kk in ("lde", "leaf_hash", "merkle", "quotient")}
+                    fe2e = lambda: group.prove(ap_, ahost.data_ptr(), apis, on_device=False, fused=fused)
+                    fe2e()
+                    adt2, _ = timed(fe2e, k)
+                    return {"workload": WORKLOADS[name], "value": 1e3 * adt / k, "unit": "ms", "ranks": world,
+                            "e2e": {"value": 1e3 * adt2 / k, "unit": "ms", "h2d_bytes_per_step": 8 * ag * ai.num_rows, "d2h_bytes_per_step": int(aproofs[-1].layout.total_words) * 8},
+                            "same_proof_on_every_rank": multi.same_on_every_rank(aproofs[-1].words),
+                            "phase_ms_rank0": aproofs[-1].phase_ms, "kernel_ms_rank0": akern}
+                leg.__name__ = "also_sharded_" + name
+                also[name] = optional(leg, world)
+            line["also"] = also
+        group.close()
 
-            fused = world > 1 and not args.no_fused
-            if fused:
-                # symmetric memory needs peer access between the GPUs of the box; probe it once and let every rank agree, so
-                # that a box without it falls back to the NCCL all-to-all instead of losing the bench line
-                ok = 1
-                try:
-                    probe = TorchGroup(world, rank).symmetric_rows(probe_plan(world), torch.device("cuda", local_rank))
-                    probe[2]()
-                    del probe
-                except Exception as e:          # noqa: BLE001
-                    ok = 0
-                    print("symmetric memory unavailable on rank %d: %r" % (rank, e), file=sys.stderr, flush=True)
-                flag = torch.tensor([ok], device="cuda")
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                fused = bool(flag.item())
+    if extras:
+        # ---- several proofs in flight on one GPU (one context and one host thread per proof): the leaf sponge of these shapes
+        # is latency-bound and the host transcript is a strictly sequential sponge, so concurrent proofs fill each other's gaps
+        more = [sb.Context(local_rank) for _ in range(3)]
 
-            def ffn():
-                out = commit_sharded(fbackend, fplan, rank, flocal, fused=fused)
-                qq = quotient_sharded(fbackend, fplan, rank, out["rows"], out["cap"], fpis)
-                return out["cap"], qq["q"][:, :4]
-            ffn()
-            dt_fe, _ = timed(ffn, max(1, args.steps - 1))
-            fN = fi.num_rows << fi.rate_bits
-            ms_fe = 1e3 * dt_fe / max(1, args.steps - 1)
-            fe = {"workload": WORKLOADS[args.sharded_stark], "ranks": world, "ms": ms_fe,
-                  "lde_merkle_gbs": 8.0 * fi.columns * fN / (ms_fe * 1e-3) / 1e9, "a2a_bytes_out_per_rank": fplan.a2a_bytes_out(0),
-                  "leaf_hash_ms_rank0": ctx.stage_ms("leaf_hash"), "lde_ms_rank0": ctx.stage_ms("lde"),
-                  "quotient_ms_rank0": ctx.stage_ms("quotient"), "k1_stores_into_peer_memory": fused,
-                  "note": "column-sharded LDE -> all-to-all (or, fused: K1 stores into the owners' row buffers over NVLink) -> row-sharded leaf hashing -> digest all-gather -> tree -> alphas -> "
-                          "halo row exchange -> row-sharded quotient -> all-gather of the 2 x N quotient values"}
-            # the WHOLE proof of that sharded trace: sb_prove_sharded on every rank, the five distributed steps (commitment,
-            # quotient, openings, FRI batch combine, query rows) as NCCL collectives; every rank ends with the same proof
-            fp_inv = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-            pbackend = GpuBackend(ctx, fp_inv)
-            comm = TorchGroup(world, rank)
-            pfn = lambda: prove_sharded(pbackend, fplan, rank, flocal, fpis, comm=comm, fused=fused)
-            pfn()
-            dt_fp, fproofs = timed(pfn, max(1, args.steps - 1))
-            caps = torch.from_numpy(fproofs[-1].words[:64].view(np.int64).copy()).cuda()
-            same = True
-            if world > 1:
-                allc = [torch.empty_like(caps) for _ in range(world)]
-                dist.all_gather(allc, caps)
-                same = all(bool(torch.equal(allc[0], c)) for c in allc)
-            fe["sharded_proof"] = {"ms": 1e3 * dt_fp / max(1, args.steps - 1), "ranks": world, "proof_words": int(fproofs[-1].layout.total_words),
-                                   "same_proof_on_every_rank": same, "hook_ms_rank0": {k: round(v, 2) for k, v in fproofs[-1].hook_ms.items()},
-                                   "library_stage_ms_rank0": {k: round(float(v), 2) for k, v in fproofs[-1].timings.items()},
-                                   "note": "one FinalExp-shaped proof, trace sharded over all ranks (sb_prove_sharded): commitment + quotient as "
-                                           "above, openings from column-sharded coefficient slices (all-gather), FRI batch combine (per-rank "
-                                           "partial sums, all-gather + add), query rows from their owners; quotient commitment, transcript, "
-                                           "FRI rounds and proof of work redundantly on every rank"}
-            del flocal, fbackend, pbackend, fproofs
-            torch.cuda.empty_cache()
-        return fe
+        def in_flight_leg():
+            hinfo = sb.STARKS[args.stark]
+            hp = sb.standard_params(hinfo.stark_id, hinfo.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+            htrace, hpis = synthetic(hinfo, 0xB2000000 + hinfo.stark_id + 1000 * rank)
+            hhost = torch.from_numpy(htrace.view(np.int64)).pin_memory()
+            del htrace
+            hptr = hhost.data_ptr()
+            k = max(1, min(args.steps, 4))
+            for c in [ctx] + more:
+                c.prove(hp, hptr, hpis, sb.TraceLayout.COLMAJOR_U64)
 
-    fe = optional(fe_leg, world)
-    # ---- several proofs in flight on one GPU (one context and one host thread per proof): the leaf sponge of these shapes
-    # is latency-bound (one 32-leaf group per SM) and the host transcript is a strictly sequential sponge (~1 us per
-    # permutation), so concurrent proofs fill each other's gaps -- how a scheduler for the reference's seven independent
-    # proofs runs them.  End to end: every proof is taken from pinned host memory. ----
-    ctx2 = sb.Context(local_rank)
-    more = [sb.Context(local_rank) for _ in range(2)]
-    for c in [ctx2] + more:
-        c.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
+            def run_with(contexts):
+                def run():
+                    def worker(c):
+                        for _ in range(k):
+                            c.prove(hp, hptr, hpis, sb.TraceLayout.COLMAJOR_U64)
+                    ts = [threading.Thread(target=worker, args=(c,)) for c in contexts]
+                    for t in ts:
+                        t.start()
+                    for t in ts:
+                        t.join()
+                return run
+            d2, _ = timed(run_with([ctx, more[0]]), 1)
+            d4, _ = timed(run_with([ctx] + more), 1)
+            return {"2": {"ms_per_proof": 1e3 * d2 / (2 * k) / world}, "4": {"ms_per_proof": 1e3 * d4 / (4 * k) / world},
+                    "note": "k contexts per GPU, one host thread each, end to end from pinned host memory, every GPU busy: the "
+                            "latency-bound leaf sponge and the sequential host transcript of one proof overlap the kernels of the others"}
+        inflight = optional(in_flight_leg, world)
 
-    def in_flight(contexts):
-        def run():
-            def worker(c):
-                for _ in range(args.steps):
-                    c.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
-            ts = [threading.Thread(target=worker, args=(c,)) for c in contexts]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-        return run
-    dt_pipe2, _ = timed(in_flight([ctx, ctx2]), 1)
-    dt_pipe4, _ = timed(in_flight([ctx, ctx2] + more), 1)
-    # ---- BASELINE configs[4]: the seven proofs of one BLS signature verification over all ranks, two in flight per GPU ----
-    def full_leg():
-        full = None
-        if not args.no_full_set:
-            for nm in set(FULL_SET):
-                airfiles.air_path(nm, "airbin")
+        # ---- BASELINE configs[4]: the seven proofs of one BLS signature verification over all ranks ----
+        def full_leg():
+            if args.no_full_set:
+                return None
             fe_ranks, per_rank = full_set_plan(world)
             mine = per_rank[rank]
-            sharded_job, fe_fused = None, None
+            sharded_job, sub = None, None
             if fe_ranks:
-                grp = dist.new_group(ranks=fe_ranks)                      # collective: every rank calls it
+                from starky_bls12_381_b200 import multi
+                sub = multi.Group.from_torch(ctx, rank, world, local_rank, ranks=fe_ranks)      # collective over all ranks
                 if rank in fe_ranks:
                     fi = sb.STARKS["final_exp"]
                     sp = sb.standard_params(fi.stark_id, fi.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-                    splan = shard_plan(fi.columns, fi.num_rows.bit_length() - 1, fi.rate_bits, len(fe_ranks))
-                    sr = fe_ranks.index(rank)
-                    srng = np.random.Generator(np.random.PCG64(0xB2400000 + sr))
-                    slocal = torch.from_numpy(srng.integers(0, 1 << 32, (splan.col_count[sr], fi.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
+                    s0, sg = sub.column_slice(sp)
+                    srng = np.random.Generator(np.random.PCG64(0xB2400000 + fe_ranks.index(rank)))
+                    slocal = torch.from_numpy(srng.integers(0, 1 << 32, (sg, fi.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
                     spis = np.random.Generator(np.random.PCG64(0xB2400099)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
-                    sbackend, scomm = GpuBackend(ctx, sp), TorchGroup(len(fe_ranks), sr, grp)
-                    fs_fused = 0 if args.no_fused else 1
-                    if fs_fused:
-                        # same probe as the sharded legs, agreed inside the FinalExp sub-group only
-                        try:
-                            probe = scomm.symmetric_rows(probe_plan(len(fe_ranks)), torch.device("cuda", local_rank))
-                            probe[2]()
-                            del probe
-                        except Exception as e:          # noqa: BLE001
-                            fs_fused = 0
-                            print("symmetric memory unavailable in the FinalExp sub-group on rank %d: %r" % (rank, e), file=sys.stderr, flush=True)
-                        flag = torch.tensor([fs_fused], device="cuda")
-                        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=grp)
-                        fs_fused = int(flag.item())
-                    fe_fused = bool(fs_fused)
-                    sharded_job = lambda: prove_sharded(sbackend, splan, sr, slocal, spis, comm=scomm, fused=fe_fused)
-            dt_full, per = run_full_set(sb, [ctx, ctx2] + more, mine, rank, timed, sharded_job)
-            full = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
-                                "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
-                    "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks, "final_exp_k1_stores_into_peer_memory": fe_fused, "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
-                    "note": "from 4 GPUs on FinalExp is sharded over half of them (sb_prove_sharded) and the other six proofs share the rest; otherwise "
-                            "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run up to four in "
-                            "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
-        return full
-
-    full = optional(full_leg, world)
-    ctx2.close()
-    for c in more:
-        c.close()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = 1e3 * dt / args.steps
-    ms_e2e = 1e3 * dt_e2e / args.steps
-    proof_bytes = int(proofs[0].layout.total_words) * 8
+                    sharded_job = lambda: sub.prove(sp, slocal.data_ptr(), spis, on_device=False, fused=not args.no_fused)
+            dt_full, per = run_full_set(sb, [ctx] + more, mine, rank, timed, sharded_job)
+            out = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
+                               "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
+                   "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks,
+                   "final_exp_k1_stores_into_peer_memory": bool(sub is not None and sub.member and sub.fused_ok and not args.no_fused) if fe_ranks else None,
+                   "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
+                   "note": "from 4 GPUs on FinalExp is sharded over half of them and the other six proofs share the rest; otherwise "
+                           "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run up to four in "
+                           "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
+            if sub is not None:
+                sub.close()
+            return out
+        full = optional(full_leg, world)
+        for c in more:
+            c.close()
+        line["in_flight"] = inflight
+        line["full_bls_set"] = full
 
     if rank == 0:
-        hbm_peak, peak_src = peaks()
-        imad = ctx.measure_imad_peak()
-        perms = -(-C // 8) * N + (N - 16)
-        t_hash = (kern["leaf_hash"] + kern["merkle"]) * 1e-3
-        t_lde = kern["lde"] * 1e-3
-        t_q = kern["quotient"] * 1e-3
-        lde_bytes = 8.0 * C * (n + n + N)           # trace read + coefficients kept + LDE written
-        roof = {
-            # dominant kernel of the step: the Poseidon leaf sponge (integer-pipe bound)
-            "kernel": ("leaf_sponge_sp_kernel" if N <= 64 * 148 else "leaf_sponge_dp_kernel") + "+merkle_level_kernel", "bound": "imad",
-            "achieved": perms * U32_MACS_PER_PERM / t_hash / 1e9, "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
-            "frac": perms * U32_MACS_PER_PERM / t_hash / 1e9 / imad["mad_lo_u32_gops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of the leaf sponge from the committed ncu --set full capture
-            # (profiles/r1_top_kernels_pairing_precomp_final.txt); algorithmic = 8 C N = 962.6 MB
-            "traffic": 975198208 if args.stark == "pairing_precomp" else None,
-            "peak_source": "sb_measure_imad_peak: dependent-free mad.lo.u32, measured in this run",
-            "share_of_step": (kern["leaf_hash"] + kern["merkle"]) / ms_step,
-            "stages": {
-                "lde": {"bound": "hbm", "achieved": lde_bytes / t_lde / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": lde_bytes / t_lde / 1e9 / hbm_peak, "ms": kern["lde"], "peak_source": peak_src},
-                "merkle_hbm_view": {"bound": "hbm", "achieved": 8.0 * C * N / t_hash / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": 8.0 * C * N / t_hash / 1e9 / hbm_peak, "ms": kern["leaf_hash"] + kern["merkle"]},
-                "quotient": {"bound": "imad", "achieved": K_CONSTRAINTS[args.stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9,
-                             "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
-                             "frac": K_CONSTRAINTS[args.stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9 / imad["mad_lo_u32_gops"],
-                             "ms": kern["quotient"]},
-            },
-        }
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            import oracle_lib as O
-            O.build()
-            flat = airfiles.air_path(args.stark, "air")
-            op = O.Params.from_buffer_copy(bytes(p))
-            t0 = time.perf_counter()
-            rc, words = O.prove(flat, op, trace, pis)
-            cpu_ms = 1e3 * (time.perf_counter() - t0)
-            same = bool(rc == 0 and np.array_equal(words, proofs[0].words))
-            cpu = {"value": cpu_ms, "unit": "ms", "cores": int(O.lib().orc_num_threads()), "kind": "port",
-                   "sample": "one full proof of the same trace", "proof_bit_identical_to_gpu": same}
-        ms_sh = 1e3 * dt_sh / args.steps
-        from helpers import pos_to_natural
-        ctx.lde_commit(p, trace, want_lde=False, want_digests=False)
-        q_one = ctx.quotient_values(p, pis0, sh_out_alphas)[:, pos_to_natural(p.log_n, p.rate_bits)]
-        sh_q_same = bool(np.array_equal(q_one, sh_q))
-        sharded = {"ms": ms_sh, "lde_merkle_gbs": 8.0 * C * N / (ms_sh * 1e-3) / 1e9, "ranks": world,
-                   "a2a_bytes_out_per_rank": plan.a2a_bytes_out(0), "digest_allgather_bytes": 32 * N,
-                   "cap_equals_single_gpu_path": bool(np.array_equal(sh_cap, proofs[0].words[:4 * (1 << p.cap_height)].reshape(-1, 4))),
-                   "quotient_ms_rank0": sh_q_ms, "quotient_equals_single_gpu_path": sh_q_same,
-                   "note": "one trace, columns sharded for K1, rows sharded for K2 and K4 (quotient), NCCL all-to-all + "
-                           "all-gathers (digests, halo rows, quotient values) in the timed region"}
-        also = {}
-        if world == 1 and args.also:
-            for name in [x for x in args.also.split(",") if x and x != args.stark]:
-                try:
-                    also[name] = run_also(ctx, sb, name)
-                except Exception as e:     # keep the headline line alive
-                    also[name] = {"error": repr(e)}
-        line = {
-            "metric": "starky_prove_ms_per_stark", "value": ms_step / world, "unit": "ms", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.stark], "trace": "uniform u32 cells, seeded PCG64, one trace per rank",
-                       "parallelism": "proofs: one independent proof per GPU (the reference's 7 proofs are independent), no "
-                                      "data-path collective; 'sharded_commit' is the column->row sharded trace commitment over all ranks",
-                       "l2": "inputs larger than L2 (trace %.0f MB, LDE %.0f MB)" % (8e-6 * C * n, 8e-6 * C * N),
-                       "lde_merkle_gbs": 8.0 * C * N / ((kern["lde"] + kern["leaf_hash"] + kern["merkle"]) * 1e-3) / 1e9},
-            "e2e": {"value": ms_e2e / world, "unit": "ms", "h2d_bytes_per_step": 8 * C * n + 8 * info.public_inputs,
-                    "d2h_bytes_per_step": proof_bytes},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stage, "kernel_ms": kern, "sharded_commit": sharded, "sharded_commit_scaling_shape": fe, "also": also,
-            "full_bls_set": full,
-            "in_flight": {"2": {"ms_per_proof": 1e3 * dt_pipe2 / (2 * args.steps) / world}, "4": {"ms_per_proof": 1e3 * dt_pipe4 / (4 * args.steps) / world},
-                          "note": "k contexts per GPU, one host thread each, end to end from pinned host memory: the latency-bound leaf "
-                                  "sponge and the sequential host transcript of one proof overlap the kernels of the others"},
-        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

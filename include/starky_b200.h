@@ -27,7 +27,7 @@ extern "C" {
 #define SB_OK 0
 #define SB_EINVAL (-1)                  /* bad argument / shape mismatch with the constraint program      */
 #define SB_ECUDA (-2)                   /* CUDA runtime failure (message in sb_last_error)                 */
-#define SB_ENCCL (-3)                   /* reserved: collective failure                                    */
+#define SB_ENCCL (-3)                   /* collective failure: NCCL missing / error, or a peer rank of a group failed */
 #define SB_EQUOTIENT_NOT_DIVISIBLE (-4) /* reference: panic "Quotient has failed, the vanishing polynomial is not divisible by Z_H" */
 #define SB_EZETA_IN_SUBGROUP (-5)       /* reference: Err("Opening point is in the subgroup.")             */
 #define SB_EPOW (-6)                    /* reference: expect("Proof of work failed...")                    */
@@ -122,7 +122,8 @@ typedef struct sb_proof {
 } sb_proof;
 
 /* ---- lifecycle ---- */
-int sb_init(const int* devices, int n_devices, sb_ctx** out); /* devices == NULL: current device */
+int sb_init(const int* devices, int n_devices, sb_ctx** out); /* devices == NULL: current device; n_devices > 1: one ctx over
+                                                                 several GPUs, sb_prove shards the trace (see "multi-GPU groups") */
 void sb_destroy(sb_ctx* ctx);
 const char* sb_last_error(sb_ctx* ctx); /* ctx may be NULL: last error of this thread */
 
@@ -136,6 +137,25 @@ int sb_air_load(sb_ctx* ctx, uint32_t stark_id, const char* path);
 int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout,
              const uint64_t* public_inputs, sb_proof** out);
 void sb_proof_free(sb_proof* proof);
+
+/* ---- proof wire formats: the proof as bytes for a consumer that does not link this library -- the
+ *      reference's verify_stark_proof / recursive verifier take a starky::proof::StarkProofWithPublicInputs<F, C, 2>
+ *      (aggregate_proof.rs:67,113,146,177,220 and :435-439).  Host code only: works in a process without a GPU. ---- */
+enum sb_wire_format {
+  SB_WIRE_POD = 0,            /* "SBPROOF1" | sb_params | total_words u64 | words (LE u64): self-describing flat POD          */
+  SB_WIRE_PLONKY2_BUFFER = 1, /* the fields of StarkProofWithPublicInputs in declaration order through the primitives of
+                                 plonky2::util::serialization::Write (write_merkle_cap, write_field_ext_vec, write_fri_proof
+                                 with u8-prefixed Merkle proofs, write_field_vec); no length prefixes: read with the params */
+  SB_WIRE_SERDE_JSON = 2      /* serde_json of the same struct (FriProof / MerkleCap / MerkleProof exactly as their
+                                 #[derive(Serialize)] print them); write-only                                              */
+};
+/* buf == NULL: only computes *len_out.  p may be NULL for the two plonky2 formats (the JSON then omits "config"). */
+int sb_proof_serialize(const sb_proof* proof, const sb_params* p, int format, void* buf, size_t cap, size_t* len_out);
+/* SB_WIRE_POD: p optional (checked against the image when given), the image's params are returned in params_out (optional);
+ * SB_WIRE_PLONKY2_BUFFER: p required.  Rejects truncated / oversized images and non-canonical field elements. */
+int sb_proof_deserialize(const void* buf, size_t len, int format, const sb_params* p, sb_params* params_out, sb_proof** out);
+/* A proof object from n_words raw POD words of the layout `p` defines (copied). */
+int sb_proof_from_words(const sb_params* p, const uint64_t* words, size_t n_words, sb_proof** out);
 
 /* ---- stage-level entry points (parity tests and benchmarks; SURVEY 8b "Stage-level exports") ----
  * Device buffers stay resident in the ctx between stage calls of one proof. */
@@ -219,6 +239,45 @@ int sb_combine_cols_device(sb_ctx* ctx, const sb_params* p, const uint64_t* d_co
                            const uint64_t* alpha, uint32_t first_col, uint64_t* d_out);
 int sb_memcpy_device(sb_ctx* ctx, void* d_dst, const void* d_src, uint64_t bytes);
 int sb_synchronize(sb_ctx* ctx);
+
+/* ---- multi-GPU groups: one proof with the trace sharded over the GPUs of one box, entirely inside the
+ *      library.  Replaces the same starky::prover::prove call (aggregate_proof.rs:59,105,138,169,212); the host only
+ *      decides which GPUs form a group.
+ *      Column-sharded K1 stores the LDE straight into the row buffers of the ranks that own the row blocks (peer memory
+ *      over NVLink: CUDA IPC mappings between processes, peer access inside one process); leaf hashing and the quotient
+ *      run row-local; digests, halo rows, quotient values, openings, FRI combine partials (added mod p on the device)
+ *      and the 84 query rows are exchanged with NCCL (one process per GPU) or with peer copies (one process, several
+ *      GPUs).  Every rank ends with the same proof.
+ *
+ *      One process per GPU:   rank 0 calls sb_group_unique_id and hands the 128 bytes to the other ranks over any channel
+ *                             (MPI, a file, torch.distributed); every rank then calls sb_group_init_rank (collective).
+ *                             NCCL is loaded with dlopen("libnccl.so.2") at that point; SB_ENCCL if it is missing.
+ *      One process, n GPUs:   sb_init(devices, n > 1, &ctx) -- sb_prove(ctx, ...) then cuts a host trace
+ *                             (SB_TRACE_COLMAJOR_U64 or SB_TRACE_COLS_U64_PTRS) into column slices and proves on all n
+ *                             devices, one internal host thread per device; or sb_group_init_local over contexts the
+ *                             caller made, with sb_group_prove called from one thread per rank. ---- */
+typedef struct sb_group sb_group;
+#define SB_GROUP_UNIQUE_ID_BYTES 128
+#define SB_GROUP_NO_FUSED 1u   /* sb_group_prove flag: all-to-all after K1 instead of K1 storing into peer memory */
+int sb_group_unique_id(uint8_t id[SB_GROUP_UNIQUE_ID_BYTES]);
+int sb_group_init_rank(sb_ctx* ctx, int rank, int world, const uint8_t id[SB_GROUP_UNIQUE_ID_BYTES], sb_group** out);
+int sb_group_init_local(sb_ctx* const* ctxs, int world, sb_group** out /* [world] */);
+void sb_group_destroy(sb_group* g);
+int sb_group_rank(const sb_group* g);
+int sb_group_size(const sb_group* g);
+/* The columns rank `rank` of a `world`-rank group owns ([first_col, first_col + n_cols_local), ragged: 97330 = 2 x 12167 +
+ * 6 x 12166) and the LDE positions per rank; pure host arithmetic.  sb_group_column_slice: the same for this rank. */
+int sb_shard_columns(const sb_params* p, uint32_t world, uint32_t rank, uint32_t* first_col, uint32_t* n_cols_local,
+                     uint32_t* rows_per_rank);
+int sb_group_column_slice(const sb_group* g, const sb_params* p, uint32_t* first_col, uint32_t* n_cols_local);
+/* Collective: every rank of the group calls it with ITS column slice, local_trace = [n_cols_local][n] u64 column-major in
+ * host memory (on_device = 0; copied inside the call) or on this rank's GPU (on_device = 1), and the same public inputs.
+ * Every rank receives the same proof (free with sb_proof_free). */
+int sb_group_prove(sb_group* g, const sb_params* p, const void* local_trace, int on_device, const uint64_t* public_inputs,
+                   uint32_t flags, sb_proof** out);
+/* Wall milliseconds this rank spent in the phases of the last sb_group_prove ("commit", "quotient", "openings",
+ * "combine", "query_rows"; includes waiting for peers); "fused" = 1 if K1 stored into peer memory.  <0 if unknown. */
+float sb_group_phase_ms(const sb_group* g, const char* phase);
 
 /* The host-side transcript permutation (plonky2 Challenger, run between kernels): variant 0 = portable scalar,
  * 1 = AVX2, 2 = AVX-512; returns 1 if that variant ran, 0 if the CPU lacks the extension.  Parity-test hook. */

@@ -1,5 +1,7 @@
 // Links libstarkyb200.so (built by `make -C starky_bls12_381_b200/csrc`).  STARKYB200_LIB_DIR overrides the location.
 fn main() {
+    println!("cargo:rerun-if-env-changed=CARGO_FEATURE_GPU");
+    if std::env::var("CARGO_FEATURE_GPU").is_err() { return; }   // pure-Rust build: nothing to link
     let dir = std::env::var("STARKYB200_LIB_DIR").unwrap_or_else(|_| {
         format!("{}/../../starky_bls12_381_b200", std::env::var("CARGO_MANIFEST_DIR").unwrap())
     });

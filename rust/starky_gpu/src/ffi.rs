@@ -19,7 +19,7 @@ pub struct sb_params {
 }
 
 #[repr(C)]
-#[derive(Clone, Copy)]
+#[derive(Clone, Copy, Default)]
 pub struct sb_proof_layout {
     pub log_n: u32, pub log_lde: u32, pub n_cols: u32, pub n_quotient_polys: u32, pub n_public_inputs: u32,
     pub cap_len: u32, pub n_fri_rounds: u32, pub final_poly_len: u32, pub n_queries: u32, pub arity_bits: u32,
@@ -54,6 +54,7 @@ pub struct sb_shard_hooks {
     pub query_rows: Option<unsafe extern "C" fn(user: *mut c_void, positions: *const u32, count: u32, d_rows_out: *mut u64) -> c_int>,
 }
 
+#[cfg(feature = "gpu")]
 extern "C" {
     pub fn sb_init(devices: *const c_int, n_devices: c_int, out: *mut *mut sb_ctx) -> c_int;
     pub fn sb_destroy(ctx: *mut sb_ctx);
@@ -80,4 +81,34 @@ extern "C" {
                                   alpha: *const u64, first_col: u32, d_out: *mut u64) -> c_int;
     pub fn sb_fri_step_path_len(l: *const sb_proof_layout, round: u32) -> u32;
     pub fn sb_fri_step_offset(l: *const sb_proof_layout, round: u32) -> u64;
+    pub fn sb_proof_layout_for(p: *const sb_params, out: *mut sb_proof_layout) -> c_int;
+    // proof wire formats (include/starky_b200.h: enum sb_wire_format); host code, no GPU needed
+    pub fn sb_proof_serialize(proof: *const sb_proof, p: *const sb_params, format: c_int, buf: *mut c_void, cap: usize,
+                              len_out: *mut usize) -> c_int;
+    pub fn sb_proof_deserialize(buf: *const c_void, len: usize, format: c_int, p: *const sb_params,
+                                params_out: *mut sb_params, out: *mut *mut sb_proof) -> c_int;
+    // multi-GPU groups, one process per GPU (a single process uses sb_init with several devices: GpuProver::new_multi)
+    pub fn sb_group_unique_id(id: *mut u8) -> c_int;
+    pub fn sb_group_init_rank(ctx: *mut sb_ctx, rank: c_int, world: c_int, id: *const u8, out: *mut *mut sb_group) -> c_int;
+    pub fn sb_group_destroy(g: *mut sb_group);
+    pub fn sb_group_column_slice(g: *const sb_group, p: *const sb_params, first_col: *mut u32, n_cols_local: *mut u32) -> c_int;
+    pub fn sb_group_prove(g: *mut sb_group, p: *const sb_params, local_trace: *const c_void, on_device: c_int,
+                          public_inputs: *const u64, flags: u32, out: *mut *mut sb_proof) -> c_int;
+    // the seven proofs of one BLS verification (aggregate_proof.rs:279-370) through one call
+    pub fn sb_prove_batch(ctxs: *const *mut sb_ctx, n_ctx: c_int, jobs: *mut sb_job, n_jobs: c_int) -> c_int;
+}
+
+#[repr(C)]
+pub struct sb_group { _private: [u8; 0] }
+
+/// Binary-identical to `sb_job` (include/starky_b200.h).
+#[repr(C)]
+pub struct sb_job {
+    pub params: sb_params,
+    pub trace: *const c_void,
+    pub layout: c_int,
+    pub public_inputs: *const u64,
+    pub proof: *mut sb_proof,
+    pub rc: c_int,
+    pub ms: f32,
 }

@@ -4,7 +4,13 @@
 //! Same signature, specialised to F = GoldilocksField, C = PoseidonGoldilocksConfig, D = 2.  The stark is identified to
 //! the C side by `GpuStark::STARK_ID` (the library holds a pre-compiled constraint program per stark; it cannot call
 //! back into `eval_packed_generic`).  SOURCE ONLY in this repository: no Rust toolchain in the build image.
+//!
+//! Cargo feature `gpu` (default): links libstarkyb200.so and provides `GpuProver` / `prove`.  Without it
+//! (`--no-default-features`) the crate is pure Rust -- `layout`, `wire`, `unpack_words` -- so that
+//! `cargo test --no-default-features` can feed a serialized GPU proof to the reference's verifier on a box without CUDA.
 pub mod ffi;
+pub mod layout;
+pub mod wire;
 
 use anyhow::{anyhow, Result};
 use plonky2::field::extension::quadratic::QuadraticExtension;
@@ -33,22 +39,36 @@ pub trait GpuStark: Stark<F, D> {
 }
 
 /// One GPU context; reuse it across the proofs of a signature verification (device buffers are grow-only).
+#[cfg(feature = "gpu")]
 pub struct GpuProver { ctx: *mut ffi::sb_ctx }
+#[cfg(feature = "gpu")]
 unsafe impl Send for GpuProver {}
 
+#[cfg(feature = "gpu")]
 impl GpuProver {
     pub fn new(device: i32) -> Result<Self> {
+        Self::new_multi(&[device])
+    }
+    /// One context over several GPUs of the box: `prove` then shards every trace over them inside the library
+    /// (column-sharded LDE storing into the owners' row buffers over NVLink, row-sharded leaf hashing and quotient;
+    /// include/starky_b200.h "multi-GPU groups").  The number of devices must be a power of two.
+    pub fn new_multi(devices: &[i32]) -> Result<Self> {
         let mut ctx = std::ptr::null_mut();
-        let rc = unsafe { ffi::sb_init(&device, 1, &mut ctx) };
-        if rc != ffi::SB_OK { return Err(anyhow!("sb_init failed: {rc}")); }
+        let rc = unsafe { ffi::sb_init(devices.as_ptr(), devices.len() as i32, &mut ctx) };
+        if rc != ffi::SB_OK {
+            let msg = unsafe { std::ffi::CStr::from_ptr(ffi::sb_last_error(std::ptr::null_mut())).to_string_lossy().into_owned() };
+            return Err(anyhow!("sb_init failed ({rc}): {msg}"));
+        }
         Ok(Self { ctx })
     }
-    fn last_error(&self) -> String {
+    pub fn last_error(&self) -> String {
         unsafe { std::ffi::CStr::from_ptr(ffi::sb_last_error(self.ctx)).to_string_lossy().into_owned() }
     }
 }
+#[cfg(feature = "gpu")]
 impl Drop for GpuProver { fn drop(&mut self) { unsafe { ffi::sb_destroy(self.ctx) } } }
 
+#[cfg(feature = "gpu")]
 fn params_for<S: GpuStark>(stark: &S, config: &StarkConfig, n_pis: usize) -> ffi::sb_params {
     let mut p = ffi::sb_params::default();
     let log_n = stark.num_rows().trailing_zeros();
@@ -66,6 +86,7 @@ fn params_for<S: GpuStark>(stark: &S, config: &StarkConfig, n_pis: usize) -> ffi
 }
 
 /// `starky::prover::prove` on the GPU.  `_timing` is accepted for signature compatibility.
+#[cfg(feature = "gpu")]
 pub fn prove<S: GpuStark>(
     gpu: &mut GpuProver, stark: S, config: &StarkConfig, trace_poly_values: Vec<PolynomialValues<F>>,
     public_inputs: &[F], _timing: &mut TimingTree,
@@ -84,13 +105,14 @@ pub fn prove<S: GpuStark>(
         ffi::SB_EQUOTIENT_NOT_DIVISIBLE => panic!("{}", gpu.last_error()),
         _ => return Err(anyhow!("{}", gpu.last_error())),
     }
-    let proof = unsafe { unpack(&*out, public_inputs) };
+    let proof = unsafe { unpack(&*out) };
     unsafe { ffi::sb_proof_free(out) };
     Ok(proof)
 }
 
 /// `prove` from the row-major `Vec<[F; COLUMNS]>` that `generate_trace` returns: skips
 /// `trace_rows_to_poly_values` (aggregate_proof.rs:57,104,137,168,211), the transpose runs on the device.
+#[cfg(feature = "gpu")]
 pub fn prove_from_rows<S: GpuStark, const COLUMNS: usize>(
     gpu: &mut GpuProver, stark: S, config: &StarkConfig, rows: &[[F; COLUMNS]], public_inputs: &[F],
 ) -> Result<StarkProofWithPublicInputs<F, C, D>> {
@@ -101,14 +123,20 @@ pub fn prove_from_rows<S: GpuStark, const COLUMNS: usize>(
         ffi::sb_prove(gpu.ctx, &p, rows.as_ptr() as *const _, ffi::SB_TRACE_ROWMAJOR_U64, pis.as_ptr(), &mut out)
     };
     if rc != ffi::SB_OK { return Err(anyhow!("{}", gpu.last_error())); }
-    let proof = unsafe { unpack(&*out, public_inputs) };
+    let proof = unsafe { unpack(&*out) };
     unsafe { ffi::sb_proof_free(out) };
     Ok(proof)
 }
 
-unsafe fn unpack(pr: &ffi::sb_proof, public_inputs: &[F]) -> StarkProofWithPublicInputs<F, C, D> {
-    let l = &pr.layout;
-    let w = std::slice::from_raw_parts(pr.words, l.total_words as usize);
+#[cfg(feature = "gpu")]
+unsafe fn unpack(pr: &ffi::sb_proof) -> StarkProofWithPublicInputs<F, C, D> {
+    unpack_words(&pr.layout, std::slice::from_raw_parts(pr.words, pr.layout.total_words as usize))
+}
+
+/// The flat POD of include/starky_b200.h (layout `l`, words `w`) as the struct the reference's verifier and recursion
+/// circuit take.  Pure Rust: also used on proofs read from a file (wire.rs).
+pub fn unpack_words(l: &ffi::sb_proof_layout, w: &[u64]) -> StarkProofWithPublicInputs<F, C, D> {
+    assert_eq!(w.len() as u64, l.total_words);
     let f = |i: usize| F::from_canonical_u64(w[i]);
     let fe = |i: usize| FE::from([f(i), f(i + 1)]);
     let cap = |off: usize| MerkleCap::<F, PoseidonHash>(
@@ -132,9 +160,9 @@ unsafe fn unpack(pr: &ffi::sb_proof, public_inputs: &[F]) -> StarkProofWithPubli
             ((0..nq).map(|i| f(b + l.q_off_quot_leaf as usize + i)).collect(), path(b + l.q_off_quot_path as usize, tl)),
         ];
         let steps = (0..l.n_fri_rounds).map(|r| {
-            let o = b + ffi::sb_fri_step_offset(l, r) as usize;
+            let o = b + layout::fri_step_offset(l, r) as usize;
             FriQueryStep { evals: (0..arity).map(|i| fe(o + 2 * i)).collect(),
-                           merkle_proof: path(o + 2 * arity, ffi::sb_fri_step_path_len(l, r) as usize) }
+                           merkle_proof: path(o + 2 * arity, layout::fri_step_path_len(l, r) as usize) }
         }).collect();
         FriQueryRound { initial_trees_proof: FriInitialTreeProof { evals_proofs }, steps }
     }).collect();
@@ -147,6 +175,6 @@ unsafe fn unpack(pr: &ffi::sb_proof, public_inputs: &[F]) -> StarkProofWithPubli
     StarkProofWithPublicInputs {
         proof: StarkProof { trace_cap: cap(l.off_trace_cap as usize), permutation_zs_cap: None,
                             quotient_polys_cap: cap(l.off_quotient_cap as usize), openings, opening_proof },
-        public_inputs: public_inputs.to_vec(),
+        public_inputs: (0..l.n_public_inputs as usize).map(|i| f(l.off_public_inputs as usize + i)).collect(),
     }
 }

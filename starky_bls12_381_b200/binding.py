@@ -124,6 +124,23 @@ def lib():
         L.sb_combine_cols_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                              C.c_void_p]
         L.sb_memcpy_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.sb_proof_serialize.argtypes = [C.POINTER(_CProof), C.POINTER(Params), C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.sb_proof_deserialize.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Params), C.POINTER(Params),
+                                           C.POINTER(C.POINTER(_CProof))]
+        L.sb_proof_from_words.argtypes = [C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.POINTER(_CProof))]
+        L.sb_group_unique_id.argtypes = [C.c_void_p]
+        L.sb_group_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.sb_group_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+        L.sb_group_destroy.argtypes = [C.c_void_p]
+        L.sb_group_rank.argtypes = [C.c_void_p]
+        L.sb_group_size.argtypes = [C.c_void_p]
+        L.sb_shard_columns.argtypes = [C.POINTER(Params), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_uint32)]
+        L.sb_group_column_slice.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.sb_group_prove.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,
+                                     C.POINTER(C.POINTER(_CProof))]
+        L.sb_group_phase_ms.argtypes = [C.c_void_p, C.c_char_p]
+        L.sb_group_phase_ms.restype = C.c_float
         _LIB = L
     return _LIB
 
@@ -149,6 +166,41 @@ def _u64(a):
     return np.ascontiguousarray(a, dtype=np.uint64)
 
 
+class WireFormat:
+    POD, PLONKY2_BUFFER, SERDE_JSON = 0, 1, 2
+
+
+def serialize_words(p, words, fmt):
+    """sb_proof_serialize of the proof whose POD words are `words` (layout of `p`) -> bytes.  Host only."""
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    cp = C.POINTER(_CProof)()
+    rc = lib().sb_proof_from_words(C.byref(p), _ptr(w), w.size, C.byref(cp))
+    if rc:
+        raise SbError(rc, lib().sb_last_error(None).decode())
+    try:
+        n = C.c_size_t()
+        rc = lib().sb_proof_serialize(cp, C.byref(p), fmt, None, 0, C.byref(n))
+        if rc:
+            raise SbError(rc, lib().sb_last_error(None).decode())
+        buf = (C.c_ubyte * n.value)()
+        rc = lib().sb_proof_serialize(cp, C.byref(p), fmt, buf, n.value, C.byref(n))
+        if rc:
+            raise SbError(rc, lib().sb_last_error(None).decode())
+        return bytes(buf)
+    finally:
+        lib().sb_proof_free(cp)
+
+
+def deserialize_words(data, fmt, p=None):
+    """sb_proof_deserialize -> (Params of the image, POD words)."""
+    cp = C.POINTER(_CProof)()
+    q = Params()
+    rc = lib().sb_proof_deserialize(data, len(data), fmt, C.byref(p) if p is not None else None, C.byref(q), C.byref(cp))
+    if rc:
+        raise SbError(rc, lib().sb_last_error(None).decode())
+    return q, Proof(cp).words
+
+
 class Proof:
     """Owns one sb_proof; `words` is a numpy view of the flat POD (copied out on construction)."""
 
@@ -171,12 +223,14 @@ class Context:
     """One sb_ctx: one GPU, one stream, resident device buffers reused across proofs.  Not re-entrant."""
 
     def __init__(self, device=None):
+        """device: None (current device), an index, or a list of indices (one ctx over several GPUs: prove() shards)."""
         self._h = C.c_void_p()
         if device is None:
             rc = lib().sb_init(None, 0, C.byref(self._h))
         else:
-            arr = (C.c_int * 1)(int(device))
-            rc = lib().sb_init(arr, 1, C.byref(self._h))
+            devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+            arr = (C.c_int * len(devs))(*devs)
+            rc = lib().sb_init(arr, len(devs), C.byref(self._h))
         if rc:
             raise SbError(rc, lib().sb_last_error(None).decode())
 

@@ -64,14 +64,17 @@ int sb_init(const int* devices, int n_devices, sb_ctx** out) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
   ctx->sm_count = prop.multiProcessorCount;
   CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  // several devices: one rank context per device behind this ctx; sb_prove shards the trace over them (group.cu)
+  if (devices && n_devices > 1) multi_init(ctx, devices, n_devices);
   *out = ctx;
   return SB_OK;
   }
-  catch (const SbError& e) { int rc = sb_fail(nullptr, e); delete ctx; return rc; }
+  catch (const SbError& e) { int rc = sb_fail(nullptr, e); if (ctx->stream) cudaStreamDestroy(ctx->stream); delete ctx; return rc; }
 }
 
 void sb_destroy(sb_ctx* ctx) {
   if (!ctx) return;
+  multi_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->tw) { kv.second.fwd.release(); kv.second.inv.release(); }

@@ -51,6 +51,7 @@ struct Twiddles {
 };
 
 struct AirProgram;  // quotient.cu
+struct sb_multi;    // group.cu: the per-device rank contexts of a multi-GPU ctx
 
 struct StageTimer {
   cudaEvent_t a = nullptr, b = nullptr;
@@ -85,6 +86,7 @@ struct sb_ctx {
   DevBuf weights;      // alpha powers
   DevBuf scratch0, scratch1, scratch2, scratch3, peer_tab;
   void* pinned = nullptr; size_t pinned_cap = 0;
+  sb_multi* multi = nullptr;   // sb_init(devices, n > 1): one rank context per device behind this ctx (group.cu)
 };
 
 const Twiddles& sb_twiddles(sb_ctx* ctx, unsigned log_size);

@@ -4,8 +4,11 @@
 // polynomials and the final proof cross PCIe.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <map>
+#include <set>
 
 #include "poseidon.cuh"
 #include "prover.cuh"
@@ -415,6 +418,7 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
 static std::mutex g_pool_mu;
 static std::vector<std::pair<size_t, void*>> g_pool;
 static std::map<void*, size_t> g_pinned_cap;     // capacity of every buffer handed out
+static std::set<void*> g_unpinned;               // buffers that came from malloc (no CUDA device in this process)
 static void* pinned_take(size_t bytes, size_t* got) {
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -430,7 +434,14 @@ static void* pinned_take(size_t bytes, size_t* got) {
   }
   void* p = nullptr;
   cudaError_t e = cudaMallocHost(&p, bytes);
-  if (e != cudaSuccess) SB_THROW(SB_ENOMEM, "cudaMallocHost(proof, %zu bytes): %s", bytes, cudaGetErrorString(e));
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+    // host-only use of the library (sb_proof_deserialize / sb_proof_from_words on a box without a GPU): pageable memory
+    cudaGetLastError();
+    p = malloc(bytes);
+    if (!p) SB_THROW(SB_ENOMEM, "malloc(proof, %zu bytes) failed", bytes);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_unpinned.insert(p);
+  } else if (e != cudaSuccess) SB_THROW(SB_ENOMEM, "cudaMallocHost(proof, %zu bytes): %s", bytes, cudaGetErrorString(e));
   *got = bytes;
   return p;
 }
@@ -445,6 +456,7 @@ static void pinned_give(void* p, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
   auto it = g_pinned_cap.find(p);
   if (it != g_pinned_cap.end()) { bytes = it->second; g_pinned_cap.erase(it); }
+  if (g_unpinned.erase(p)) { free(p); return; }
   if (g_pool.size() >= 16) {
     size_t small = 0;
     for (size_t i = 1; i < g_pool.size(); i++) if (g_pool[i].first < g_pool[small].first) small = i;
@@ -460,6 +472,17 @@ static void quiesce(sb_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
 }
 
+// an empty proof object of the right shape (wire.cu: deserialisation)
+sb_proof* proof_alloc(const sb_params& p) {
+  sb_proof* proof = new sb_proof();
+  memset(proof, 0, sizeof(*proof));
+  try {
+    proof->layout = proof_layout(p);
+    proof->words = (u64*)pinned_take(8ull * proof->layout.total_words);
+  } catch (...) { delete proof; throw; }
+  return proof;
+}
+
 extern "C" {
 
 int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, const uint64_t* public_inputs, sb_proof** out) {
@@ -468,6 +491,7 @@ int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, con
   try {
     CUDA_CHECK(cudaSetDevice(ctx->device));
     check_params(p);
+    if (ctx->multi) return multi_prove(ctx, p, trace, layout, public_inputs, out);
     proof = new sb_proof();
     memset(proof, 0, sizeof(*proof));
     proof->layout = proof_layout(*p);

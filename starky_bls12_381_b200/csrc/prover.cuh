@@ -22,3 +22,11 @@ void air_release_all(sb_ctx* ctx);
 
 // fri.cu
 void sb_bitrev_permute_device(sb_ctx* ctx, const u64* d_in, u64* d_out, unsigned log_size, uint32_t count);
+
+// prover.cu
+sb_proof* proof_alloc(const sb_params& p);
+
+// group.cu
+void multi_init(sb_ctx* ctx, const int* devices, int n);
+void multi_destroy(sb_ctx* ctx);
+int multi_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout, const uint64_t* public_inputs, sb_proof** out);

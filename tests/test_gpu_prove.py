@@ -104,7 +104,8 @@ def test_reference_constraint_programs_quotient_parity(ctx, name, log_n):
         assert np.array_equal(got, want), (name, full)
 
 
-@pytest.mark.parametrize("name,log_n", [("fp12_mul", 4), ("miller_loop", 6), ("pairing_precomp", 5), ("ecc_agg", 7)])
+@pytest.mark.parametrize("name,log_n", [("fp12_mul", 4), ("miller_loop", 6), ("pairing_precomp", 5), ("ecc_agg", 7), ("final_exp", 5),
+                                        ("final_exp", 8)])
 def test_reference_starks_full_proof_parity_on_random_traces(ctx, name, log_n):
     info = sb.STARKS[name]
     flat = airfiles.air_path(name, "air")

@@ -1,8 +1,9 @@
 """GPU: the reference's five starks at the sizes the reference instantiates them with, on VALID
 traces from the witness generators: sb_prove through the C ABI WITHOUT SB_FLAG_ALLOW_INVALID_TRACE (the quotient must
 divide), and the oracle's independent verifier (restatement of starky::verifier::verify_stark_proof) must accept the
-GPU's proof and reject a tampered one.  FP12Mul and PairingPrecomp are additionally compared word for word with the
-oracle prover's proof of the same trace."""
+GPU's proof and reject a tampered one.  All five -- including the full-size MillerLoop 97330 x 1024 (the sp leaf sponge)
+and FinalExp 73527 x 8192 (the dp throughput leaf sponge) -- are additionally compared word for word with the oracle
+prover's proof of the same trace (one CPU proof each: the two large ones are marked slow, ~20 s and a few minutes)."""
 import numpy as np
 import pytest
 
@@ -38,7 +39,8 @@ def make(name, rng):
 
 
 @pytest.mark.parametrize("name,compare", [("fp12_mul", True), ("pairing_precomp", True), ("ecc_agg", True),
-                                          ("miller_loop", False), ("final_exp", False)])
+                                          pytest.param("miller_loop", True, marks=pytest.mark.slow),
+                                          pytest.param("final_exp", True, marks=pytest.mark.slow)])
 def test_valid_trace_proof_verifies(ctx, name, compare):
     info = sb.STARKS[name]
     rng = np.random.default_rng(0xB2002000 + info.stark_id)
@@ -59,6 +61,7 @@ def test_valid_trace_proof_verifies(ctx, name, compare):
         bad[off] = (int(bad[off]) + 1) % O.P
         assert O.verify(flat, op, bad) != 0, off
     if compare:
+        O.lib().orc_set_num_threads(__import__("os").cpu_count() or 1)
         rc, want = O.prove(flat, op, trace, pis)
         assert rc == 0, O.err()
         assert np.array_equal(proof.words, want)
