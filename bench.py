@@ -5,17 +5,18 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full proof (sb_prove: trace LDE -> Poseidon Merkle -> quotient -> FRI -> proof in host memory) of one
-synthetic trace of the workload stark (default MillerLoopStark 97330 x 1024, BASELINE configs[2]).
+synthetic trace of the workload stark (default FinalExponentiateStark 73527 x 8192, BASELINE configs[3]: the heaviest of
+the reference's proofs -- 92 s of its ~2 min on 32 vCPU -- and the shape whose leaf hashing and quotient shard by rows).
   N = 1  value : ms per proof, trace already resident in HBM when the timed region starts (DEVICE_COLMAJOR_U64)
          e2e   : ms per proof through the plugin call with the trace in pinned HOST memory (H2D of the trace and D2H of
-                 the proof inside); `e2e_pageable_cols` is the same from 97 330 separately allocated pageable columns,
+                 the proof inside); `e2e_pageable_cols` is the same from 73 527 separately allocated pageable columns,
                  the Vec<PolynomialValues<F>> the reference hands to prove() (aggregate_proof.rs:57-59)
-         also  : FinalExponentiateStark 73527 x 8192 (BASELINE configs[3]) with its own value / e2e / roofline / CPU sample
+         also  : MillerLoopStark 97330 x 1024 (BASELINE configs[2]) with its own value / e2e / roofline / full CPU proof
   N > 1  value : ms of ONE proof of the same stark with the trace SHARDED over the N GPUs (column-sharded LDE -> NVLink
                  exchange -> row-sharded leaf hashing + quotient -> small collectives): strong scaling.
-                 `replicas` (one independent proof per GPU, weak) and the FinalExp-shaped sharded proof are extras.
+                 `replicas` (one independent proof per GPU, weak) and the sharded MillerLoop proof are extras.
   --impl reference : the CPU restatement of the reference's prover (oracle/, all host threads) on the same stark; each
-                 step is a bounded sample (the same AIR and all columns on 1/8 of the rows, time x 8).
+                 step is a bounded sample (the same AIR and all columns on 1/32 of the rows, time x 32).
 """
 import argparse
 import ctypes
@@ -44,7 +45,7 @@ WORKLOADS = {
 K_CONSTRAINTS = {"fp12_mul": 82560, "pairing_precomp": 113634, "miller_loop": 145574, "final_exp": 360800, "ecc_agg": 20013}
 # rows of the CPU sample: the same AIR and all columns on 2^-shift of the rows, time x 2^shift (leaf hashing, quotient
 # and openings are linear in the rows; the NTTs lose a log factor, so the scaled figure slightly favours the CPU)
-CPU_SAMPLE_SHIFT = {"fp12_mul": 0, "pairing_precomp": 2, "miller_loop": 3, "final_exp": 4, "ecc_agg": 2}
+CPU_SAMPLE_SHIFT = {"fp12_mul": 0, "pairing_precomp": 2, "miller_loop": 3, "final_exp": 5, "ecc_agg": 2}
 
 
 def config_for(stark, world):
@@ -136,7 +137,7 @@ def oracle_all_threads():
     return O, int(O.lib().orc_num_threads())
 
 
-def cpu_sample(O, sb, stark, seed, shift=None):
+def cpu_sample(O, sb, stark, seed, shift=None, check_ctx=None):
     """One proof by the CPU port of the same AIR and all columns on num_rows >> shift rows.  Returns (ms scaled to the
     full height, description)."""
     from starky_bls12_381_b200 import airfiles
@@ -150,12 +151,34 @@ def cpu_sample(O, sb, stark, seed, shift=None):
     p = O.make_params(stark_id=info.stark_id, log_n=rows.bit_length() - 1, n_cols=info.columns, n_pis=info.public_inputs,
                       degree=info.constraint_degree, rate_bits=info.rate_bits, flags=1)
     t0 = time.perf_counter()
-    rc, _ = O.prove(flat, p, trace, pis)
+    rc, words = O.prove(flat, p, trace, pis)
     dt = time.perf_counter() - t0
     assert rc == 0, O.err()
     what = ("one full proof" if shift == 0 else
             "one proof of the same AIR and all %d columns on %d of the %d rows, time x %d" % (info.columns, rows, info.num_rows, 1 << shift))
+    if check_ctx is not None:          # the GPU path on the very same sample must give the very same proof
+        gp = sb.standard_params(info.stark_id, rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
+        same = bool(np.array_equal(check_ctx.prove(gp, trace, pis).words, words))
+        return 1e3 * dt * (1 << shift), what, same
     return 1e3 * dt * (1 << shift), what
+
+
+def cpu_baseline_for(ctx, sb, stark, p, trace, pis, gpu_proof):
+    """cpu_baseline block of one stark at N = 1: the CPU port with all host threads.  Starks whose whole proof fits the time
+    budget (everything but FinalExp: <= ~20 s) are proved in full on the SAME trace and compared word for word with the
+    GPU's proof; FinalExp (minutes on CPU) is sampled on 1/32 of the rows, and the GPU proves that same sample."""
+    O, cores = oracle_all_threads()
+    from starky_bls12_381_b200 import airfiles
+    if stark != "final_exp":
+        op = O.Params.from_buffer_copy(bytes(p))
+        t0 = time.perf_counter()
+        rc, words = O.prove(airfiles.air_path(stark, "air"), op, trace, pis)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        return {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port",
+                "sample": "one full proof of the same trace (whole workload, no scaling)",
+                "proof_bit_identical_to_gpu": bool(rc == 0 and np.array_equal(words, gpu_proof.words))}
+    ms, what, same = cpu_sample(O, sb, stark, 0xB2500000 + sb.STARKS[stark].stark_id, check_ctx=ctx)
+    return {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": what, "proof_bit_identical_to_gpu_on_the_sample": same}
 
 
 def run_reference(args, rank, world):
@@ -288,57 +311,34 @@ def full_set_assignment_of(names, world):
 
 
 def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
-    """Proves `names` on this rank's GPU, end to end from pinned host memory, with len(contexts) proofs in flight (one host
-    thread per context, work queue in cost order).  Returns (seconds max over ranks, per-proof ms)."""
+    """Proves `names` on this rank's GPU, end to end from pinned host memory, through sb_prove_batch: the library's scheduler
+    (internal host threads, one per context) runs the latency-bound proofs up to len(contexts) in flight and gives the
+    throughput-bound ones the GPU to themselves.  Returns (seconds max over ranks, per-proof ms)."""
     import torch
-    jobs = []
+    from starky_bls12_381_b200.binding import prove_batch
+    jobs, keep = [], []
     for i, name in enumerate(names):
         info = sb.STARKS[name]
         trace, pis = synthetic(info, 0xB2300000 + 16 * rank + i)
         host = torch.from_numpy(trace.view(np.int64)).pin_memory()
         del trace
         p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-        jobs.append((name, p, host, pis))
-    lock, per = threading.Lock(), []
-    # Phase A: the latency-bound proofs (few leaves: MillerLoop, PairingPrecomp, FP12Mul -- the leaf sponge is a long
-    # sequential chain, the host transcript is a large share) up to four in flight, so that the transcript of one overlaps the
-    # kernels of the other; phase B: the throughput-bound ones (FinalExp, ECCAgg: 32768 leaves fill the GPU) one at a
-    # time.  Measured alternatives: FinalExp next to MillerLoop slows the latter to 937 ms (from 225); five latency-bound
-    # proofs in flight serialise on the one-block-per-SM leaf sponge (893 ms for the phase instead of ~500).
-    few = lambda j: (sb.STARKS[j[0]].num_rows << sb.STARKS[j[0]].rate_bits) <= 64 * 148
-    phases = [([j for j in jobs if few(j)], contexts), ([j for j in jobs if not few(j)], contexts[:1])]
+        keep.append(host)
+        jobs.append((p, host.data_ptr(), sb.TraceLayout.COLMAJOR_U64, pis))
+    per = []
 
     def go():
         if sharded_job is not None:
             t0 = time.perf_counter()
             sharded_job()
             per.append(("final_exp(sharded)", 1e3 * (time.perf_counter() - t0)))
-        for phase_jobs, phase_ctx in phases:
-            # job i of a phase always runs on context i % len(contexts): the warm-up pass then sizes exactly the device
-            # buffers the timed pass needs -- with a shared work queue a context can meet its largest shape for the first time
-            # inside the timed pass and pay a multi-GB cudaMalloc there
-            lanes = full_set_assignment_of([j[0] for j in phase_jobs], len(phase_ctx))     # longest-first over the contexts
-            pool = list(phase_jobs)
-            mine_jobs = []
-            for lane in lanes:
-                got = []
-                for nm in lane:
-                    i = next(i for i, j in enumerate(pool) if j[0] == nm)
-                    got.append(pool.pop(i))
-                mine_jobs.append(got)
-
-            def worker(k, c):
-                for name, p, host, pis in mine_jobs[k]:
-                    t0 = time.perf_counter()
-                    c.prove(p, host.data_ptr(), pis, sb.TraceLayout.COLMAJOR_U64)
-                    with lock:
-                        per.append((name, 1e3 * (time.perf_counter() - t0)))
-            ts = [threading.Thread(target=worker, args=(k, c)) for k, c in enumerate(phase_ctx)]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
+        if jobs:
+            for name, (res, ms) in zip(names, prove_batch(contexts, jobs)):
+                if isinstance(res, Exception):
+                    raise res
+                per.append((name, ms))
     go()                 # warm-up: buffers of every shape allocated, constraint programs bound
+    go()                 # (the scheduler may give a context another shape the second time: settle the buffer sizes)
     per.clear()
     dt, _ = timed(go, 1)
     return dt, per
@@ -361,13 +361,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--stark", default="miller_loop", choices=sorted(WORKLOADS))
+    ap.add_argument("--stark", default="final_exp", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="sharded legs: NCCL all-to-all after K1 instead of K1 storing into peer memory")
     ap.add_argument("--no-full-set", action="store_true", help="skip the 7-proof BLS set (BASELINE configs[4])")
     ap.add_argument("--no-extras", action="store_true", help="headline line only (no 'also', sharded FinalExp, in-flight, full set)")
-    ap.add_argument("--also", default="final_exp",
+    ap.add_argument("--also", default="miller_loop",
                     help="further starks measured after the headline workload (N=1: whole proofs; N>1: sharded proofs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)            # timing rules: at least three warm-up steps
@@ -421,15 +421,7 @@ def main():
         imad = ctx.measure_imad_peak()
         cpu = None
         if not args.no_cpu_baseline:
-            O, cores = oracle_all_threads()
-            from starky_bls12_381_b200 import airfiles
-            op = O.Params.from_buffer_copy(bytes(p))
-            t0 = time.perf_counter()
-            rc, words = O.prove(airfiles.air_path(args.stark, "air"), op, trace, pis)
-            cpu_ms = 1e3 * (time.perf_counter() - t0)
-            cpu = {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port",
-                   "sample": "one full proof of the same trace (whole workload, no scaling)",
-                   "proof_bit_identical_to_gpu": bool(rc == 0 and np.array_equal(words, last.words))}
+            cpu = cpu_baseline_for(ctx, sb, args.stark, p, trace, pis, last)
         del trace
         line = {
             "metric": "starky_prove_ms_per_stark", "value": m["ms"], "unit": "ms", "n_gpus": 1, "steps": args.steps,
@@ -447,16 +439,14 @@ def main():
         for name in also_names:
             def leg(name=name):
                 ai = sb.STARKS[name]
-                am, atrace, _, _, _ = measure_stark(ctx, sb, name, 2, 1, timed, 0xB2000000 + ai.stark_id, pageable_leg=False)
-                del atrace
+                am, atrace, apis, alast, ap_ = measure_stark(ctx, sb, name, 3, 3, timed, 0xB2000000 + ai.stark_id, pageable_leg=False)
                 out = {"workload": WORKLOADS[name], "value": am["ms"], "unit": "ms",
                        "e2e": {"value": am["ms_e2e"], "unit": "ms", "h2d_bytes_per_step": am["h2d_bytes"], "d2h_bytes_per_step": am["d2h_bytes"]},
                        "stage_ms": am["stage_ms"], "kernel_ms": am["kernel_ms"], "leaf_hash_mperm_s": am["leaf_hash_mperm_s"],
                        "roofline": roofline_for(name, ai, am["kernel_ms"], am["ms"], imad, hbm_peak, peak_src)}
                 if not args.no_cpu_baseline:
-                    O, cores = oracle_all_threads()
-                    ms, what = cpu_sample(O, sb, name, 0xB2500000 + ai.stark_id)
-                    out["cpu_baseline"] = {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": what}
+                    out["cpu_baseline"] = cpu_baseline_for(ctx, sb, name, ap_, atrace, apis, alast)
+                del atrace
                 return out
             leg.__name__ = "also_" + name
             also[name] = optional(leg, world)
@@ -466,11 +456,12 @@ def main():
         from starky_bls12_381_b200 import multi
         group = multi.Group.from_torch(ctx, rank, world, local_rank)       # NCCL communicator + peer row buffers inside the library
         p = sb.standard_params(info.stark_id, info.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
-        trace, pis = synthetic(info, 0xB2000000 + info.stark_id)           # same seed on every rank: one trace, sliced
+        # one trace whose column slices are drawn where they live (seed + rank): no 4.8 GB trace is replicated per rank
         c0, cg = group.column_slice(p)
-        local_host = torch.from_numpy(np.ascontiguousarray(trace[c0:c0 + cg]).view(np.int64)).pin_memory()
+        lrng = np.random.Generator(np.random.PCG64(0xB2000000 + info.stark_id + 1000 * rank))
+        local_host = torch.from_numpy(lrng.integers(0, 1 << 32, (cg, info.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
         local_dev = local_host.cuda()
-        del trace
+        pis = np.random.Generator(np.random.PCG64(0xB2000000 + info.stark_id)).integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
         fused = not args.no_fused
         res_fn = lambda: group.prove(p, local_dev.data_ptr(), pis, on_device=True, fused=fused)
         e2e_fn = lambda: group.prove(p, local_host.data_ptr(), pis, on_device=False, fused=fused)
@@ -514,7 +505,7 @@ def main():
         if extras:
             # replicas: one independent proof per GPU (the reference's seven proofs are independent), weak scaling
             def replicas():
-                rm, rtrace, _, _, _ = measure_stark(ctx, sb, args.stark, max(1, args.steps // 2), 1, timed, 0xB2000000 + info.stark_id + 1000 * rank,
+                rm, rtrace, _, _, _ = measure_stark(ctx, sb, args.stark, max(1, min(args.steps, 3)), 1, timed, 0xB2000000 + info.stark_id + 1000 * rank,
                                                     pageable_leg=False)
                 del rtrace
                 return {"ms_per_proof_per_gpu": rm["ms"], "ms_per_proof_whole_box": rm["ms"] / world, "e2e_ms_per_proof_whole_box": rm["ms_e2e"] / world,
@@ -554,7 +545,7 @@ def main():
         more = [sb.Context(local_rank) for _ in range(3)]
 
         def in_flight_leg():
-            hinfo = sb.STARKS[args.stark]
+            hinfo = sb.STARKS["miller_loop"]            # the latency-bound shape: FinalExp fills the GPU on its own
             hp = sb.standard_params(hinfo.stark_id, hinfo.num_rows.bit_length() - 1, flags=sb.Flags.ALLOW_INVALID_TRACE)
             htrace, hpis = synthetic(hinfo, 0xB2000000 + hinfo.stark_id + 1000 * rank)
             hhost = torch.from_numpy(htrace.view(np.int64)).pin_memory()
@@ -577,7 +568,7 @@ def main():
                 return run
             d2, _ = timed(run_with([ctx, more[0]]), 1)
             d4, _ = timed(run_with([ctx] + more), 1)
-            return {"2": {"ms_per_proof": 1e3 * d2 / (2 * k) / world}, "4": {"ms_per_proof": 1e3 * d4 / (4 * k) / world},
+            return {"workload": WORKLOADS["miller_loop"], "2": {"ms_per_proof": 1e3 * d2 / (2 * k) / world}, "4": {"ms_per_proof": 1e3 * d4 / (4 * k) / world},
                     "note": "k contexts per GPU, one host thread each, end to end from pinned host memory, every GPU busy: the "
                             "latency-bound leaf sponge and the sequential host transcript of one proof overlap the kernels of the others"}
         inflight = optional(in_flight_leg, world)

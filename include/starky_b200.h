@@ -138,6 +138,24 @@ int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout,
              const uint64_t* public_inputs, sb_proof** out);
 void sb_proof_free(sb_proof* proof);
 
+/* ---- the proofs of one job list through one call.  The reference proves the seven starky proofs of one BLS
+ *      signature verification one after the other (aggregate_proof.rs:279-370: 2 x PairingPrecomp, 2 x MillerLoop,
+ *      FP12Mul, FinalExp, ECCAgg); they are independent.  sb_prove_batch runs the jobs on the given contexts (any mix of
+ *      devices, several contexts per device allowed, multi-device contexts allowed), one internal host thread per context,
+ *      longest job first: few-leaf (latency-bound) proofs share a GPU up to its number of contexts, many-leaf
+ *      (throughput-bound) proofs get an idle GPU to themselves.  On return jobs[i].proof / rc / ms are filled in job order;
+ *      the return value is the first failing job's code (0 if all proofs were produced). ---- */
+typedef struct sb_job {
+  sb_params params;
+  const void* trace;             /* as for sb_prove */
+  int layout;                    /* enum sb_trace_layout */
+  const uint64_t* public_inputs;
+  sb_proof* proof;               /* out: free with sb_proof_free */
+  int rc;                        /* out: SB_OK or the error of this job */
+  float ms;                      /* out: wall milliseconds of this job's sb_prove */
+} sb_job;
+int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int n_jobs);
+
 /* ---- proof wire formats: the proof as bytes for a consumer that does not link this library -- the
  *      reference's verify_stark_proof / recursive verifier take a starky::proof::StarkProofWithPublicInputs<F, C, 2>
  *      (aggregate_proof.rs:67,113,146,177,220 and :435-439).  Host code only: works in a process without a GPU. ---- */

@@ -62,6 +62,12 @@ HOOK_COMBINE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_
 HOOK_QUERY_ROWS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p)
 
 
+class Job(C.Structure):
+    """Binary-identical to sb_job (include/starky_b200.h)."""
+    _fields_ = [("params", Params), ("trace", C.c_void_p), ("layout", C.c_int), ("public_inputs", C.c_void_p),
+                ("proof", C.POINTER(_CProof)), ("rc", C.c_int), ("ms", C.c_float)]
+
+
 class ShardHooks(C.Structure):
     """Binary-identical to sb_shard_hooks (include/starky_b200.h)."""
     _fields_ = [("user", C.c_void_p), ("commit", HOOK_COMMIT), ("quotient", HOOK_QUOTIENT), ("openings", HOOK_OPENINGS),
@@ -128,6 +134,7 @@ def lib():
         L.sb_proof_deserialize.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Params), C.POINTER(Params),
                                            C.POINTER(C.POINTER(_CProof))]
         L.sb_proof_from_words.argtypes = [C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.POINTER(_CProof))]
+        L.sb_prove_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Job), C.c_int]
         L.sb_group_unique_id.argtypes = [C.c_void_p]
         L.sb_group_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.sb_group_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
@@ -217,6 +224,30 @@ class Proof:
     def field(self, name, count):
         off = getattr(self.layout, name)
         return self.words[off:off + count]
+
+
+def prove_batch(contexts, jobs):
+    """sb_prove_batch: jobs = [(Params, trace pointer or array, layout, public inputs)], returns [(Proof or SbError, ms)] in
+    job order.  The proofs run on `contexts` with the library's scheduler (internal host threads)."""
+    n = len(jobs)
+    arr = (Job * n)()
+    keep = []
+    for i, (p, trace, layout, pis) in enumerate(jobs):
+        pis = _u64(pis)
+        keep.append((pis, trace))
+        arr[i].params = p
+        arr[i].trace = _ptr(trace)
+        arr[i].layout = layout
+        arr[i].public_inputs = _ptr(pis) if pis.size else None
+    hs = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    lib().sb_prove_batch(hs, len(contexts), arr, n)
+    out = []
+    for i in range(n):
+        if arr[i].rc:
+            out.append((SbError(arr[i].rc, "job %d failed" % i), arr[i].ms))
+        else:
+            out.append((Proof(arr[i].proof), arr[i].ms))
+    return out
 
 
 class Context:

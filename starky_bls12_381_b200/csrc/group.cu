@@ -39,7 +39,6 @@ void sb_openings_device(sb_ctx* ctx, const u64* d_coeffs, unsigned log_n, uint32
 void sb_combine_device(sb_ctx* ctx, const u64* d_coeffs, unsigned log_n, uint32_t n_polys, e2_t alpha, uint32_t j0,
                        e2_t* d_apow, e2_t* d_partial, size_t partial_capacity_elems, e2_t* d_out);
 
-#define SB_GROUP_NO_FUSED 1u
 
 // ---------------------------------------------------------------------------------------------------------
 // NCCL through dlopen: only the handful of entry points used here

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "poseidon_fast.h"
 #include "poseidon_rc.h"
 
 #if defined(__x86_64__)
@@ -229,15 +230,91 @@ __attribute__((target("avx512f,avx512dq,avx512bw,avx512vl"))) static void permut
   _mm512_mask_storeu_epi64((void*)(s + 8), 0x0F, s1);
   for (int i = 0; i < 12; i++) s[i] -= mask_of(s[i] >= P) & P;
 }
+// ---- AVX-512 full rounds + SPARSE partial rounds (poseidon_fast.h, the factorisation plonky2 ships as FAST_PARTIAL_*).
+// The 22 partial rounds of the dense form above cost a full vector MDS each although only word 0 went through the
+// S-box; in sparse form a partial round is
+//     y = x0^7 + POST[r];   x0' = 25 y + sum_i WHAT[r][i] x_i;   x_i' = x_i + VS[r][i] y
+// and with  sum_i WHAT[r+1][i] x_i' = sum_i WHAT[r+1][i] x_i + U[r+1] y  the dot product of the NEXT round is taken from
+// the values before this round's update, so the only thing on the round's dependency chain is the S-box and one
+// multiply-add (~40 cycles); the eleven multiply-adds of the update and the eleven of the look-ahead dot product run
+// beside it.  128-bit sums of products are kept as (sum of low words, sum of high words) and folded once.
+static const u64 F_FIRST[12] = POSEIDON_FAST_FIRST, F_POST[22] = POSEIDON_FAST_POST, F_INIT[121] = POSEIDON_FAST_INIT,
+                 F_WHAT[22 * 11] = POSEIDON_FAST_WHAT, F_VS[22 * 11] = POSEIDON_FAST_VS, F_U[22] = POSEIDON_FAST_U;
+
+alignas(64) static u64 VSW[22][16];      // VS[r][0..10] padded to two vectors
+static const bool vsw_ready = [] {
+  for (int r = 0; r < 22; r++)
+    for (int i = 0; i < 16; i++) VSW[r][i] = i < 11 ? F_VS[11 * r + i] : 0;
+  return true;
+}();
+// lazy -> canonical
+T512 W wcanon(W a) { return _mm512_mask_sub_epi64(a, _mm512_cmpge_epu64_mask(a, wset(P)), a, wset(P)); }
+static inline u64 add_lazy(u64 a, u64 c) { u64 v = a + c; v += mask_of(v < a) & EPS; return v; }   // lazy + any -> lazy (c <= 2^64 - 2^32)
+// sum_i c[i] * x[i] (n <= 16 terms) -> lazy u64
+static inline u64 dot_lazy(const u64* c, const u64* x, int n) {
+  u128 lo = 0, hi = 0;
+  for (int i = 0; i < n; i++) { u128 m = (u128)c[i] * x[i]; lo += (u64)m; hi += (u64)(m >> 64); }
+  // lo + hi * 2^64 with hi < 2^68:  2^64 = EPS (mod p), hi * EPS < 2^100
+  return red128(lo + hi * (u128)EPS);
+}
+
+__attribute__((target("avx512f,avx512dq,avx512bw,avx512vl"))) static void permute_avx512_sparse(u64 s[12]) {
+  W s0 = _mm512_loadu_si512((const void*)s);
+  W s1 = _mm512_maskz_loadu_epi64(0x0F, (const void*)(s + 8));
+  for (int r = 0; r < 4; r++) {
+    s0 = wadd_lazy(s0, _mm512_load_si512((const void*)RCW[r]));
+    s1 = wadd_lazy(s1, _mm512_load_si512((const void*)(RCW[r] + 8)));
+    s0 = wsbox(s0); s1 = wsbox(s1);
+    wmds(s0, s1);
+  }
+  alignas(64) u64 x[16];
+  _mm512_store_si512((void*)x, s0); _mm512_store_si512((void*)(x + 8), s1);
+  // x += FIRST;  x[1..] = INIT . x[1..]
+  u64 t[12];
+  for (int i = 0; i < 12; i++) t[i] = add_lazy(x[i], F_FIRST[i]);
+  x[0] = t[0];
+  for (int j = 0; j < 11; j++) x[j + 1] = dot_lazy(F_INIT + 11 * j, t + 1, 11);
+  // partial rounds: x0 and the dot products in scalar registers, the eleven updates x_i += VS[r][i] y as two vectors
+  // (words 1..8 and 9..11; stored after every round so that the scalar dot product of the next round can read them)
+  u64 x0 = x[0], y_prev = 0;
+  u64 A = dot_lazy(F_WHAT, x + 1, 11);                      // sum_i WHAT[0][i] x_i
+  W xa = _mm512_loadu_si512((const void*)(x + 1));
+  W xb = _mm512_maskz_loadu_epi64(0x07, (const void*)(x + 9));
+  for (int r = 0; r < 22; r++) {
+    const u64 D = r ? red128((u128)F_U[r] * y_prev + A) : A;   // sum_i WHAT[r][i] x_i(r)
+    const u64 y = add_lazy(sbox(x0), F_POST[r]);
+    const u64 A_next = r + 1 < 22 ? dot_lazy(F_WHAT + 11 * (r + 1), x + 1, 11) : 0;   // from the values BEFORE this update
+    x0 = red128((u128)25 * y + D);
+    const W yv = wset(y);
+    xa = wadd_lazy(xa, wcanon(wmul(_mm512_load_si512((const void*)VSW[r]), yv)));
+    xb = wadd_lazy(xb, wcanon(wmul(_mm512_load_si512((const void*)(VSW[r] + 8)), yv)));
+    _mm512_storeu_si512((void*)(x + 1), xa);
+    _mm512_mask_storeu_epi64((void*)(x + 9), 0x07, xb);
+    A = A_next; y_prev = y;
+  }
+  x[0] = x0;
+  s0 = _mm512_load_si512((const void*)x);
+  s1 = _mm512_maskz_load_epi64(0x0F, (const void*)(x + 8));
+  for (int r = 26; r < 30; r++) {
+    s0 = wadd_lazy(s0, _mm512_load_si512((const void*)RCW[r]));
+    s1 = wadd_lazy(s1, _mm512_load_si512((const void*)(RCW[r] + 8)));
+    s0 = wsbox(s0); s1 = wsbox(s1);
+    wmds(s0, s1);
+  }
+  _mm512_storeu_si512((void*)s, s0);
+  _mm512_mask_storeu_epi64((void*)(s + 8), 0x0F, s1);
+  for (int i = 0; i < 12; i++) s[i] -= mask_of(s[i] >= P) & P;
+}
 #endif
 
-// variant: 0 = scalar, 1 = AVX2, 2 = AVX-512 (tests compare them; returns 0 if the CPU lacks the extension)
+// variant: 0 = scalar, 1 = AVX2, 2 = AVX-512 dense, 3 = AVX-512 full rounds + sparse partial rounds (tests compare them; returns 0 if the CPU lacks the extension)
 extern "C" int sb_host_poseidon_permute_variant(u64 s[12], int variant) {
 #if defined(__x86_64__)
-  if (variant == 2) {
+  if (variant == 2 || variant == 3) {
     if (!(__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512bw") &&
           __builtin_cpu_supports("avx512vl"))) return 0;
-    permute_avx512(s); return 1;
+    if (variant == 3) permute_avx512_sparse(s); else permute_avx512(s);
+    return 1;
   }
   if (variant == 1) { if (!__builtin_cpu_supports("avx2")) return 0; permute_avx2(s); return 1; }
 #endif
@@ -248,8 +325,8 @@ extern "C" int sb_host_poseidon_permute_variant(u64 s[12], int variant) {
 void sb_host_poseidon_permute(u64 s[12]) {
 #if defined(__x86_64__)
   static const bool have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") &&
-                                  __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && cw_ready && rcw_ready;
-  if (have_avx512) { permute_avx512(s); return; }
+                                  __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && cw_ready && rcw_ready && vsw_ready;
+  if (have_avx512) { permute_avx512_sparse(s); return; }
   static const bool have_avx2 = __builtin_cpu_supports("avx2") && cv_ready;
   if (have_avx2) { permute_avx2(s); return; }
 #endif

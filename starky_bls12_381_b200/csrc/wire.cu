@@ -28,7 +28,6 @@
 
 #include "prover.cuh"
 
-enum { SB_WIRE_POD = 0, SB_WIRE_PLONKY2_BUFFER = 1, SB_WIRE_SERDE_JSON = 2 };
 
 namespace {
 

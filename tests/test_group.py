@@ -133,3 +133,38 @@ def test_one_ctx_over_several_devices_shards_inside_sb_prove():
     finally:
         one.close()
         many.close()
+
+
+@pytest.mark.gpu
+def test_prove_batch_schedules_the_seven_proofs_and_returns_them_in_job_order():
+    """sb_prove_batch: the job list of one BLS verification (aggregate_proof.rs:279-370 order), at reduced
+    heights so that both job classes occur (32768 LDE positions = throughput-bound, the others latency-bound), on three
+    contexts: every proof equals the one sb_prove gives alone; a bad job fails alone with its own code."""
+    from starky_bls12_381_b200.binding import prove_batch
+    names = ["pairing_precomp", "pairing_precomp", "miller_loop", "miller_loop", "fp12_mul", "final_exp", "ecc_agg"]
+    logs = {"pairing_precomp": 6, "miller_loop": 5, "fp12_mul": 4, "final_exp": 6, "ecc_agg": 13}
+    rng = np.random.default_rng(0xB2006000)
+    jobs, want = [], []
+    one = sb.Context(0)
+    ctxs = [sb.Context(0) for _ in range(3)]
+    try:
+        for nm in names:
+            info = sb.STARKS[nm]
+            p = sb.standard_params(info.stark_id, logs[nm], flags=sb.Flags.ALLOW_INVALID_TRACE)
+            trace = random_trace(rng, info.columns, logs[nm])
+            pis = rng.integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
+            jobs.append((p, trace, sb.TraceLayout.COLMAJOR_U64, pis))
+            want.append(one.prove(p, trace, pis).words)
+        bad = sb.standard_params(sb.StarkId.MILLER_LOOP, 5)
+        bad.n_cols = 17                                            # does not match the constraint program
+        jobs.append((bad, np.zeros((17, 32), np.uint64), sb.TraceLayout.COLMAJOR_U64, np.zeros(5064, np.uint64)))
+        for contexts in (ctxs, ctxs[:1]):
+            got = prove_batch(contexts, jobs)
+            assert len(got) == len(jobs)
+            for (res, ms), w in zip(got[:-1], want):
+                assert np.array_equal(res.words, w) and ms > 0
+            assert isinstance(got[-1][0], sb.SbError) and got[-1][0].code == -1
+    finally:
+        one.close()
+        for c in ctxs:
+            c.close()
