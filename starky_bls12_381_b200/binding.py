@@ -75,7 +75,8 @@ class ShardHooks(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libstarkyb200.so")
+    # SB_LIBRARY: another build of the same library (A/B runs of compile-time kernel variants); still no CPU fallback
+    return os.environ.get("SB_LIBRARY") or os.path.join(_HERE, "libstarkyb200.so")
 
 
 def lib():

@@ -267,6 +267,35 @@ __global__ void __launch_bounds__(LAYOUT == 2 ? 512 : 384) leaf_sponge_w12_kerne
 //   The dense 11x11 "initial" matrix of the sparse form is folded into the linear layer of full round 3 (D3ROT, K3).
 // Barrier ids: A = 1 (full rounds, 12 warps), B = 2..4, G = 5..7, F = 8..10, Y = 11..13.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b, u32 c) {
+  u32 d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// limb accumulators (each < 2^28) -> lazy u64:  a0 + a1 2^16 + a2 2^32 + a3 2^48
+__device__ __forceinline__ u64 limbs_recombine(u32 a0, u32 a1, u32 a2, u32 a3) {
+  const u64 al = (u64)a0 + ((u64)a1 << 16), ah = (u64)a2 + ((u64)a3 << 16);     // both < 2^45
+  return mds_recombine((u32)al, (u32)(al >> 32), (u32)ah, (u32)(ah >> 32));
+}
+
+// one MDS row on dp2a for a thread that holds the twelve words rotated (t[i] = word (row + i) mod 12): six word pairs x
+// four 16-bit limbs, coefficients (CIRC[2p], CIRC[2p+1]) as immediates; `diag0`: row 0 adds 8 * word 0
+__device__ __forceinline__ u64 mds_row_dp2a(const u64 (&t)[12], u64 rc, bool diag0) {
+  constexpr u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  const u32 lo = (u32)rc, hi = (u32)(rc >> 32);
+  u32 a0 = lo & 0xFFFFu, a1 = lo >> 16, a2 = hi & 0xFFFFu, a3 = hi >> 16;
+#pragma unroll
+  for (int p = 0; p < 6; p++) {
+    const u32 alo = (u32)t[2 * p], ahi = (u32)(t[2 * p] >> 32), blo = (u32)t[2 * p + 1], bhi = (u32)(t[2 * p + 1] >> 32);
+    const u32 q0 = __byte_perm(alo, blo, 0x5410), q1 = __byte_perm(alo, blo, 0x7632);
+    const u32 q2 = __byte_perm(ahi, bhi, 0x5410), q3 = __byte_perm(ahi, bhi, 0x7632);
+    const u32 b = CIRC[2 * p] | (CIRC[2 * p + 1] << 8);
+    a0 = dp2a_lo(q0, b, a0); a1 = dp2a_lo(q1, b, a1); a2 = dp2a_lo(q2, b, a2); a3 = dp2a_lo(q3, b, a3);
+    if (p == 0 && diag0) { a0 = dp2a_lo(q0, 8u, a0); a1 = dp2a_lo(q1, 8u, a1); a2 = dp2a_lo(q2, 8u, a2); a3 = dp2a_lo(q3, 8u, a3); }
+  }
+  return limbs_recombine(a0, a1, a2, a3);
+}
+
 #include <type_traits>
 
 #include "poseidon_fast.h"
@@ -335,14 +364,27 @@ __device__ long long* g_sp_trace;      // [64] clock64 stamps of block 0 / lane 
 #else
 #define SP_STAMP(i) do { } while (0)
 #endif
-__global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+// VAR (lab variants, tools/perf/poseidon_lab.cu; the product launches the one that measured fastest):
+//   bit 0  the warp that owns word 0 sits alone in its SM sub-partition: 16 warps, warps 7, 11 and 15 (the ones that would
+//          share scheduler 3 with warp 3) exit at once; its S-box chain then issues without competing for the scheduler or
+//          the half-rate IMAD.WIDE pipe
+//   bit 1  round 3's dense row (D3ROT, K3) lives in registers for the whole kernel instead of twelve indexed constant loads
+//   bit 2  full-round MDS rows on dp2a (16-bit limbs, 24 IDP.2A per row) instead of 24 IMAD.WIDE
+template <int VAR>
+__global__ void __launch_bounds__((VAR & 1) ? 512 : 416) leaf_sponge_sp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                              uint32_t n_leaves, unsigned log_block,
                                                              u64* __restrict__ digests) {
   __shared__ __align__(16) u64 xch[2][24][32];
   __shared__ __align__(16) u64 ybuf[3][32];
   __shared__ __align__(16) u64 ebuf[3][12][32];
   __shared__ __align__(16) u64 Ebuf[3][64];   // per lane: (sum of low halves, sum of high halves)
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31, warp_raw = threadIdx.x >> 5;
+  unsigned warp = warp_raw;                   // logical warp 0..12
+  if (VAR & 1) {
+    if (warp_raw == 7 || warp_raw == 11 || warp_raw == 15) return;
+    // physical 0..6 -> 0..6 (3 = word 0), 8..10 -> 7..9, 12..14 -> 10..12
+    warp = warp_raw < 7 ? warp_raw : (warp_raw < 11 ? warp_raw - 1 : warp_raw - 2);
+  }
   const bool reducer = warp == 12;
   const unsigned wid = reducer ? 0 : (warp + 9) % 12;      // the state word this warp owns
   const bool crit = !reducer && wid == 0;
@@ -355,6 +397,12 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
   const uint32_t n_chunks = (leaf_len + 7) / 8;
   if (!reducer && wid < 8 && wid < leaf_len) nx = cols[(size_t)wid * n_leaves + pos];
   unsigned xb = 0;
+  u64 d3row[12], k3v = 0;
+  if (VAR & 2) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) d3row[i] = c_fast_d3rot[12 * wid + i];
+    k3v = c_fast_k3[wid];
+  }
 
   for (uint32_t m = 0; m < n_chunks; m++) {
     if (!reducer) {
@@ -377,10 +425,13 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         u64 t[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) t[i] = xch[xb][wid + i][lane];
-        u32 al0, al1, ah0, ah1;
-        mds_row<1>(t, [&](int i) { return CIRC[i]; }, next, 0, al0, al1, ah0, ah1);
-        if (wid == 0) { mac32(al0, al1, (u32)t[0], 8u); mac32(ah0, ah1, (u32)(t[0] >> 32), 8u); }   // DIAG[0] = 8
-        s = mds_recombine(al0, al1, ah0, ah1);
+        if (VAR & 4) s = mds_row_dp2a(t, next, wid == 0);
+        else {
+          u32 al0, al1, ah0, ah1;
+          mds_row<1>(t, [&](int i) { return CIRC[i]; }, next, 0, al0, al1, ah0, ah1);
+          if (wid == 0) { mac32(al0, al1, (u32)t[0], 8u); mac32(ah0, ah1, (u32)(t[0] >> 32), 8u); }   // DIAG[0] = 8
+          s = mds_recombine(al0, al1, ah0, ah1);
+        }
         xb ^= 1;
         if (crit) SP_STAMP(52);
       };
@@ -395,9 +446,9 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         xch[xb][wid][lane] = v; xch[xb][wid + 12][lane] = v;
         named_bar_sync(1, 384);
         // twelve unreduced 128-bit products into one 192-bit accumulator, one reduction (instead of twelve)
-        Acc192 acc = {c_fast_k3[wid], 0, 0};
+        Acc192 acc = {(VAR & 2) ? k3v : c_fast_k3[wid], 0, 0};
 #pragma unroll
-        for (int i = 0; i < 12; i++) acc192_mul(acc, c_fast_d3rot[12 * wid + i], xch[xb][wid + i][lane]);
+        for (int i = 0; i < 12; i++) acc192_mul(acc, (VAR & 2) ? d3row[i] : c_fast_d3rot[12 * wid + i], xch[xb][wid + i][lane]);
         s = gl_canon(acc192_reduce(acc));
         xb ^= 1;
       }
@@ -501,10 +552,13 @@ __global__ void __launch_bounds__(416) leaf_sponge_sp_kernel(const u64* __restri
         u64 t[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) t[i] = xch[xb][wid + i][lane];
-        u32 al0, al1, ah0, ah1;
-        mds_row<1>(t, [&](int i) { return CIRC[i]; }, c_poseidon_rc[12 * (rd + 1) + wid], 0, al0, al1, ah0, ah1);
-        if (wid == 0) { mac32(al0, al1, (u32)t[0], 8u); mac32(ah0, ah1, (u32)(t[0] >> 32), 8u); }
-        s = mds_recombine(al0, al1, ah0, ah1);
+        if (VAR & 4) s = mds_row_dp2a(t, c_poseidon_rc[12 * (rd + 1) + wid], wid == 0);
+        else {
+          u32 al0, al1, ah0, ah1;
+          mds_row<1>(t, [&](int i) { return CIRC[i]; }, c_poseidon_rc[12 * (rd + 1) + wid], 0, al0, al1, ah0, ah1);
+          if (wid == 0) { mac32(al0, al1, (u32)t[0], 8u); mac32(ah0, ah1, (u32)(t[0] >> 32), 8u); }
+          s = mds_recombine(al0, al1, ah0, ah1);
+        }
         xb ^= 1;
       }
     }
@@ -626,17 +680,6 @@ __global__ void __launch_bounds__(64) leaf_sponge_st_kernel(const u64* __restric
 // < 2^27.  The pair packing (28 PRMT on the ALU pipe) is shared by the three rows a thread owns, which is why this
 // variant exists for the three-words-per-thread layout only.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b, u32 c) {
-  u32 d;
-  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-// limb accumulators (each < 2^28) -> lazy u64:  a0 + a1 2^16 + a2 2^32 + a3 2^48
-__device__ __forceinline__ u64 limbs_recombine(u32 a0, u32 a1, u32 a2, u32 a3) {
-  const u64 al = (u64)a0 + ((u64)a1 << 16), ah = (u64)a2 + ((u64)a3 << 16);     // both < 2^45
-  return mds_recombine((u32)al, (u32)(al >> 32), (u32)ah, (u32)(ah >> 32));
-}
-
 __global__ void __launch_bounds__(128) leaf_sponge_dp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                              uint32_t n_leaves, unsigned log_block,
                                                              u64* __restrict__ digests) {

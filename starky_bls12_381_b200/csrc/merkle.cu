@@ -71,7 +71,17 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
   if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
   const uint32_t groups = (n_leaves + 31) / 32;
   if (kind == 13) {
-    LAUNCH(ctx, leaf_sponge_sp_kernel, groups, 416, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+    // SB_SP_VARIANT: lab variants of the sp kernel (leafhash.cuh); 0 = the round-1 kernel
+    static const int spv = [] { const char* e = getenv("SB_SP_VARIANT"); return e ? atoi(e) : 0; }();
+    switch (spv) {
+      case 1: LAUNCH(ctx, leaf_sponge_sp_kernel<1>, groups, 512, 0, d_cols, leaf_len, n_leaves, log_block, d_digests); break;
+      case 2: LAUNCH(ctx, leaf_sponge_sp_kernel<2>, groups, 416, 0, d_cols, leaf_len, n_leaves, log_block, d_digests); break;
+      case 3: LAUNCH(ctx, leaf_sponge_sp_kernel<3>, groups, 512, 0, d_cols, leaf_len, n_leaves, log_block, d_digests); break;
+      case 4: LAUNCH(ctx, leaf_sponge_sp_kernel<4>, groups, 416, 0, d_cols, leaf_len, n_leaves, log_block, d_digests); break;
+      case 6: LAUNCH(ctx, leaf_sponge_sp_kernel<6>, groups, 416, 0, d_cols, leaf_len, n_leaves, log_block, d_digests); break;
+      case 7: LAUNCH(ctx, leaf_sponge_sp_kernel<7>, groups, 512, 0, d_cols, leaf_len, n_leaves, log_block, d_digests); break;
+      default: LAUNCH(ctx, leaf_sponge_sp_kernel<0>, groups, 416, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+    }
   } else if (kind == 12) {
     LAUNCH(ctx, (leaf_sponge_w12_kernel<0, 1>), groups, 384, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 4) {

@@ -104,6 +104,26 @@ def test_reference_constraint_programs_quotient_parity(ctx, name, log_n):
         assert np.array_equal(got, want), (name, full)
 
 
+@pytest.mark.parametrize("name,log_n", [("pairing_precomp", 4), ("ecc_agg", 6)])
+def test_word_form_interpreter_still_matches_oracle(ctx, monkeypatch, name, log_n):
+    """SB_QUOTIENT_VM=1 selects round 1's word-form interpreter instead of the run-form evaluator: both must give the oracle's
+    quotient values (the run form is what every other test in this file exercises)."""
+    monkeypatch.setenv("SB_QUOTIENT_VM", "1")
+    info = sb.STARKS[name]
+    flat = airfiles.air_path(name, "air")
+    p = sb.standard_params(info.stark_id, log_n)
+    rng = np.random.default_rng(0xB2000100 + info.stark_id)
+    trace = random_trace(rng, info.columns, log_n, full_width=True)
+    pis = rng.integers(0, 1 << 32, info.public_inputs, dtype=np.uint64)
+    alphas = rng.integers(0, 1 << 63, 2, dtype=np.uint64) % np.uint64(P)
+    ctx.lde_commit(p, trace, want_lde=False, want_digests=False)
+    got = ctx.quotient_values(p, pis, alphas)
+    want = O.quotient_values(flat, to_oracle_params(p), trace, pis, alphas)
+    assert np.array_equal(got, want)
+    monkeypatch.delenv("SB_QUOTIENT_VM")
+    assert np.array_equal(ctx.quotient_values(p, pis, alphas), want)
+
+
 @pytest.mark.parametrize("name,log_n", [("fp12_mul", 4), ("miller_loop", 6), ("pairing_precomp", 5), ("ecc_agg", 7), ("final_exp", 5),
                                         ("final_exp", 8)])
 def test_reference_starks_full_proof_parity_on_random_traces(ctx, name, log_n):

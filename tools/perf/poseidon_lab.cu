@@ -209,7 +209,7 @@ int main(int argc, char** argv) {
     CK(cudaMemset(d_tr, 0, 64 * 8));
     CK(cudaMemcpyToSymbol(g_sp_trace, &d_tr, sizeof(d_tr)));
     fill_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_cols, cells);
-    for (int rep = 0; rep < 2; rep++) leaf_sponge_sp_kernel<<<(nl + 31) / 32, 416>>>(d_cols, ll, nl, 0, d_dig);
+    for (int rep = 0; rep < 2; rep++) leaf_sponge_sp_kernel<0><<<(nl + 31) / 32, 416>>>(d_cols, ll, nl, 0, d_dig);
     CK(cudaDeviceSynchronize());
     long long h[64]; CK(cudaMemcpy(h, d_tr, sizeof(h), cudaMemcpyDeviceToHost));
     printf("perm start %lld\n", 0ll);
@@ -237,7 +237,9 @@ int main(int argc, char** argv) {
         if (wps == 43) leaf_sponge_dp_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 45) leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 101) leaf_sponge_st_kernel<<<g32, 32>>>(d_cols, ll, nl, 0, d_dig);
-        else if (wps == 130) leaf_sponge_sp_kernel<<<g32, 416>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 130) leaf_sponge_sp_kernel<0><<<g32, 416>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 131) leaf_sponge_sp_kernel<1><<<g32, 512>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 137) leaf_sponge_sp_kernel<7><<<g32, 512>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 122) leaf_sponge_w12_kernel<2><<<g32, 512>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 120) leaf_sponge_w12_kernel<0><<<g32, 384>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 12) leaf_sponge_ws_kernel<12><<<g32, 384>>>(d_cols, ll, nl, 0, d_dig);
@@ -248,7 +250,9 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
+  const bool only_sp = argc > 1 && !strcmp(argv[1], "sp");     // the latency-bound shapes and the sp variants only
   // ---- latency / throughput probes ----
+  if (!only_sp) {
   if (mul_check()) return 1;
   u64* d_out; long long* d_cyc; CK(cudaMalloc(&d_out, 1 << 20)); CK(cudaMalloc(&d_cyc, 64));
   long long cyc;
@@ -290,11 +294,13 @@ int main(int argc, char** argv) {
     }
     cudaFree(d_out); cudaFree(d_cyc);
   }
+  }
 
   // ---- leaf sponge variants ----
   struct Shape { const char* name; uint32_t n_leaves, leaf_len; };
   std::vector<Shape> shapes = {{"ML-like", 2048, 8003}, {"PP-like", 4096, 8003}, {"ECC-like", 32768, 3339}, {"FE-like", 32768, 8003},
                                {"ragged", 1000, 77}};
+  if (only_sp) shapes = {{"ML-like", 2048, 8003}, {"PP-like", 4096, 8003}, {"ragged", 1000, 77}};
   if (argc > 1 && !strcmp(argv[1], "full")) {
     shapes.push_back({"PP", 4096, 29376}); shapes.push_back({"ML", 2048, 97330}); shapes.push_back({"FE", 32768, 73527});
   }
@@ -326,6 +332,7 @@ int main(int argc, char** argv) {
       printf("    %-28s %9.3f ms  %7.1f Mperm/s  %s\n", name, t, perms / t / 1e3, ok ? "ok" : "MISMATCH");
     };
     const unsigned g32 = (sh.n_leaves + 31) / 32;
+    if (!only_sp) {
     run("ws<1>  (12 words/thread)", [&] { leaf_sponge_ws_kernel<1><<<g32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("ws<2>  (6 words/thread)", [&] { leaf_sponge_ws_kernel<2><<<g32, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("ws<3>  (4 words/thread)", [&] { leaf_sponge_ws_kernel<3><<<g32, 96>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
@@ -337,8 +344,17 @@ int main(int argc, char** argv) {
     run("ds (dp2a full + sparse partial)", [&] { leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("st (sparse, one thread per leaf, block 32)", [&] { leaf_sponge_st_kernel<<<g32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("st (sparse, one thread per leaf, block 64)", [&] { leaf_sponge_st_kernel<<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
-    run("sp (sparse partial rounds, 13 warps)", [&] { leaf_sponge_sp_kernel<<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    }
+    run("sp<0> (sparse partial rounds, 13 warps)", [&] { leaf_sponge_sp_kernel<0><<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("sp<1> word-0 warp alone on its scheduler", [&] { leaf_sponge_sp_kernel<1><<<g32, 512>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("sp<2> round-3 row in registers", [&] { leaf_sponge_sp_kernel<2><<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("sp<4> full-round rows on dp2a", [&] { leaf_sponge_sp_kernel<4><<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("sp<3> = 1 + 2", [&] { leaf_sponge_sp_kernel<3><<<g32, 512>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("sp<6> = 2 + 4", [&] { leaf_sponge_sp_kernel<6><<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("sp<7> = 1 + 2 + 4", [&] { leaf_sponge_sp_kernel<7><<<g32, 512>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    if (!only_sp)
     run("w12<0,2> (2 chains/half)", [&] { leaf_sponge_w12_kernel<0, 2><<<g32, 384>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    if (!only_sp)
     run("w12<0,3> (3 chains/half)", [&] { leaf_sponge_w12_kernel<0, 3><<<g32, 384>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     cudaFree(d_cols); cudaFree(d_ref); cudaFree(d_dig);
   }
