@@ -132,6 +132,12 @@ const char* sb_last_error(sb_ctx* ctx); /* ctx may be NULL: last error of this t
  * The five standard programs are linked into the library (csrc/air_blobs.S) and bound on first use; when $SB_AIR_DIR
  * is set, <dir>/<name>.airbin (fp12_mul, pairing_precomp, miller_loop, final_exp, ecc_agg) is read instead. */
 int sb_air_load(sb_ctx* ctx, uint32_t stark_id, const char* path);
+/* The run form the loader builds from a program image (groups reordered by column locality, bodies folded into run records,
+ * weight slots permuted; csrc/quotient.cu: translate_runs), for inspection and for the CPU test that emulates it.  Host
+ * only.  info_out[8] = {run-form words, weight slots, K, groups, runs, bodies in runs, bodies, columns}; the other outputs
+ * are optional (code2_out == NULL: sizes only). */
+int sb_air_run_form(const void* image, size_t image_len, uint64_t* code2_out, size_t code2_cap, uint32_t* slot_off2_out,
+                    uint32_t* slot_ks2_out, uint32_t* group_pc2_out, uint32_t* group_slot2_out, uint32_t* info_out);
 
 /* ---- the hot path: replaces starky::prover::prove ---- */
 int sb_prove(sb_ctx* ctx, const sb_params* p, const void* trace, int layout,
@@ -187,6 +193,14 @@ int sb_lde_commit(sb_ctx* ctx, const sb_params* p, const void* trace, int layout
  * Needs a preceding sb_lde_commit on this ctx.  out (host): [num_challenges][N] in NATURAL LDE index order. */
 int sb_quotient_values(sb_ctx* ctx, const sb_params* p, const uint64_t* public_inputs,
                        const uint64_t* alphas, uint64_t* out);
+/* StarkOpeningSet::new on the trace committed by the preceding sb_lde_commit on this ctx: local_out[c] = P_c(zeta),
+ * next_out[c] = P_c(g zeta), g = primitive_root_of_unity(log_n); extension elements as (c0, c1), host [n_cols][2] each. */
+int sb_openings(sb_ctx* ctx, const sb_params* p, const uint64_t* zeta, uint64_t* local_out, uint64_t* next_out);
+/* fri_committed_trees on a given polynomial: coeffs = host [n][2] extension coefficients in natural order (the final_poly
+ * of PolynomialBatch::prove_openings), betas = [n_fri_rounds][2] folding challenges in place of the transcript.
+ * caps_out: [n_fri_rounds][2^cap_height][4], final_poly_out: [final_poly_len][2] (sb_proof_layout_for gives both counts). */
+int sb_fri_commit(sb_ctx* ctx, const sb_params* p, const uint64_t* coeffs, const uint64_t* betas, uint64_t* caps_out,
+                  uint64_t* final_poly_out);
 /* Batched forward/inverse NTT of `count` length-2^log_n vectors (natural order in and out). */
 int sb_ntt_batch(sb_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t count, int inverse);
 /* `count` Poseidon-12 permutations on host states [count][12]. */

@@ -126,6 +126,22 @@ int orc_prove(const char* air_path, const Params* p, const uint64_t* trace_colma
   return 0;
 }
 
+// stage export for the parity test of sb_fri_commit: commit phase with injected folding challenges
+int orc_fri_commit(const Params* p, const uint64_t* coeffs, const uint64_t* betas, uint64_t* caps_out, uint64_t* final_poly_out) {
+  try {
+    const size_t n = size_t(1) << p->log_n, cap_len = size_t(1) << p->cap_height;
+    std::vector<E2> fp(n);
+    for (size_t i = 0; i < n; i++) fp[i] = e2(coeffs[2 * i], coeffs[2 * i + 1]);
+    std::vector<MerkleTree> trees;
+    std::vector<E2> out = fri_commit_phase(*p, fp, trees, [&](size_t round, const std::vector<Hash>& cap) {
+      put_cap(caps_out + round * 4 * cap_len, cap);
+      return e2(betas[2 * round], betas[2 * round + 1]);
+    });
+    for (size_t i = 0; i < out.size(); i++) { final_poly_out[2 * i] = out[i].a; final_poly_out[2 * i + 1] = out[i].b; }
+    return (int)out.size();
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
 int orc_verify(const char* air_path, const Params* p, const uint64_t* words, size_t n_words) {
   auto air = get_air(air_path); if (!air) return -8;
   try { return verify(*air, *p, words, n_words, &g_err); } catch (std::exception& e) { g_err = e.what(); return -1; }

@@ -188,6 +188,44 @@ static inline u64 pow_grind(const Challenger& ch, unsigned bits) {
   }
 }
 
+// fri_committed_trees (A.9): values of the (zero-padded) polynomial on the current coset, arity-sized leaves in
+// bit-reversed order, Merkle tree to the cap, then `next_beta(round, cap)` and the fold in coefficient form.
+// Returns the final polynomial's coefficients (length n >> sum of arity bits).
+template <class BetaFn>
+static inline std::vector<E2> fri_commit_phase(const Params& p, const std::vector<E2>& final_poly, std::vector<MerkleTree>& fri_trees,
+                                               BetaFn&& next_beta) {
+  const unsigned r = p.rate_bits, log_lde = p.log_n + r;
+  const size_t N = size_t(1) << log_lde;
+  std::vector<E2> coeffs = final_poly; coeffs.resize(N, e2(0));
+  std::vector<E2> values = coset_fft_e2(coeffs, log_lde, GL_GEN);
+  std::vector<unsigned> ar = fri_arities(p);
+  fri_trees.assign(ar.size(), MerkleTree());
+  u64 shift = GL_GEN;
+  unsigned cur_log = log_lde;
+  for (size_t round = 0; round < ar.size(); round++) {
+    unsigned ab = ar[round]; size_t arity = size_t(1) << ab;
+    reverse_index_bits(values);
+    MerkleTree& t = fri_trees[round];
+    t.n_leaves = values.size() / arity; t.leaf_len = 2 * arity; t.cap_height = p.cap_height;
+    t.leaves.resize(values.size() * 2);
+    for (size_t i = 0; i < values.size(); i++) { t.leaves[2 * i] = values[i].a; t.leaves[2 * i + 1] = values[i].b; }
+    t.build();
+    E2 beta = next_beta(round, t.cap());
+    std::vector<E2> folded(coeffs.size() / arity);
+    for (size_t m = 0; m < folded.size(); m++) {
+      E2 acc = e2(0);
+      for (size_t i = arity; i-- > 0;) acc = e2_add(e2_mul(acc, beta), coeffs[arity * m + i]);
+      folded[m] = acc;
+    }
+    coeffs.swap(folded);
+    shift = gl_pow(shift, arity);
+    cur_log -= ab;
+    values = coset_fft_e2(coeffs, cur_log, shift);
+  }
+  coeffs.resize(coeffs.size() >> r);
+  return coeffs;
+}
+
 struct ProofOut { Layout layout; std::vector<u64> words; };
 
 static inline int prove(const Air& air, const Params& p, const u64* trace_colmajor, const u64* pis, ProofOut& out,
@@ -271,36 +309,14 @@ static inline int prove(const Air& air, const Params& p, const u64* trace_colmaj
     for (size_t k = 0; k < n; k++) final_poly[k] = e2_add(e2_mul(final_poly[k], shift), q[k]);
   }
   if (p.flags & FLAG_FRI_MUL_X) { final_poly.insert(final_poly.begin(), e2(0)); final_poly.pop_back(); }
-  std::vector<E2> coeffs = final_poly; coeffs.resize(N, e2(0));
-  std::vector<E2> values = coset_fft_e2(coeffs, log_lde, GL_GEN);
   // commit phase
   std::vector<unsigned> ar = fri_arities(p);
-  std::vector<MerkleTree> fri_trees(ar.size());
-  u64 shift = GL_GEN;
-  unsigned cur_log = log_lde;
-  for (size_t round = 0; round < ar.size(); round++) {
-    unsigned ab = ar[round]; size_t arity = size_t(1) << ab;
-    reverse_index_bits(values);
-    MerkleTree& t = fri_trees[round];
-    t.n_leaves = values.size() / arity; t.leaf_len = 2 * arity; t.cap_height = p.cap_height;
-    t.leaves.resize(values.size() * 2);
-    for (size_t i = 0; i < values.size(); i++) { t.leaves[2 * i] = values[i].a; t.leaves[2 * i + 1] = values[i].b; }
-    t.build();
-    ch.observe_cap(t.cap());
-    put_cap(W + L.off_fri_caps + round * 4ull * L.cap_len, t.cap());
-    E2 beta = ch.ext_challenge();
-    std::vector<E2> folded(coeffs.size() / arity);
-    for (size_t m = 0; m < folded.size(); m++) {
-      E2 acc = e2(0);
-      for (size_t i = arity; i-- > 0;) acc = e2_add(e2_mul(acc, beta), coeffs[arity * m + i]);
-      folded[m] = acc;
-    }
-    coeffs.swap(folded);
-    shift = gl_pow(shift, arity);
-    cur_log -= ab;
-    values = coset_fft_e2(coeffs, cur_log, shift);
-  }
-  coeffs.resize(coeffs.size() >> r);
+  std::vector<MerkleTree> fri_trees;
+  std::vector<E2> coeffs = fri_commit_phase(p, final_poly, fri_trees, [&](size_t round, const std::vector<Hash>& cap) {
+    ch.observe_cap(cap);
+    put_cap(W + L.off_fri_caps + round * 4ull * L.cap_len, cap);
+    return ch.ext_challenge();
+  });
   if (coeffs.size() != L.final_poly_len) { if (err) *err = "internal: final poly length"; return -1; }
   for (size_t i = 0; i < coeffs.size(); i++) { W[L.off_final_poly + 2 * i] = coeffs[i].a; W[L.off_final_poly + 2 * i + 1] = coeffs[i].b; ch.observe_ext(coeffs[i]); }
   // PoW

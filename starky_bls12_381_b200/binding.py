@@ -135,6 +135,8 @@ def lib():
         L.sb_proof_deserialize.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Params), C.POINTER(Params),
                                            C.POINTER(C.POINTER(_CProof))]
         L.sb_proof_from_words.argtypes = [C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.POINTER(_CProof))]
+        L.sb_openings.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sb_fri_commit.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sb_prove_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Job), C.c_int]
         L.sb_group_unique_id.argtypes = [C.c_void_p]
         L.sb_group_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -306,6 +308,23 @@ class Context:
         pis, al = _u64(public_inputs), _u64(alphas)
         self._check(lib().sb_quotient_values(self._h, C.byref(p), _ptr(pis), _ptr(al), _ptr(out)))
         return out
+
+    def openings(self, p, zeta):
+        """sb_openings: (local_values, next_values) of the committed trace at zeta / g zeta, uint64 [n_cols][2] each."""
+        z = _u64(zeta)
+        loc, nxt = np.empty((p.n_cols, 2), np.uint64), np.empty((p.n_cols, 2), np.uint64)
+        self._check(lib().sb_openings(self._h, C.byref(p), _ptr(z), _ptr(loc), _ptr(nxt)))
+        return loc, nxt
+
+    def fri_commit(self, p, coeffs, betas):
+        """sb_fri_commit: (caps [rounds][2^cap_height][4], final_poly [len][2]) for injected folding challenges."""
+        l = ProofLayout()
+        self._check(lib().sb_proof_layout_for(C.byref(p), C.byref(l)))
+        c, b = _u64(coeffs), _u64(betas)
+        caps = np.zeros((l.n_fri_rounds, l.cap_len, 4), np.uint64)
+        fin = np.zeros((l.final_poly_len, 2), np.uint64)
+        self._check(lib().sb_fri_commit(self._h, C.byref(p), _ptr(c), _ptr(b) if b.size else None, _ptr(caps), _ptr(fin)))
+        return caps, fin
 
     def ntt_batch(self, data, inverse=False):
         d = _u64(data).copy()

@@ -3,6 +3,8 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <thread>
+
 #include "common.cuh"
 #include "prover.cuh"
 
@@ -200,6 +202,21 @@ void commit_trace(sb_ctx* ctx, const sb_params* p, const u64* d_values) {
   ctx->have_lde = true;
 }
 
+// Vec<PolynomialValues<F>> -> one contiguous (pinned) slab.  One host core copies ~10 GB/s, PCIe takes ~55: four helper
+// threads per slab keep the gather ahead of the H2D copy (FinalExp, 4.8 GB in 73 527 pageable columns: 1115 -> ~760 ms).
+static void gather_columns(u64* dst, const u64* const* cols, size_t cnt, size_t n) {
+  const size_t bytes = 8 * n * cnt;
+  const unsigned workers = bytes >= (4u << 20) ? 4 : 1;
+  if (workers == 1) { for (size_t c = 0; c < cnt; c++) memcpy(dst + c * n, cols[c], 8 * n); return; }
+  std::vector<std::thread> th;
+  for (unsigned w = 0; w < workers; w++)
+    th.emplace_back([=] {
+      const size_t a = cnt * w / workers, b = cnt * (w + 1) / workers;
+      for (size_t c = a; c < b; c++) memcpy(dst + c * n, cols[c], 8 * n);
+    });
+  for (auto& t : th) t.join();
+}
+
 // Ingest + from_values in one pipeline for the host column layouts: the trace crosses PCIe in column slabs on a second
 // stream while K1 already extends the slabs that have arrived, so the H2D copy (the larger of the two for every stark:
 // 8 C n bytes at ~55 GB/s) hides the whole LDE.  `h2d_done` is recorded on the copy stream after the last slab.
@@ -240,7 +257,7 @@ void ingest_and_commit_trace(sb_ctx* ctx, const sb_params* p, const void* trace,
       const u64* const* cols = (const u64* const*)trace;
       u64* dst = stage + (i & 1) * slab_cols * n;
       if (i >= 2) CUDA_CHECK(cudaEventSynchronize(ctx->slab_ev[(i - 2) % 4]));   // that staging slab has left the host
-      for (size_t c = 0; c < cnt; c++) memcpy(dst + c * n, cols[c0 + c], 8 * n);
+      gather_columns(dst, cols + c0, cnt, n);
       CUDA_CHECK(cudaMemcpyAsync(d_slab, dst, 8 * n * cnt, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
     // (re-recording an event does not disturb a cudaStreamWaitEvent already enqueued on its previous record)

@@ -144,6 +144,56 @@ struct Arena {
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// fri_committed_trees (plonky2 fri::prover): per round the coefficients go to values on the current coset
+// (shift^m scaling on the host, zero padding to the LDE size, forward transform on the device, bit-reversed order), the
+// arity-sized leaves are hashed and the tree built to the cap; `next_beta(round, cap)` supplies the folding challenge
+// (the transcript in a proof, injected values in the sb_fri_commit stage export) and the polynomial is folded in
+// coefficient form.  caps_out: host, [rounds][cap_len][4].
+struct FriRound { u64* re; u64* im; u64* tree; uint32_t n_leaves; unsigned log_size; };
+template <class BetaFn>
+static void fri_commit_phase(sb_ctx* ctx, const sb_params* p, Arena& ar, std::vector<e2_t>& coeffs, u64* caps_out,
+                             std::vector<FriRound>& rounds, BetaFn&& next_beta) {
+  const std::vector<unsigned> arities = fri_arities(*p);
+  const uint32_t cap_len = 1u << p->cap_height;
+  cudaStream_t st = ctx->stream;
+  u64 shift = 7;
+  unsigned cur_log = p->log_n + p->rate_bits;
+  for (size_t round = 0; round < arities.size(); round++) {
+    const unsigned ab = arities[round];
+    const size_t size = size_t(1) << cur_log;
+    u64* d_vals = ar.take<u64>(2 * size);
+    std::vector<u64> host(2 * size, 0);
+    u64 s = 1;
+    for (size_t m = 0; m < coeffs.size(); m++) {
+      host[m] = gl_mul(coeffs[m].a, s);
+      host[size + m] = gl_mul(coeffs[m].b, s);
+      s = gl_mul(s, shift);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d_vals, host.data(), 16ull * size, cudaMemcpyHostToDevice, st));
+    sb_ntt_device(ctx, d_vals, cur_log, 2, false, /*dif=*/true);
+    FriRound R;
+    R.re = d_vals; R.im = d_vals + size; R.log_size = cur_log; R.n_leaves = (uint32_t)(size >> ab);
+    R.tree = ar.take<u64>(8ull * R.n_leaves + 64);
+    sb_fri_leaf_hash_device(ctx, R.re, R.im, R.n_leaves, ab, R.tree);
+    sb_merkle_levels(ctx, R.tree, R.n_leaves, p->cap_height);
+    u64* cap_dst = caps_out + round * 4ull * cap_len;
+    CUDA_CHECK(cudaMemcpyAsync(cap_dst, tree_cap_ptr(R.tree, R.n_leaves, p->cap_height), 32ull * cap_len, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));   // also keeps `host` alive until the upload is done
+    rounds.push_back(R);
+    const e2_t beta = next_beta(round, (const u64*)cap_dst);
+    const size_t arity = size_t(1) << ab;
+    std::vector<e2_t> folded(coeffs.size() / arity);
+    for (size_t m = 0; m < folded.size(); m++) {
+      e2_t acc = e2_make(0, 0);
+      for (size_t i = arity; i-- > 0;) acc = e2_add(e2_mul(acc, beta), coeffs[arity * m + i]);
+      folded[m] = acc;
+    }
+    coeffs.swap(folded);
+    shift = gl_pow(shift, arity);
+    cur_log -= ab;
+  }
+}
+
 #define HOOK(call)                                                                              \
   do {                                                                                          \
     int rc_ = (call);                                                                           \
@@ -303,47 +353,11 @@ static void prove_impl(sb_ctx* ctx, const sb_params* p, const void* trace, int l
 
   // ---- FRI commit phase ----
   const std::vector<unsigned> arities = fri_arities(*p);
-  struct Round { u64* re; u64* im; u64* tree; uint32_t n_leaves; unsigned log_size; };
-  std::vector<Round> rounds;
-  u64 shift = 7;
-  unsigned cur_log = log_N;
-  std::vector<u64> stage_re, stage_im;
-  for (size_t round = 0; round < arities.size(); round++) {
-    const unsigned ab = arities[round];
-    const size_t size = size_t(1) << cur_log;
-    // coset_fft(shift): c_m * shift^m, zero-padded to the LDE size, forward transform to bit-reversed order
-    u64* d_vals = ar.take<u64>(2 * size);
-    std::vector<u64> host(2 * size, 0);
-    u64 s = 1;
-    for (size_t m = 0; m < coeffs.size(); m++) {
-      host[m] = gl_mul(coeffs[m].a, s);
-      host[size + m] = gl_mul(coeffs[m].b, s);
-      s = gl_mul(s, shift);
-    }
-    CUDA_CHECK(cudaMemcpyAsync(d_vals, host.data(), 16ull * size, cudaMemcpyHostToDevice, st));
-    sb_ntt_device(ctx, d_vals, cur_log, 2, false, /*dif=*/true);
-    Round R;
-    R.re = d_vals; R.im = d_vals + size; R.log_size = cur_log; R.n_leaves = (uint32_t)(size >> ab);
-    R.tree = ar.take<u64>(8ull * R.n_leaves + 64);
-    sb_fri_leaf_hash_device(ctx, R.re, R.im, R.n_leaves, ab, R.tree);
-    sb_merkle_levels(ctx, R.tree, R.n_leaves, p->cap_height);
-    u64* cap_dst = W + L.off_fri_caps + round * 4ull * L.cap_len;
-    CUDA_CHECK(cudaMemcpyAsync(cap_dst, tree_cap_ptr(R.tree, R.n_leaves, p->cap_height), 32ull * L.cap_len, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));   // also keeps `host` alive until the upload is done
-    rounds.push_back(R);
-    ch.observe_many(cap_dst, 4ull * L.cap_len);
-    const e2_t beta = ch.ext_challenge();
-    const size_t arity = size_t(1) << ab;
-    std::vector<e2_t> folded(coeffs.size() / arity);
-    for (size_t m = 0; m < folded.size(); m++) {
-      e2_t acc = e2_make(0, 0);
-      for (size_t i = arity; i-- > 0;) acc = e2_add(e2_mul(acc, beta), coeffs[arity * m + i]);
-      folded[m] = acc;
-    }
-    coeffs.swap(folded);
-    shift = gl_pow(shift, arity);
-    cur_log -= ab;
-  }
+  std::vector<FriRound> rounds;
+  fri_commit_phase(ctx, p, ar, coeffs, W + L.off_fri_caps, rounds, [&](size_t, const u64* cap) {
+    ch.observe_many(cap, 4ull * L.cap_len);
+    return ch.ext_challenge();
+  });
   if (coeffs.size() != L.final_poly_len) SB_THROW(SB_EINVAL, "internal: final polynomial length %zu != %u", coeffs.size(), L.final_poly_len);
   for (size_t i = 0; i < coeffs.size(); i++) { W[L.off_final_poly + 2 * i] = coeffs[i].a; W[L.off_final_poly + 2 * i + 1] = coeffs[i].b; }
   ch.observe_many(W + L.off_final_poly, 2ull * coeffs.size());
@@ -583,6 +597,46 @@ int sb_memcpy_device(sb_ctx* ctx, void* d_dst, const void* d_src, uint64_t bytes
     CUDA_CHECK(cudaSetDevice(ctx->device));
     CUDA_CHECK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+
+// ---- stage exports: openings of the committed trace, FRI commit phase with injected challenges ----
+// StarkOpeningSet::new on the trace committed by the preceding sb_lde_commit / sb_prove on this ctx:
+// local_out[c] = P_c(zeta), next_out[c] = P_c(g zeta), extension elements as (c0, c1).
+int sb_openings(sb_ctx* ctx, const sb_params* p, const uint64_t* zeta, uint64_t* local_out, uint64_t* next_out) {
+  if (!ctx || !p || !zeta || !local_out || !next_out) return SB_EINVAL;
+  try {
+    check_params(p);
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!ctx->have_lde || ctx->cur.n_cols != p->n_cols || ctx->cur.log_n != p->log_n)
+      SB_THROW(SB_EINVAL, "sb_openings needs a preceding sb_lde_commit with the same shape on this ctx");
+    const e2_t z = e2_make(zeta[0], zeta[1]), zn = e2_scale(z, gl_root(p->log_n));
+    const u64 zn_w[2] = {zn.a, zn.b};
+    return sb_openings_cols_device(ctx, p, ctx->coeffs.as<u64>(), p->n_cols, zeta, zn_w, local_out, next_out);
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+
+// fri_committed_trees on a given polynomial: coeffs = [n][2] extension coefficients in natural order (the `final_poly` of
+// prove_openings), betas = [rounds][2] folding challenges in place of the transcript.  caps_out: [rounds][2^cap_height][4],
+// final_poly_out: [final_poly_len][2] (sb_proof_layout_for gives both counts).
+int sb_fri_commit(sb_ctx* ctx, const sb_params* p, const uint64_t* coeffs, const uint64_t* betas, uint64_t* caps_out,
+                  uint64_t* final_poly_out) {
+  if (!ctx || !p || !coeffs || !caps_out || !final_poly_out) return SB_EINVAL;
+  try {
+    check_params(p);
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    const sb_proof_layout L = proof_layout(*p);
+    if (L.n_fri_rounds && !betas) SB_THROW(SB_EINVAL, "betas is NULL");
+    const uint32_t n = 1u << p->log_n, N = n << p->rate_bits;
+    ctx->scratch2.ensure(16ull * N * 2 + 64ull * N + (1 << 16));
+    Arena ar(ctx->scratch2.p, ctx->scratch2.cap);
+    std::vector<e2_t> c(n);
+    for (uint32_t i = 0; i < n; i++) c[i] = e2_make(coeffs[2 * i], coeffs[2 * i + 1]);
+    std::vector<FriRound> rounds;
+    fri_commit_phase(ctx, p, ar, c, caps_out, rounds, [&](size_t round, const u64*) { return e2_make(betas[2 * round], betas[2 * round + 1]); });
+    if (c.size() != L.final_poly_len) SB_THROW(SB_EINVAL, "internal: final polynomial length %zu != %u", c.size(), L.final_poly_len);
+    for (size_t i = 0; i < c.size(); i++) { final_poly_out[2 * i] = c[i].a; final_poly_out[2 * i + 1] = c[i].b; }
     return SB_OK;
   } catch (const SbError& e) { return sb_fail(ctx, e); }
 }

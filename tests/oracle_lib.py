@@ -178,3 +178,14 @@ def prove(air_path, p, trace_colmajor, pis):
 def verify(air_path, p, words):
     w = u64(words)
     return lib().orc_verify(air_path.encode(), C.byref(p), ptr(w), w.size)
+
+
+def fri_commit(p, coeffs, betas):
+    """Commit phase of FRI with injected folding challenges -> (caps [rounds][cap_len][4], final_poly [len][2])."""
+    l = layout(p)
+    c, b = u64(coeffs), u64(betas)
+    caps = np.zeros((l.n_fri_rounds, l.cap_len, 4), np.uint64)
+    fin = np.zeros((l.final_poly_len, 2), np.uint64)
+    n = lib().orc_fri_commit(C.byref(p), ptr(c), ptr(b), ptr(caps), ptr(fin))
+    assert n == l.final_poly_len, err()
+    return caps, fin

@@ -122,3 +122,46 @@ def test_errors_are_codes_not_aborts(ctx):
     with pytest.raises(sb.SbError) as e:
         ctx.lde_commit(p, np.zeros((4, 16), np.uint64))
     assert e.value.code == -1
+
+
+def test_openings_stage_matches_direct_evaluation(ctx):
+    """sb_openings (SURVEY 8b stage export): P_c(zeta), P_c(g zeta) of the committed trace against a plain Horner evaluation
+    of the natural-order coefficients in F_p[X]/(X^2 - 7), in Python integers."""
+    rng = np.random.default_rng(31)
+    p = custom(6, 9, 1)
+    trace = random_trace(rng, p.n_cols, p.log_n, full_width=True)
+    ctx.lde_commit(p, trace, want_lde=False, want_digests=False)
+    coeffs = O.ntt_batch(trace, inverse=True)                       # natural-order coefficients of every column
+    zeta = [int(x) for x in rng.integers(1, 1 << 62, 2)]
+    loc, nxt = ctx.openings(p, np.array(zeta, np.uint64))
+    g = int(O.lib().orc_gl_root(p.log_n))
+
+    def ext_mul(x, y):
+        return ((x[0] * y[0] + 7 * x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+
+    def horner(c, z):
+        acc = (0, 0)
+        for a in reversed([int(v) for v in c]):
+            acc = ext_mul(acc, z)
+            acc = ((acc[0] + a) % P, acc[1])
+        return acc
+    zn = (zeta[0] * g % P, zeta[1] * g % P)
+    for col in range(p.n_cols):
+        assert tuple(int(v) for v in loc[col]) == horner(coeffs[col], tuple(zeta))
+        assert tuple(int(v) for v in nxt[col]) == horner(coeffs[col], zn)
+
+
+@pytest.mark.parametrize("log_n,rate_bits", [(5, 1), (6, 2), (10, 1), (13, 2)])
+def test_fri_commit_stage_matches_oracle(ctx, log_n, rate_bits):
+    """sb_fri_commit (SURVEY 8b stage export): round caps and final polynomial of fri_committed_trees for an injected
+    polynomial and injected folding challenges == the oracle's (0, 1 and 2 arity-16 rounds)."""
+    rng = np.random.default_rng(1000 + log_n)
+    p = custom(log_n, 8, rate_bits)
+    op = to_oracle_params(p)
+    n = 1 << log_n
+    coeffs = rng.integers(0, 1 << 63, (n, 2), dtype=np.uint64) % np.uint64(P)
+    betas = rng.integers(0, 1 << 63, (4, 2), dtype=np.uint64) % np.uint64(P)
+    caps, fin = ctx.fri_commit(p, coeffs, betas)
+    want_caps, want_fin = O.fri_commit(op, coeffs, betas)
+    assert caps.shape[0] == {5: 0, 6: 1, 10: 2, 13: 2}[log_n]
+    assert np.array_equal(caps, want_caps) and np.array_equal(fin, want_fin)
