@@ -162,6 +162,18 @@ typedef struct sb_job {
 } sb_job;
 int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int n_jobs);
 
+/* ---- witness generation: the reference's generate_trace in C++, so that the caller hands over a few field
+ *      elements instead of a multi-GB trace.  Cells are row-major uint32_t (SB_TRACE_ROWMAJOR_U32: every cell the reference
+ *      writes is a u32 limb, a carry or a bit -- utils.rs:7-19), half the PCIe bytes of the u64 layouts.  Host code.
+ *      sb_witness_fp12_mul: FP12MulStark::generate_trace (fp12_mul.rs:44-48; fill_trace_fp12_multiplication fp12.rs:186-232
+ *      and the fp / fp2 / fp6 gadgets below it) + the public inputs of fp12_mul_main (aggregate_proof.rs:124-151).
+ *      x, y: Fp12 operands as 12 x 12 little-endian u32 limbs ([Fp; 12], Fp = [u32; 12]), each coefficient < p.
+ *      trace_out: [num_rows][60285] uint32_t; public_inputs_out: 432 values (x ++ y ++ x*y).
+ *      sb_prove_fp12_mul: both steps in one call (generate on the host, prove on the ctx's GPU). ---- */
+int sb_witness_fp12_mul(const uint32_t* x, const uint32_t* y, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out);
+int sb_prove_fp12_mul(sb_ctx* ctx, const sb_params* p, const uint32_t* x, const uint32_t* y, sb_proof** out);
+const char* sb_witness_last_error(void);
+
 /* ---- proof wire formats: the proof as bytes for a consumer that does not link this library -- the
  *      reference's verify_stark_proof / recursive verifier take a starky::proof::StarkProofWithPublicInputs<F, C, 2>
  *      (aggregate_proof.rs:67,113,146,177,220 and :435-439).  Host code only: works in a process without a GPU. ---- */

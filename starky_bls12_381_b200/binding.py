@@ -135,6 +135,9 @@ def lib():
         L.sb_proof_deserialize.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Params), C.POINTER(Params),
                                            C.POINTER(C.POINTER(_CProof))]
         L.sb_proof_from_words.argtypes = [C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.POINTER(_CProof))]
+        L.sb_witness_fp12_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.sb_prove_fp12_mul.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(_CProof))]
+        L.sb_witness_last_error.restype = C.c_char_p
         L.sb_openings.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
         L.sb_fri_commit.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sb_prove_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Job), C.c_int]
@@ -227,6 +230,22 @@ class Proof:
     def field(self, name, count):
         off = getattr(self.layout, name)
         return self.words[off:off + count]
+
+
+def fp12_limbs(x):
+    """Fp12 as twelve Python ints (the reference's [Fp; 12]) -> uint32 [144] little-endian limbs."""
+    return np.array([(int(v) >> (32 * i)) & 0xFFFFFFFF for v in x for i in range(12)], dtype=np.uint32)
+
+
+def witness_fp12_mul(x, y, num_rows=16):
+    """sb_witness_fp12_mul: (trace uint32 [num_rows][60285] row-major, public inputs uint64 [432])."""
+    xl, yl = fp12_limbs(x), fp12_limbs(y)
+    trace = np.empty((num_rows, 60285), np.uint32)
+    pis = np.empty(432, np.uint64)
+    rc = lib().sb_witness_fp12_mul(_ptr(xl), _ptr(yl), num_rows, _ptr(trace), _ptr(pis))
+    if rc:
+        raise SbError(rc, lib().sb_witness_last_error().decode())
+    return trace, pis
 
 
 def prove_batch(contexts, jobs):
@@ -347,6 +366,13 @@ class Context:
         out = C.POINTER(_CProof)()
         pis = _u64(public_inputs)
         self._check(lib().sb_prove(self._h, C.byref(p), _ptr(trace), layout, _ptr(pis), C.byref(out)))
+        return Proof(out)
+
+    def prove_fp12_mul(self, p, x, y):
+        """sb_prove_fp12_mul: FP12MulStark proof from the two Fp12 operands (witness generated in C++ on the host)."""
+        out = C.POINTER(_CProof)()
+        xl, yl = fp12_limbs(x), fp12_limbs(y)
+        self._check(lib().sb_prove_fp12_mul(self._h, C.byref(p), _ptr(xl), _ptr(yl), C.byref(out)))
         return Proof(out)
 
     def synchronize(self):

@@ -641,6 +641,21 @@ int sb_fri_commit(sb_ctx* ctx, const sb_params* p, const uint64_t* coeffs, const
   } catch (const SbError& e) { return sb_fail(ctx, e); }
 }
 
+// FP12MulStark from its operands: witness generation on the host (witness.cpp), then the proof
+int sb_prove_fp12_mul(sb_ctx* ctx, const sb_params* p, const uint32_t* x, const uint32_t* y, sb_proof** out) {
+  if (!ctx || !p || !x || !y || !out) return SB_EINVAL;
+  try {
+    check_params(p);
+    if (p->stark_id != SB_STARK_FP12_MUL || p->n_cols != 60285 || p->n_public_inputs != 432)
+      SB_THROW(SB_EINVAL, "sb_prove_fp12_mul needs the FP12MulStark parameters (60285 columns, 432 public inputs)");
+    const uint32_t rows = 1u << p->log_n;
+    std::vector<uint32_t> trace((size_t)rows * p->n_cols);
+    std::vector<uint64_t> pis(p->n_public_inputs);
+    if (sb_witness_fp12_mul(x, y, rows, trace.data(), pis.data())) SB_THROW(SB_EINVAL, "%s", sb_witness_last_error());
+    return sb_prove(ctx, p, trace.data(), SB_TRACE_ROWMAJOR_U32, pis.data(), out);
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+
 void sb_proof_free(sb_proof* proof) {
   if (!proof) return;
   if (proof->words) pinned_give(proof->words, 8ull * proof->layout.total_words);

@@ -1,0 +1,66 @@
+"""The C++ witness generator (csrc/witness.cpp) against the Python restatement of the reference's
+generate_trace (starky_bls12_381_b200/witness): cell for cell and public input for public input, and every one of the
+82 560 extracted constraints vanishes on every row of the C++ trace (CPU).  GPU: sb_prove_fp12_mul (operands in, proof
+out) equals the proof of the Python trace and the oracle's verifier accepts it."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import starky_bls12_381_b200 as sb
+from helpers import to_oracle_params
+from starky_bls12_381_b200 import airfiles, witness as W
+from starky_bls12_381_b200.binding import witness_fp12_mul
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_cpp_fp12_mul_trace_equals_the_python_restatement(seed):
+    rng = np.random.default_rng(0xB2007000 + seed)
+    x, y = W.random_fp12(rng), W.random_fp12(rng)
+    if seed == 3:                      # edge values: zero and p - 1 coefficients
+        x = (0, W.N.P - 1) + tuple(x[2:])
+        y = (W.N.P - 1,) * 12
+    want_t, want_p = W.fp12_mul_trace(x, y, 16)            # column-major uint64 [60285][16]
+    got_t, got_p = witness_fp12_mul(x, y, 16)              # row-major uint32 [16][60285]
+    assert np.array_equal(got_p, want_p)
+    assert np.array_equal(got_t.astype(np.uint64).T, want_t)
+
+
+def test_every_constraint_vanishes_on_the_cpp_trace():
+    rng = np.random.default_rng(0xB2007100)
+    trace, pis = witness_fp12_mul(W.random_fp12(rng), W.random_fp12(rng), 16)
+    flat = airfiles.air_path("fp12_mul", "air")
+    rows = trace.astype(np.uint64)
+    for r in range(16):
+        c = O.eval_constraints_row(flat, rows[r], rows[(r + 1) % 16], pis)
+        # transition constraints are not enforced on the last row, first / last-row classes only there: check what vanishes
+        # everywhere -- the plain ones -- on all rows and all classes on the rows where they apply via the oracle prover below
+        if r < 15:
+            assert not c.any(), (r, int(np.count_nonzero(c)))
+    p = sb.standard_params(sb.StarkId.FP12_MUL, 4)
+    rc, words = O.prove(flat, to_oracle_params(p), np.ascontiguousarray(rows.T), pis)     # flags = 0: the quotient must divide
+    assert rc == 0, O.err()
+    assert O.verify(flat, to_oracle_params(p), words) == 0, O.err()
+
+
+def test_unreduced_operands_are_rejected():
+    bad = (W.N.P,) + (0,) * 11
+    with pytest.raises(sb.SbError):
+        witness_fp12_mul(bad, bad, 16)
+    with pytest.raises(sb.SbError):
+        witness_fp12_mul((1,) * 12, (1,) * 12, 12)          # not a power of two
+
+
+@pytest.mark.gpu
+def test_gpu_proof_from_operands_equals_the_proof_of_the_python_trace():
+    rng = np.random.default_rng(0xB2007200)
+    x, y = W.random_fp12(rng), W.random_fp12(rng)
+    trace, pis = W.fp12_mul_trace(x, y, 16)
+    p = sb.standard_params(sb.StarkId.FP12_MUL, 4)
+    ctx = sb.Context(0)
+    try:
+        want = ctx.prove(p, trace, pis)
+        got = ctx.prove_fp12_mul(p, x, y)
+    finally:
+        ctx.close()
+    assert np.array_equal(got.words, want.words)
+    assert O.verify(airfiles.air_path("fp12_mul", "air"), to_oracle_params(p), got.words) == 0, O.err()

@@ -72,5 +72,43 @@ def kernels(path):
             pass
 
 
+def stalls(path):
+    """Warp-stall shares and executed instructions of the one profiled kernel, from the SASS source page."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
+    h, data = rows[hi], rows[hi + 1:]
+    iex, ismp = h.index("Instructions Executed"), h.index("# Samples")
+    tot = sum(int(r[ismp]) for r in data) or 1
+    print("# SASS page of %s: %d instructions, %d warp-level instructions executed" % (path, len(data), sum(int(r[iex]) for r in data)))
+    for name in [x for x in h if x.startswith("stall_") and "Not Issued" not in x]:
+        share = 100.0 * sum(int(r[h.index(name)]) for r in data) / tot
+        if share >= 1.0:
+            print("  %-28s %5.1f %% of warp samples" % (name, share))
+
+
+def traffic(spec):
+    """traffic stark:kernel_regex=report.ncu-rep ... -> JSON {stark: {kernel: bytes per launch}} on stdout."""
+    import json
+    import re
+    res = {}
+    for item in spec:
+        key, path = item.split("=")
+        stark, pat = key.split(":")
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        h = rows[0]
+        for r in rows[2:]:
+            d = dict(zip(h, r))
+            m = re.search(pat, d.get("Kernel Name", ""))
+            if m:
+                name = m.group(0)
+                res.setdefault(stark, {})[name] = int(float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))
+    print(json.dumps(res, indent=1, sort_keys=True))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
+    else:
+        {"launches": launches, "kernels": kernels, "stalls": stalls}[sys.argv[1]](sys.argv[2])
