@@ -366,6 +366,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="sharded legs: NCCL all-to-all after K1 instead of K1 storing into peer memory")
     ap.add_argument("--no-full-set", action="store_true", help="skip the 7-proof BLS set (BASELINE configs[4])")
+    ap.add_argument("--bundled", action="store_true",
+                    help="N=1: also prove the seven proofs of the reference's bundled light_client_update_period_1052/1053 inputs "
+                         "(valid traces from the witness generators, ~1 min of host-side trace generation outside the timed region)")
     ap.add_argument("--no-extras", action="store_true", help="headline line only (no 'also', sharded FinalExp, in-flight, full set)")
     ap.add_argument("--also", default="miller_loop",
                     help="further starks measured after the headline workload (N=1: whole proofs; N>1: sharded proofs)")
@@ -604,10 +607,46 @@ def main():
                 sub.close()
             return out
         full = optional(full_leg, world)
+
+        def bundled_leg():
+            """BASELINE configs[4] on the reference's own inputs (main.rs:8-55): tests/golden/bundled_inputs.json through
+            bls.prepare and the witness generators, VALID traces, flags = 0 (a non-divisible quotient would be an error)."""
+            if not args.bundled or world != 1:
+                return None
+            from starky_bls12_381_b200 import airfiles, bundled
+            from starky_bls12_381_b200.binding import prove_batch
+            t0 = time.perf_counter()
+            js = bundled.jobs(bundled.load_inputs())
+            gen_s = time.perf_counter() - t0
+            keep, batch = [], []
+            for name, trace, pis in js:
+                host = torch.from_numpy(trace.view(np.int64)).pin_memory()
+                keep.append(host)
+                batch.append((sb.standard_params(sb.STARKS[name].stark_id, trace.shape[1].bit_length() - 1), host.data_ptr(),
+                              sb.TraceLayout.COLMAJOR_U64, pis))
+            del js
+            ctxs = [ctx] + more
+            prove_batch(ctxs, batch)
+            prove_batch(ctxs, batch)
+            dtb, outs = timed(lambda: prove_batch(ctxs, batch), 1)
+            res = outs[0]
+            accepted = None
+            if not args.no_cpu_baseline:
+                O, _ = oracle_all_threads()
+                accepted = all(O.verify(airfiles.air_path(nm, "air"), O.Params.from_buffer_copy(bytes(b[0])), r[0].words) == 0
+                               for nm, b, r in zip(bundled.ORDER, batch, res))
+            return {"workload": "the seven proofs of the reference's bundled run (light_client_update_period_1052 public keys, "
+                                "_1053 sync aggregate and attested header; main.rs:8-55), valid traces, end to end from pinned host memory",
+                    "data": "bundled", "ms": 1e3 * dtb, "proof_ms": {("%s#%d" % (nm, i)): round(r[1], 2) for i, (nm, r) in enumerate(zip(bundled.ORDER, res))},
+                    "final_exp_output_is_one": bool([int(v) for v in batch[-1][3][-144:]] == [1] + [0] * 143),
+                    "every_proof_accepted_by_the_oracle_verifier": accepted, "host_trace_generation_s": round(gen_s, 1)}
+        bundled_out = optional(bundled_leg, world)
         for c in more:
             c.close()
         line["in_flight"] = inflight
         line["full_bls_set"] = full
+        if bundled_out is not None:
+            line["bundled_bls_set"] = bundled_out
 
     if rank == 0:
         print(json.dumps(line), flush=True)
