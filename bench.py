@@ -229,7 +229,7 @@ def roofline_for(stark, info, kern, ms_step, imad, hbm_peak, peak_src):
             "quotient": {"bound": "imad", "achieved": K_CONSTRAINTS[stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9,
                          "peak": imad["mad_lo_u32_gops"], "unit": "Gop/s (u32 multiply-add)",
                          "frac": K_CONSTRAINTS[stark] * N * U32_MACS_PER_CONSTRAINT / t_q / 1e9 / imad["mad_lo_u32_gops"],
-                         "ms": kern["quotient"], "traffic": measured_traffic(stark, "quotient_kernel"), "algorithmic_bytes": 8 * C * N},
+                         "ms": kern["quotient"], "traffic": measured_traffic(stark, "quotient_run_kernel"), "algorithmic_bytes": 8 * C * N},
             "lde_quotient_merkle": {"ms": kern["lde"] + kern["quotient"] + kern["leaf_hash"] + kern["merkle"],
                                     "lde_merkle_gbs": 8.0 * C * N / ((kern["lde"] + kern["leaf_hash"] + kern["merkle"]) * 1e-3) / 1e9},
         },

@@ -22,9 +22,13 @@ PolynomialBatch::from_values as called by starky::prover::prove (aggregate_proof
                               alpha-power offset, all-gather of n extension values, added mod p) and the query rows
                               (84 x C values, summed over the ranks that own them)
 
-The module is backend-agnostic plumbing (torch.distributed only): `backend` supplies the three kernels -- GpuBackend
-(libstarkyb200 through the C ABI, device pointers of torch CUDA tensors) in production, an oracle-backed CPU double in
-the gloo tests.  Tensors are int64 views of canonical u64 field elements.
+THE PRODUCT PATH IS NOT HERE: since round 2 the sharded proof runs inside libstarkyb200 (csrc/group.cu -- NCCL or
+peer copies, CUDA IPC row buffers, modular add of the combine partials on the device; thin ctypes caller: multi.py).
+This module is the executable specification of that exchange pattern, kept because it runs WITHOUT a GPU: with the
+oracle-backed double of the three kernels it is what the world-size-2/4/8 gloo tests on CPU exercise (shard plan, halo
+successor, tail collectives), and with GpuBackend + ThreadGroup (ranks emulated by host threads on one GPU) it is the
+test harness of the per-rank stage entry points of the C ABI (sb_lde_cols_device, sb_hash_rows_device, ...).
+Tensors are int64 views of canonical u64 field elements.
 """
 import dataclasses
 
@@ -162,22 +166,6 @@ class TorchGroup:
         dist.all_to_all_single(rows, slabs, output_split_sizes=plan.recv_splits(self.rank),
                                input_split_sizes=plan.send_splits(self.rank), group=self.group)
         return rows
-
-
-    def symmetric_rows(self, plan, device):
-        """This rank's row buffer [C][N/world] in symmetric memory + the peer-mapped pointers of every rank's buffer.
-        Returns (rows tensor, [device pointers by rank], barrier function)."""
-        import torch
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
-        rows = symm_mem.empty(plan.n_cols * plan.rows_per_rank, dtype=torch.int64, device=device)
-        hdl = symm_mem.rendezvous(rows, self.group if self.group is not None else dist.group.WORLD)
-
-        def barrier():
-            torch.cuda.synchronize()
-            hdl.barrier()
-            torch.cuda.synchronize()
-        return rows, [int(x) for x in hdl.buffer_ptrs], barrier
 
 
 class ThreadGroup:
