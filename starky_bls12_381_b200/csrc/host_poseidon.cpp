@@ -305,11 +305,208 @@ __attribute__((target("avx512f,avx512dq,avx512bw,avx512vl"))) static void permut
   _mm512_mask_storeu_epi64((void*)(s + 8), 0x0F, s1);
   for (int i = 0; i < 12; i++) s[i] -= mask_of(s[i] >= P) & P;
 }
+// ---- Hybrid form (variant 4): AVX-512 IFMA + BMI2.  What the variants above leave on the table (rdtsc per phase, one
+// core): a full round is throughput-bound on the two 512-bit ports (two wsbox = 176 uops, half of the second vector
+// idle) and a partial round executes ~360 instructions around a 50-cycle dependency chain.  Here
+//   * full rounds: words 0..7 in one vector, words 8..11 in scalar registers (mulx) -- the scalar ports are otherwise
+//     idle, so the four scalar S-boxes run beside the vector one;
+//   * the MDS layer is 12 broadcast loads per half and one fused multiply-add per (word, half, row block):
+//     vpmadd52luq (32-bit half x coefficient <= 49 fits the 52-bit product), accumulators seeded with the next round's
+//     constants, four chains per accumulator;
+//   * partial rounds: mulx with three-word carry-chain sums for the look-ahead dot product, the eleven updates as two
+//     vector multiplies stored to a 64-byte aligned array with full-width stores (a masked store does not forward to
+//     the scalar loads of the next dot product).
+#define THYB __attribute__((target("avx512f,avx512dq,avx512bw,avx512vl,avx512ifma,bmi2")))
+typedef __m256i Y;
+// GCC materialises every carry of the _addcarry_u64 / _subborrow_u64 forms with setb + movzbl (a partial round compiled to
+// ~300 instructions); the carry sequences are written out instead: `sbb r32, r32` turns the flag into the 0 / 2^32-1 mask.
+THYB static inline u64 hred(u64 lo, u64 hi) {   // lo + hi * 2^64 -> lazy u64
+  const u64 hh = hi >> 32, hl = (u32)hi, t1 = (hl << 32) - hl;
+  u64 m;
+  asm("sub %[hh], %[lo]\n\t"
+      "sbb %k[m], %k[m]\n\t"     // borrow: wrapped by 2^64 = EPS (mod p)
+      "sub %[m], %[lo]\n\t"
+      "add %[t1], %[lo]\n\t"
+      "sbb %k[m], %k[m]\n\t"
+      "add %[m], %[lo]"
+      : [lo] "+r"(lo), [m] "=&r"(m) : [hh] "r"(hh), [t1] "r"(t1) : "cc");
+  return lo;
+}
+THYB static inline u64 hmul(u64 a, u64 b) { unsigned long long hi; const u64 lo = _mulx_u64(a, b, &hi); return hred(lo, hi); }
+THYB static inline u64 hsbox(u64 x) { const u64 x2 = hmul(x, x), x4 = hmul(x2, x2), x3 = hmul(x2, x); return hmul(x3, x4); }
+// sum_{i<11} c[i] * x[i] -> lazy u64.  Two carry chains (even / odd terms), each lo + hi 2^64 + top 2^128 with
+// 2^128 = -2^32 (mod p)
+#define HDOT_TERM(i, LO, HI, TOP)                                                              \
+  asm("mulx %[xm], %[l], %[h]\n\tadd %[l], %[lo]\n\tadc %[h], %[hi]\n\tadc $0, %[top]"         \
+      : [lo] "+r"(LO), [hi] "+r"(HI), [top] "+r"(TOP), [l] "=&r"(l), [h] "=&r"(h) : "d"(c[i]), [xm] "m"(x[i]) : "cc")
+THYB static inline u64 hdot11(const u64* c, const u64* x) {
+  u64 lo0 = 0, hi0 = 0, top0 = 0, lo1 = 0, hi1 = 0, top1 = 0, l, h;
+  HDOT_TERM(0, lo0, hi0, top0); HDOT_TERM(1, lo1, hi1, top1); HDOT_TERM(2, lo0, hi0, top0); HDOT_TERM(3, lo1, hi1, top1);
+  HDOT_TERM(4, lo0, hi0, top0); HDOT_TERM(5, lo1, hi1, top1); HDOT_TERM(6, lo0, hi0, top0); HDOT_TERM(7, lo1, hi1, top1);
+  HDOT_TERM(8, lo0, hi0, top0); HDOT_TERM(9, lo1, hi1, top1); HDOT_TERM(10, lo0, hi0, top0);
+  asm("add %[a], %[lo]\n\tadc %[b], %[hi]\n\tadc %[c], %[top]" : [lo] "+r"(lo0), [hi] "+r"(hi0), [top] "+r"(top0) : [a] "r"(lo1), [b] "r"(hi1), [c] "r"(top1) : "cc");
+  u64 r = hred(lo0, hi0), m;
+  top0 <<= 32;
+  asm("sub %[t], %[r]\n\tsbb %k[m], %k[m]\n\tsub %[m], %[r]" : [r] "+r"(r), [m] "=&r"(m) : [t] "r"(top0) : "cc");
+  return r;
+}
+// a * b + c with a small enough that the high word is < 2^32 (a <= 2^32): lo + h * EPS
+THYB static inline u64 hmad_small(u64 a, u64 b, u64 c) {
+  unsigned long long h;
+  u64 l = _mulx_u64(a, b, &h), m;
+  asm("add %[c], %[l]\n\tadc $0, %[h]" : [l] "+r"(l), [h] "+r"(h) : [c] "r"(c) : "cc");
+  const u64 t1 = (h << 32) - h;
+  asm("add %[t1], %[l]\n\tsbb %k[m], %k[m]\n\tadd %[m], %[l]" : [l] "+r"(l), [m] "=&r"(m) : [t1] "r"(t1) : "cc");
+  return l;
+}
+THYB static inline u64 hmad(u64 a, u64 b, u64 c) {   // a * b + c -> lazy
+  unsigned long long h;
+  u64 l = _mulx_u64(a, b, &h);
+  asm("add %[c], %[l]\n\tadc $0, %[h]" : [l] "+r"(l), [h] "+r"(h) : [c] "r"(c) : "cc");   // h <= 2^64 - 2, no overflow
+  return hred(l, h);
+}
+
+// MDS tables: column w of the matrix for rows 0..7 (one vector) and rows 8..11 (half a vector)
+alignas(64) static u64 HC8[12][8], HC4[12][4];
+// accumulator seeds: seed s = 0..7 -> the constants added before the S-box of round s+1 (s < 3), FIRST (s = 3),
+// rounds 27..29 (s = 4..6), nothing (s = 7); split into 32-bit halves
+alignas(64) static u64 HSL8[8][8], HSH8[8][8], HSL4[8][4], HSH4[8][4];
+static u64 HU2[22];                       // U2[r] = WHAT[r] . VS[r-2]
+static const bool hyb_ready = [] {
+  for (int r = 2; r < 22; r++) {
+    u64 acc = 0;
+    for (int i = 0; i < 11; i++) {
+      u64 m = mul(F_WHAT[11 * r + i], F_VS[11 * (r - 2) + i]);
+      m -= mask_of(m >= P) & P;
+      acc = add_lazy(acc, m);
+    }
+    HU2[r] = acc - (mask_of(acc >= P) & P);
+  }
+  for (int w = 0; w < 12; w++)
+    for (int row = 0; row < 12; row++) {
+      const u64 c = CIRC[((w - row) % 12 + 12) % 12] + ((w == 0 && row == 0) ? 8 : 0);
+      if (row < 8) HC8[w][row] = c; else HC4[w][row - 8] = c;
+    }
+  for (int sd = 0; sd < 8; sd++)
+    for (int i = 0; i < 12; i++) {
+      u64 c = 0;
+      if (sd < 3) c = RC[12 * (sd + 1) + i];
+      else if (sd == 3) c = F_FIRST[i];
+      else if (sd < 7) c = RC[12 * (27 + sd - 4) + i];
+      if (i < 8) { HSL8[sd][i] = c & EPS; HSH8[sd][i] = c >> 32; } else { HSL4[sd][i - 8] = c & EPS; HSH4[sd][i - 8] = c >> 32; }
+    }
+  return true;
+}();
+
+THYB static inline W hrecombine8(W al, W ah) {      // al + ah * 2^32 (mod p), al, ah < 2^43 -> lazy
+  const W a_hi = _mm512_srli_epi64(ah, 32);
+  const W c = _mm512_sub_epi64(_mm512_slli_epi64(a_hi, 32), a_hi), b = _mm512_slli_epi64(ah, 32);
+  const W t = _mm512_add_epi64(al, c), v = _mm512_add_epi64(b, t);
+  return _mm512_mask_add_epi64(v, _mm512_cmplt_epu64_mask(v, t), v, wset(EPS));
+}
+THYB static inline Y hrecombine4(Y al, Y ah) {
+  const Y a_hi = _mm256_srli_epi64(ah, 32);
+  const Y c = _mm256_sub_epi64(_mm256_slli_epi64(a_hi, 32), a_hi), b = _mm256_slli_epi64(ah, 32);
+  const Y t = _mm256_add_epi64(al, c), v = _mm256_add_epi64(b, t);
+  return _mm256_mask_add_epi64(v, _mm256_cmplt_epu64_mask(v, t), v, _mm256_set1_epi64x((long long)EPS));
+}
+
+// one full round on (v = words 0..7, q[0..3] = words 8..11): S-box everywhere, MDS, + the constants of seed `sd`
+THYB static inline void hfull(W& v, u64 (&q)[4], int sd) {
+  alignas(64) u64 lo[16], hi[16];
+  v = wsbox(v);
+  _mm512_store_si512((void*)lo, _mm512_and_si512(v, wset(EPS)));
+  _mm512_store_si512((void*)hi, _mm512_srli_epi64(v, 32));
+#pragma GCC unroll 4
+  for (int k = 0; k < 4; k++) { const u64 t = hsbox(q[k]); lo[8 + k] = t & EPS; hi[8 + k] = t >> 32; }
+  // four accumulation chains per half (a chain of twelve dependent vpmadd52luq would be 48 cycles)
+  W al[4], ah[4];
+  Y bl[4], bh[4];
+  al[0] = _mm512_load_si512((const void*)HSL8[sd]); ah[0] = _mm512_load_si512((const void*)HSH8[sd]);
+  bl[0] = _mm256_load_si256((const __m256i*)HSL4[sd]); bh[0] = _mm256_load_si256((const __m256i*)HSH4[sd]);
+  for (int k = 1; k < 4; k++) { al[k] = ah[k] = _mm512_setzero_si512(); bl[k] = bh[k] = _mm256_setzero_si256(); }
+#pragma GCC unroll 12
+  for (int w = 0; w < 12; w++) {
+    const W c = _mm512_load_si512((const void*)HC8[w]);
+    const Y d = _mm256_load_si256((const __m256i*)HC4[w]);
+    const W l = _mm512_set1_epi64((long long)lo[w]), h = _mm512_set1_epi64((long long)hi[w]);
+    al[w & 3] = _mm512_madd52lo_epu64(al[w & 3], l, c); ah[w & 3] = _mm512_madd52lo_epu64(ah[w & 3], h, c);
+    bl[w & 3] = _mm256_madd52lo_epu64(bl[w & 3], _mm512_castsi512_si256(l), d);
+    bh[w & 3] = _mm256_madd52lo_epu64(bh[w & 3], _mm512_castsi512_si256(h), d);
+  }
+  v = hrecombine8(_mm512_add_epi64(_mm512_add_epi64(al[0], al[1]), _mm512_add_epi64(al[2], al[3])),
+                  _mm512_add_epi64(_mm512_add_epi64(ah[0], ah[1]), _mm512_add_epi64(ah[2], ah[3])));
+  const Y bls = _mm256_add_epi64(_mm256_add_epi64(bl[0], bl[1]), _mm256_add_epi64(bl[2], bl[3]));
+  const Y bhs = _mm256_add_epi64(_mm256_add_epi64(bh[0], bh[1]), _mm256_add_epi64(bh[2], bh[3]));
+  alignas(32) u64 out[4];
+  _mm256_store_si256((__m256i*)out, hrecombine4(bls, bhs));
+  q[0] = out[0]; q[1] = out[1]; q[2] = out[2]; q[3] = out[3];
+}
+
+// LA = how many rounds ahead the dot product of the partial rounds is taken (1 or 2)
+template <int LA> THYB static void permute_hybrid(u64 s[12]) {
+  W v = wadd_lazy(_mm512_loadu_si512((const void*)s), _mm512_load_si512((const void*)RCW[0]));
+  u64 q[4];
+  for (int k = 0; k < 4; k++) q[k] = add_lazy(s[8 + k], RC[8 + k]);
+  for (int r = 0; r < 4; r++) hfull(v, q, r);                  // the fourth one adds FIRST
+  // x[1..] = INIT . x[1..]
+  alignas(64) u64 t[16], xs[16];
+  _mm512_store_si512((void*)t, v);
+  t[8] = q[0]; t[9] = q[1]; t[10] = q[2]; t[11] = q[3];
+  u64 x0 = t[0];
+  for (int j = 0; j < 11; j++) xs[j] = hdot11(F_INIT + 11 * j, t + 1);
+  for (int j = 11; j < 16; j++) xs[j] = 0;
+  // look-ahead: with x(r) = the words before round r's update and A(r) = WHAT[r] . x(r),
+  //   A(r+1) = WHAT[r+1] . x(r) + U[r+1] y(r)          A(r+2) = WHAT[r+2] . x(r) + U2[r+2] y(r) + U[r+2] y(r+1)
+  // so the dot product needed by round r+LA reads the vector stores of round r-1: the store -> scalar-load forwarding,
+  // the multiply of the update and the carry chains of the dot product have LA rounds of the S-box chain to finish.
+  u64 B_cur = hdot11(F_WHAT, xs);                           // round 0: A(0), no correction
+  u64 B_next = LA == 2 ? hdot11(F_WHAT + 11, xs) : 0;       // round 1: WHAT[1] . x(0); + U[1] y(0) when used
+  u64 y_prev = 0;
+  W xa = _mm512_load_si512((const void*)xs), xb = _mm512_load_si512((const void*)(xs + 8));
+  for (int r = 0; r < 22; r++) {
+    const u64 D = r ? hmad(F_U[r], y_prev, B_cur) : B_cur;  // A(r)
+    const u64 y = add_lazy(hsbox(x0), F_POST[r]);
+    x0 = hmad_small(25, y, D);
+    u64 B2 = 0;                                             // xs = x(r): before this round's update
+    if (LA == 2) { if (r + 2 < 22) B2 = hmad(HU2[r + 2], y, hdot11(F_WHAT + 11 * (r + 2), xs)); }
+    else if (r + 1 < 22) B2 = hdot11(F_WHAT + 11 * (r + 1), xs);
+    const W yv = wset(y);
+    xa = wadd_lazy(xa, wcanon(wmul(_mm512_load_si512((const void*)VSW[r]), yv)));
+    xb = wadd_lazy(xb, wcanon(wmul(_mm512_load_si512((const void*)(VSW[r] + 8)), yv)));
+    _mm512_store_si512((void*)xs, xa);
+    _mm512_store_si512((void*)(xs + 8), xb);
+    y_prev = y;
+    if (LA == 2) { B_cur = B_next; B_next = B2; } else B_cur = B2;
+  }
+  // words 0..7 = x0, xs[0..6]; words 8..11 = xs[7..10]; + the constants of round 26
+  v = wadd_lazy(_mm512_alignr_epi64(xa, wset(x0), 7), _mm512_load_si512((const void*)RCW[26]));
+  for (int k = 0; k < 4; k++) q[k] = add_lazy(xs[7 + k], RC[12 * 26 + 8 + k]);
+  for (int r = 0; r < 4; r++) hfull(v, q, 4 + r);
+  v = wcanon(v);
+  _mm512_storeu_si512((void*)s, v);
+  for (int k = 0; k < 4; k++) s[8 + k] = q[k] - (mask_of(q[k] >= P) & P);
+}
 #endif
 
-// variant: 0 = scalar, 1 = AVX2, 2 = AVX-512 dense, 3 = AVX-512 full rounds + sparse partial rounds (tests compare them; returns 0 if the CPU lacks the extension)
+// variant: 0 = scalar, 1 = AVX2, 2 = AVX-512 dense, 3 = AVX-512 full rounds + sparse partial rounds, 4, 5 = hybrid (AVX-512 IFMA +
+// BMI2; dot products one / two rounds ahead) (tests compare them; returns 0 if the CPU lacks the extension)
+#if defined(__x86_64__)
+static bool have_hybrid() {
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512bw") &&
+                         __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512ifma") && __builtin_cpu_supports("bmi2") &&
+                         cw_ready && rcw_ready && vsw_ready && hyb_ready;
+  return ok;
+}
+#endif
+
 extern "C" int sb_host_poseidon_permute_variant(u64 s[12], int variant) {
 #if defined(__x86_64__)
+  if (variant == 4 || variant == 5) {
+    if (!have_hybrid()) return 0;
+    if (variant == 4) permute_hybrid<1>(s); else permute_hybrid<2>(s);
+    return 1;
+  }
   if (variant == 2 || variant == 3) {
     if (!(__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512bw") &&
           __builtin_cpu_supports("avx512vl"))) return 0;
@@ -326,6 +523,7 @@ void sb_host_poseidon_permute(u64 s[12]) {
 #if defined(__x86_64__)
   static const bool have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") &&
                                   __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && cw_ready && rcw_ready && vsw_ready;
+  if (have_hybrid()) { permute_hybrid<1>(s); return; }
   if (have_avx512) { permute_avx512_sparse(s); return; }
   static const bool have_avx2 = __builtin_cpu_supports("avx2") && cv_ready;
   if (have_avx2) { permute_avx2(s); return; }

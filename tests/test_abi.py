@@ -75,7 +75,7 @@ def test_host_transcript_permutation_variants_match_oracle():
     states = [np.zeros(12, np.uint64), np.arange(12, dtype=np.uint64), np.full(12, O.P - 1, np.uint64),
               np.full(12, 2 ** 64 - 1, np.uint64)] + [rng.integers(0, 2 ** 63, 12, dtype=np.uint64) * np.uint64(2) for _ in range(50)]
     ran = 0
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4, 5):
         for st in states:
             got = st.copy()
             if not L.sb_host_poseidon_permute_variant(got.ctypes.data_as(C.c_void_p), variant):
