@@ -680,12 +680,28 @@ __global__ void __launch_bounds__(64) leaf_sponge_st_kernel(const u64* __restric
 // < 2^27.  The pair packing (28 PRMT on the ALU pipe) is shared by the three rows a thread owns, which is why this
 // variant exists for the three-words-per-thread layout only.
 // ---------------------------------------------------------------------------------------------------------
+// VAR != 0 (lab only, tools/perf/poseidon_lab dp): the warp that owns words 0..2 -- the only one with an S-box in the 22
+// partial rounds -- differs from block to block (1: by block index, 2: by arrival order on the SM).  The idea was that
+// warp k of every block sits on sub-partition k, so one scheduler would issue 22 x ~75 instructions per permutation
+// more than the others.  Measured (profiles/r2_poseidon_lab_dp_roles.txt): both are 2-10 % SLOWER -- the hardware already
+// staggers the warp slots of successive blocks over the sub-partitions, and a software rotation undoes part of that.
+static __device__ unsigned dp_role_counter[256];
+template <int VAR>
 __global__ void __launch_bounds__(128) leaf_sponge_dp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                              uint32_t n_leaves, unsigned log_block,
                                                              u64* __restrict__ digests) {
   constexpr int W = 3, NW = W + 11, NP = NW / 2;
   __shared__ __align__(16) u64 xch[2][24][32];
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  unsigned rot = 0;
+  if (VAR == 1) rot = blockIdx.x + blockIdx.x / 148;           // lab: assumes round-robin placement over 148 SMs
+  if (VAR == 2) {                                               // arrival order on this SM: balanced whatever the block scheduler does
+    __shared__ unsigned s_rot;
+    if (threadIdx.x == 0) { unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); s_rot = atomicAdd(&dp_role_counter[sm & 255], 1u); }
+    __syncthreads();
+    rot = s_rot;
+  }
+  const unsigned wid = ((threadIdx.x >> 5) + rot) & 3;
   const unsigned w0 = wid * W;
   const uint32_t pos_raw = blockIdx.x * 32 + lane;
   const bool live = pos_raw < n_leaves;

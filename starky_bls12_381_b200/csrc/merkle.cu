@@ -85,7 +85,7 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
   } else if (kind == 12) {
     LAUNCH(ctx, (leaf_sponge_w12_kernel<0, 1>), groups, 384, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 4) {
-    LAUNCH(ctx, leaf_sponge_dp_kernel, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+    LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 5) {
     LAUNCH(ctx, leaf_sponge_ds_kernel, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 3) {

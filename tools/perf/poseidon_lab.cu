@@ -234,7 +234,8 @@ int main(int argc, char** argv) {
     unsigned g32 = (nl + 31) / 32;
     for (int rep = 0; rep < 2; rep++) {
       float ms = time_ms([&] {
-        if (wps == 43) leaf_sponge_dp_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
+        if (wps == 43) leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 44) leaf_sponge_dp_kernel<2><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 45) leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 101) leaf_sponge_st_kernel<<<g32, 32>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 130) leaf_sponge_sp_kernel<0><<<g32, 416>>>(d_cols, ll, nl, 0, d_dig);
@@ -248,6 +249,35 @@ int main(int argc, char** argv) {
       }, 1);
       printf("ws<%d> N=%u C=%u: %.3f ms\n", wps, nl, ll, ms);
     }
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "dp")) {   // throughput-bound shapes: which warp owns the partial-round S-box
+    struct Shape { const char* name; uint32_t n_leaves, leaf_len; };
+    for (const Shape& sh : {Shape{"ECC-like", 32768, 3339}, Shape{"FE-like", 32768, 8003}, Shape{"FE/4", 32768, 18382}, Shape{"FE 1/2 box", 16384, 18382}}) {
+      const size_t cells = (size_t)sh.n_leaves * sh.leaf_len;
+      u64 *d_cols, *d_ref, *d_dig;
+      CK(cudaMalloc(&d_cols, 8 * cells)); CK(cudaMalloc(&d_ref, 32ull * sh.n_leaves)); CK(cudaMalloc(&d_dig, 32ull * sh.n_leaves));
+      fill_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_cols, cells);
+      CK(cudaDeviceSynchronize());
+      const double perms = (double)((sh.leaf_len + 7) / 8) * sh.n_leaves;
+      const unsigned g32 = (sh.n_leaves + 31) / 32;
+      std::vector<u64> ref(4ull * sh.n_leaves), got(4ull * sh.n_leaves);
+      printf("%-10s N=%6u C=%6u\n", sh.name, sh.n_leaves, sh.leaf_len);
+      auto run = [&](const char* name, auto launch, bool is_ref) {
+        CK(cudaMemset(d_dig, 0, 32ull * sh.n_leaves));
+        float t = time_ms(launch);
+        CK(cudaMemcpy(is_ref ? ref.data() : got.data(), d_dig, 32ull * sh.n_leaves, cudaMemcpyDeviceToHost));
+        bool ok = is_ref || !memcmp(got.data(), ref.data(), 32ull * sh.n_leaves);
+        printf("    %-46s %9.3f ms  %7.1f Mperm/s  %s\n", name, t, perms / t / 1e3, ok ? "ok" : "MISMATCH");
+      };
+      for (int rep = 0; rep < 2; rep++) {
+        run("dp<0> words 0..2 always on warp 0", [&] { leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, true);
+        run("dp<1> S-box warp rotates by block index", [&] { leaf_sponge_dp_kernel<1><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+        run("dp<2> S-box warp rotates by arrival on the SM", [&] { leaf_sponge_dp_kernel<2><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      }
+      cudaFree(d_cols); cudaFree(d_ref); cudaFree(d_dig);
+    }
+    printf("lab done\n");
     return 0;
   }
   const bool only_sp = argc > 1 && !strcmp(argv[1], "sp");     // the latency-bound shapes and the sp variants only
@@ -340,7 +370,9 @@ int main(int argc, char** argv) {
     run("ws<6>  (2 words/thread)", [&] { leaf_sponge_ws_kernel<6><<<g32, 192>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("ws<12> (1 word/thread)", [&] { leaf_sponge_ws_kernel<12><<<g32, 384>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("w12<0> (two-barrier partial)", [&] { leaf_sponge_w12_kernel<0><<<g32, 384>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
-    run("dp (3 words/thread, dp2a MDS)", [&] { leaf_sponge_dp_kernel<<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("dp (3 words/thread, dp2a MDS)", [&] { leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("dp<1> S-box warp rotates by block index", [&] { leaf_sponge_dp_kernel<1><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
+    run("dp<2> S-box warp rotates by arrival on the SM", [&] { leaf_sponge_dp_kernel<2><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("ds (dp2a full + sparse partial)", [&] { leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("st (sparse, one thread per leaf, block 32)", [&] { leaf_sponge_st_kernel<<<g32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
     run("st (sparse, one thread per leaf, block 64)", [&] { leaf_sponge_st_kernel<<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); });
