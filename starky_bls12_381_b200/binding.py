@@ -214,18 +214,34 @@ def deserialize_words(data, fmt, p=None):
     return q, Proof(cp).words
 
 
+class _ProofMemory:
+    """Keeps one sb_proof alive for as long as a numpy view of its words exists (the array's base is this object)."""
+
+    def __init__(self, cproof, n_words):
+        self._cp = cproof
+        self.__array_interface__ = {"shape": (int(n_words),), "typestr": "<u8", "version": 3,
+                                    "data": (C.cast(cproof.contents.words, C.c_void_p).value, False)}
+
+    def __del__(self):
+        cp, self._cp = getattr(self, "_cp", None), None
+        if cp:
+            try:
+                lib().sb_proof_free(cp)
+            except Exception:
+                pass
+
+
 class Proof:
-    """Owns one sb_proof; `words` is a numpy view of the flat POD (copied out on construction)."""
+    """Owns one sb_proof; `words` is a zero-copy numpy view of the flat POD in the library's pinned buffer.  The buffer goes
+    back to the library's pool when the last view of it is dropped (no 50 MB copy per FinalExp proof, as in the Rust shim)."""
 
     def __init__(self, cproof):
         c = cproof.contents
         self.layout = ProofLayout()
         C.memmove(C.byref(self.layout), C.byref(c.layout), C.sizeof(ProofLayout))
-        n = self.layout.total_words
-        self.words = np.ctypeslib.as_array(c.words, shape=(n,)).copy()
         self.timings = {k: getattr(c, k) for k in ("ms_h2d", "ms_trace_commit", "ms_quotient", "ms_quotient_commit",
                                                    "ms_openings", "ms_fri", "ms_d2h", "ms_total")}
-        lib().sb_proof_free(cproof)
+        self.words = np.asarray(_ProofMemory(cproof, self.layout.total_words))
 
     def field(self, name, count):
         off = getattr(self.layout, name)

@@ -83,7 +83,7 @@ void sb_destroy(sb_ctx* ctx) {
   for (auto& kv : ctx->coset_scale) kv.second.release();
   for (auto& kv : ctx->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
   DevBuf* bufs[] = {&ctx->trace, &ctx->staging, &ctx->coeffs, &ctx->lde, &ctx->tree, &ctx->qvals, &ctx->qcoeffs, &ctx->qlde,
-                    &ctx->qtree, &ctx->pis, &ctx->weights, &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->peer_tab};
+                    &ctx->qtree, &ctx->pis, &ctx->weights, &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->peer_tab, &ctx->sponge};
   for (DevBuf* b : bufs) b->release();
   air_release_all(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -238,14 +238,27 @@ void ingest_and_commit_trace(sb_ctx* ctx, const sb_params* p, const void* trace,
   ctx->coeffs.ensure(8 * n * C);
   ctx->lde.ensure(8 * N * C);
   ctx->tree.ensure(32 * 2 * N);
-  const size_t slab_cols = std::max<size_t>(1, (32u << 20) / (8 * n));
+  // SB_SLAB_BYTES: tests shrink the slabs so that small traces take the multi-slab path too
+  size_t slab_bytes = 32u << 20;
+  if (const char* e = getenv("SB_SLAB_BYTES")) slab_bytes = std::max<size_t>(64 * n, strtoull(e, nullptr, 10));
+  const size_t slab_cols = std::max<size_t>(8, slab_bytes / (8 * n) / 8 * 8);
+  // leaf hashing follows the slabs: the sponge absorbs columns in order, so a group of slabs is hashed as soon as it is
+  // extended, while the next ones cross PCIe -- the copy is hidden behind K2 as well as K1.  hash_group slabs per launch
+  // (>= 2048 columns, SB_HASH_GROUP_COLS: the state save / restore and the launch are noise).  SB_NO_STREAM_HASH=1: hash
+  // after the last slab.
+  const bool stream_hash = C > 2 * slab_cols && sb_hash_leaves_streamable((uint32_t)C) && !getenv("SB_NO_STREAM_HASH");
+  size_t group_cols = 2048;
+  if (const char* e = getenv("SB_HASH_GROUP_COLS")) group_cols = std::max<size_t>(8, strtoull(e, nullptr, 10));
+  const size_t hash_group = std::max<size_t>(1, group_cols / slab_cols);
+  if (stream_hash) ctx->sponge.ensure(8ull * 12 * N);
   u64* stage = nullptr;
   if (layout == SB_TRACE_COLS_U64_PTRS) stage = (u64*)pinned_staging(ctx, 2 * slab_cols * 8 * n);
   // the copy stream starts where the main stream is now (earlier work may still be using ctx->trace)
   CUDA_CHECK(cudaEventRecord(ctx->fork_ev, ctx->stream));
   CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
   stage_begin(ctx, "lde");
-  size_t i = 0;
+  size_t i = 0, hashed = 0;          // columns [0, hashed) are in the sponge state
+  const size_t n_slabs = (C + slab_cols - 1) / slab_cols;
   for (size_t c0 = 0; c0 < C; c0 += slab_cols, i++) {
     const size_t cnt = std::min(slab_cols, C - c0);
     cudaEvent_t ev = ctx->slab_ev[i % 4];
@@ -264,12 +277,20 @@ void ingest_and_commit_trace(sb_ctx* ctx, const sb_params* p, const void* trace,
     CUDA_CHECK(cudaEventRecord(ev, ctx->copy_stream));
     CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ev, 0));
     sb_lde_trace(ctx, d_slab, ctx->coeffs.as<u64>() + c0 * n, ctx->lde.as<u64>() + c0 * N, (uint32_t)cnt, p->log_n, p->rate_bits);
+    if (i + 1 == n_slabs) stage_end(ctx, "lde");
+    if (stream_hash && ((i + 1) % hash_group == 0 || i + 1 == n_slabs)) {
+      if (hashed == 0) stage_begin(ctx, "leaf_hash");          // (in this path the two stage timers overlap)
+      sb_hash_leaves_stream(ctx, ctx->lde.as<u64>() + hashed * N, (uint32_t)(c0 + cnt - hashed), (uint32_t)N, p->log_n,
+                            ctx->sponge.as<u64>(), hashed == 0, i + 1 == n_slabs, ctx->tree.as<u64>());
+      hashed = c0 + cnt;
+    }
   }
-  stage_end(ctx, "lde");
   if (h2d_done) CUDA_CHECK(cudaEventRecord(h2d_done, ctx->copy_stream));
   ctx->have_trace = true;
-  stage_begin(ctx, "leaf_hash");
-  sb_hash_leaves_device(ctx, ctx->lde.as<u64>(), (uint32_t)C, (uint32_t)N, p->log_n, ctx->tree.as<u64>());
+  if (!stream_hash) {
+    stage_begin(ctx, "leaf_hash");
+    sb_hash_leaves_device(ctx, ctx->lde.as<u64>(), (uint32_t)C, (uint32_t)N, p->log_n, ctx->tree.as<u64>());
+  }
   stage_end(ctx, "leaf_hash");
   stage_begin(ctx, "merkle");
   sb_merkle_levels(ctx, ctx->tree.as<u64>(), (uint32_t)N, p->cap_height);

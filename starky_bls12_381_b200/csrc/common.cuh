@@ -85,6 +85,7 @@ struct sb_ctx {
   DevBuf pis;          // public inputs
   DevBuf weights;      // alpha powers
   DevBuf scratch0, scratch1, scratch2, scratch3, peer_tab;
+  DevBuf sponge;       // [12][N] leaf-sponge state between the column slabs of a streamed trace commitment
   void* pinned = nullptr; size_t pinned_cap = 0;
   sb_multi* multi = nullptr;   // sb_init(devices, n > 1): one rank context per device behind this ctx (group.cu)
 };
@@ -126,5 +127,8 @@ void sb_transpose_rows_to_cols(sb_ctx* ctx, const void* d_rows, u64* d_cols, uin
 // merkle.cu
 void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, uint32_t n_leaves, unsigned log_block, u64* d_digests);
 void sb_merkle_levels(sb_ctx* ctx, u64* d_tree, uint32_t n_leaves, unsigned cap_height);
+bool sb_hash_leaves_streamable(uint32_t leaf_len_total);
+void sb_hash_leaves_stream(sb_ctx* ctx, const u64* d_cols, uint32_t n_cols, uint32_t n_leaves, unsigned log_block, u64* d_state,
+                           bool first, bool last, u64* d_digests);
 void sb_poseidon_permute_device(sb_ctx* ctx, u64* d_states, uint32_t count);
 void sb_digests_to_leaf_order(sb_ctx* ctx, const u64* d_pos_order, u64* d_leaf_order, uint32_t n_leaves, unsigned log_block);

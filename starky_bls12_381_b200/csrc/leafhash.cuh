@@ -373,7 +373,11 @@ __device__ long long* g_sp_trace;      // [64] clock64 stamps of block 0 / lane 
 template <int VAR>
 __global__ void __launch_bounds__((VAR & 1) ? 512 : 416) leaf_sponge_sp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                              uint32_t n_leaves, unsigned log_block,
-                                                             u64* __restrict__ digests) {
+                                                             u64* __restrict__ digests,
+                                                             const u64* __restrict__ state_in = nullptr,
+                                                             u64* __restrict__ state_out = nullptr) {
+  // state_in / state_out ([12][n_leaves], position order): the sponge fed in column order, one slab of columns per launch
+  // (capi.cu: the leaf hashing of slab k runs while slab k+1 crosses PCIe); leaf_len % 8 == 0 on every launch but the last
   __shared__ __align__(16) u64 xch[2][24][32];
   __shared__ __align__(16) u64 ybuf[3][32];
   __shared__ __align__(16) u64 ebuf[3][12][32];
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__((VAR & 1) ? 512 : 416) leaf_sponge_sp_kernel(c
   const u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 
   u64 s = 0, nx = 0;
+  if (state_in && !reducer) s = state_in[(size_t)wid * n_leaves + pos];
   const uint32_t n_chunks = (leaf_len + 7) / 8;
   if (!reducer && wid < 8 && wid < leaf_len) nx = cols[(size_t)wid * n_leaves + pos];
   unsigned xb = 0;
@@ -566,7 +571,9 @@ __global__ void __launch_bounds__((VAR & 1) ? 512 : 416) leaf_sponge_sp_kernel(c
 #ifdef SP_TRACE
   // (the chunk loop variable is out of scope here; the end-of-permutation stamp is taken inside the loop)
 #endif
-  if (live && !reducer && wid < 4) digests[4ull * leaf_index_of(pos, log_block) + wid] = gl_canon(s);
+  if (state_out) {
+    if (live && !reducer) state_out[(size_t)wid * n_leaves + pos] = s;
+  } else if (live && !reducer && wid < 4) digests[4ull * leaf_index_of(pos, log_block) + wid] = gl_canon(s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -689,7 +696,9 @@ static __device__ unsigned dp_role_counter[256];
 template <int VAR>
 __global__ void __launch_bounds__(128) leaf_sponge_dp_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                              uint32_t n_leaves, unsigned log_block,
-                                                             u64* __restrict__ digests) {
+                                                             u64* __restrict__ digests,
+                                                             const u64* __restrict__ state_in = nullptr,
+                                                             u64* __restrict__ state_out = nullptr) {
   constexpr int W = 3, NW = W + 11, NP = NW / 2;
   __shared__ __align__(16) u64 xch[2][24][32];
   const unsigned lane = threadIdx.x & 31;
@@ -710,7 +719,7 @@ __global__ void __launch_bounds__(128) leaf_sponge_dp_kernel(const u64* __restri
 
   u64 s[W], nx[W];
 #pragma unroll
-  for (int k = 0; k < W; k++) { s[k] = 0; nx[k] = 0; }
+  for (int k = 0; k < W; k++) { s[k] = state_in ? state_in[(size_t)(w0 + k) * n_leaves + pos] : 0; nx[k] = 0; }
   const uint32_t n_chunks = (leaf_len + 7) / 8;
   auto fetch = [&](uint32_t chunk) {
 #pragma unroll
@@ -791,7 +800,12 @@ __global__ void __launch_bounds__(128) leaf_sponge_dp_kernel(const u64* __restri
 #pragma unroll 1
     for (int rd = 26; rd < 30; rd++) full_round(rd);
   }
-  if (live) {
+  if (state_out) {
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < W; k++) state_out[(size_t)(w0 + k) * n_leaves + pos] = s[k];
+    }
+  } else if (live) {
     u64* d = digests + 4ull * leaf_index_of(pos, log_block);
 #pragma unroll
     for (int k = 0; k < W; k++)

@@ -96,6 +96,23 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
   }
 }
 
+// The same sponge fed one slab of columns at a time (capi.cu ingest_and_commit_trace: the trace arrives over PCIe in
+// column slabs and the sponge absorbs columns in order, so slab k is hashed while slab k+1 is copied and extended).
+// d_state = [12][n_leaves] u64 carried between launches; n_cols % 8 == 0 on every launch but the last; the last launch
+// writes the digests.  Only the two product kernels (sp: few leaves, dp: many leaves) take part.
+bool sb_hash_leaves_streamable(uint32_t leaf_len_total) { return leaf_len_total > 64 && !getenv("SB_LEAF_KERNEL"); }
+void sb_hash_leaves_stream(sb_ctx* ctx, const u64* d_cols, uint32_t n_cols, uint32_t n_leaves, unsigned log_block, u64* d_state,
+                           bool first, bool last, u64* d_digests) {
+  if (!last && (n_cols % 8)) SB_THROW(SB_EINVAL, "internal: a %u-column slab inside a streamed leaf sponge", n_cols);
+  const uint32_t groups = (n_leaves + 31) / 32;
+  const u64* in = first ? nullptr : d_state;
+  u64* out = last ? nullptr : d_state;
+  if ((uint64_t)n_leaves <= 64ull * ctx->sm_count)
+    LAUNCH(ctx, leaf_sponge_sp_kernel<0>, groups, 416, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
+  else
+    LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
+}
+
 // one level: out[i] = two_to_one(in[2i], in[2i+1])
 __global__ void merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, uint32_t n_out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

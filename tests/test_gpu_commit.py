@@ -90,6 +90,30 @@ def test_lde_commit_matches_oracle(ctx, log_n, n_cols, rate_bits, full):
     assert np.array_equal(ctx.coeffs(p), want["coeffs"][:, bitrev_perm(log_n)])
 
 
+@pytest.mark.parametrize("log_n,n_cols,rate_bits", [(5, 300, 3), (7, 203, 2), (6, 1037, 1), (10, 70, 5)])
+@pytest.mark.parametrize("layout", ["colmajor", "col_ptrs"])
+def test_streamed_leaf_sponge_matches_oracle(ctx, monkeypatch, log_n, n_cols, rate_bits, layout):
+    """The host-trace path hashes the leaves slab by slab behind the copy (capi.cu ingest_and_commit_trace): with small
+    slabs every shape here is fed to the sponge in several launches (sp kernel: few leaves, dp kernel: many leaves, a
+    last slab that is not a multiple of 8 columns) and must give the digests of the one-launch path and of the oracle."""
+    rng = np.random.default_rng(77 * log_n + n_cols)
+    p = custom(log_n, n_cols, rate_bits)
+    trace = random_trace(rng, n_cols, log_n, full_width=True)
+    want = O.lde_commit(to_oracle_params(p), trace)
+    monkeypatch.setenv("SB_SLAB_BYTES", str(64 << log_n))          # 8 columns per slab
+    monkeypatch.setenv("SB_HASH_GROUP_COLS", "64")                 # one sponge launch per 64 columns
+    if layout == "colmajor":
+        got = ctx.lde_commit(p, trace)
+    else:
+        cols = [np.ascontiguousarray(trace[c]).copy() for c in range(n_cols)]
+        ptrs = np.array([c.ctypes.data for c in cols], dtype=np.uint64)
+        got = ctx.lde_commit(p, ptrs, sb.TraceLayout.COLS_U64_PTRS)
+    assert np.array_equal(got["digests"], want["digests"])
+    assert np.array_equal(got["cap"], want["cap"])
+    monkeypatch.setenv("SB_NO_STREAM_HASH", "1")
+    assert np.array_equal(ctx.lde_commit(p, trace)["digests"], want["digests"])
+
+
 def test_trace_layouts_agree(ctx):
     rng = np.random.default_rng(7)
     p = custom(6, 45, 1)
