@@ -90,7 +90,7 @@ def test_lde_commit_matches_oracle(ctx, log_n, n_cols, rate_bits, full):
     assert np.array_equal(ctx.coeffs(p), want["coeffs"][:, bitrev_perm(log_n)])
 
 
-@pytest.mark.parametrize("log_n,n_cols,rate_bits", [(5, 300, 3), (7, 203, 2), (6, 1037, 1), (10, 70, 5)])
+@pytest.mark.parametrize("log_n,n_cols,rate_bits", [(5, 300, 3), (7, 203, 2), (6, 1037, 1), (11, 70, 4), (12, 141, 2)])
 @pytest.mark.parametrize("layout", ["colmajor", "col_ptrs"])
 def test_streamed_leaf_sponge_matches_oracle(ctx, monkeypatch, log_n, n_cols, rate_bits, layout):
     """The host-trace path hashes the leaves slab by slab behind the copy (capi.cu ingest_and_commit_trace): with small
