@@ -7,11 +7,15 @@
 //     32-leaf group per SM walking a chain of ceil(C/8) permutations, and a large share of the proof is the strictly
 //     sequential host transcript.  Several of them in flight on one GPU fill each other's gaps (2 in flight: 212 -> 118 ms
 //     per MillerLoop proof, 4: 78 ms).
-//   * many-leaf proofs (FinalExp, ECCAgg: 32768 leaves) fill the GPU on their own; next to one of them a latency-bound
-//     chain starves (MillerLoop 225 -> 937 ms), so they run alone on their device.
-// Rule per device: a throughput-bound job starts only on an idle device and keeps it to itself -- and always on the
-// device's first context, so that its tens of GB of buffers exist once; latency-bound jobs share a device up to the
-// number of contexts it has.  Jobs are taken in decreasing estimated cost.
+//   * many-leaf proofs (FinalExp, ECCAgg: 32768 leaves) fill the GPU on their own.  With a device-resident trace their leaf
+//     sponge is ONE launch whose blocks hold every SM for the whole chain, and a latency-bound chain next to it starves
+//     (MillerLoop 225 -> 937 ms): such a job runs alone on its device.  With a host trace the sponge follows the column
+//     slabs (capi.cu: one launch per >= 2048 columns, ~12 ms), the small jobs' blocks get in at every launch boundary and
+//     fill the issue slots the dp kernel leaves (it is heavy-pipe bound at 64 % issue): the full BLS set on one GPU,
+//     918 -> 806 ms, FinalExp 608 -> 773 ms with both MillerLoops, both PairingPrecomps and FP12Mul inside it.
+// Rule per device: a throughput-bound job always runs on the device's first context, so that its tens of GB of buffers
+// exist once, and one at a time; latency-bound jobs share a device up to the number of contexts it has, next to a
+// throughput-bound job only if that one streams its trace from the host.  Jobs are taken in decreasing estimated cost.
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -22,7 +26,7 @@
 
 namespace {
 
-struct DeviceState { int running_few = 0; bool running_big = false; };
+struct DeviceState { int running_few = 0; bool running_big = false, big_is_streamed = false; };
 
 double job_cost(const sb_params& p) {
   // permutations of the trace commitment dominate every proof; a long per-leaf chain costs latency on top
@@ -50,6 +54,7 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
   auto is_big = [&](const sb_job& j, const sb_ctx* ctx) {
     return (uint64_t(1) << (j.params.log_n + j.params.rate_bits)) > 64ull * (uint64_t)ctx->sm_count;
   };
+  const bool mix = !(getenv("SB_SCHED_MIX") && atoi(getenv("SB_SCHED_MIX")) == 0);   // SB_SCHED_MIX=0: never share a device with a big job
   auto worker = [&](int c) {
     sb_ctx* ctx = ctxs[c];
     const int d = dev_of(c);
@@ -67,8 +72,9 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
             if (taken[k]) continue;
             any_left = true;
             const bool b = is_big(jobs[k], ctx);
-            if (st.running_big) break;                              // the device belongs to a throughput-bound job
-            if (b && (!takes_big || st.running_few > 0)) continue;  // needs an idle device and its first context; a smaller job may still fit
+            const bool streamed = mix && (jobs[k].layout == SB_TRACE_COLMAJOR_U64 || jobs[k].layout == SB_TRACE_COLS_U64_PTRS);
+            if (st.running_big && (b || !st.big_is_streamed)) break;   // the device belongs to a throughput-bound job
+            if (b && (!takes_big || (st.running_few > 0 && !streamed))) continue;  // needs its device's first context (and an idle device unless it streams); a smaller job may still fit
             pick = k; big = b;
             break;
           }
@@ -78,7 +84,10 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
         if (pick < 0) return;                                       // nothing left to take (others are finishing)
         taken[pick] = 1;
         DeviceState& st = dev[d];
-        if (big) st.running_big = true; else st.running_few++;
+        if (big) {
+          st.running_big = true;
+          st.big_is_streamed = mix && (jobs[pick].layout == SB_TRACE_COLMAJOR_U64 || jobs[pick].layout == SB_TRACE_COLS_U64_PTRS);
+        } else st.running_few++;
       }
       sb_job& j = jobs[pick];
       const auto t0 = std::chrono::steady_clock::now();
