@@ -291,15 +291,20 @@ def full_set_assignment(world):
     return full_set_assignment_of(FULL_SET, world)
 
 
-def full_set_plan(world):
-    """How the seven proofs are laid over `world` GPUs.  From four GPUs on, the critical path (FinalExp, ~630 ms on one GPU)
-    is sharded over half of them (SURVEY 8e "proof-level parallelism on top") and the other six proofs share the rest;
-    below that whole proofs are assigned longest-first.  Returns (ranks of the sharded FinalExp proof or [], per-rank lists)."""
+def full_set_plan(world, fe_over="all"):
+    """How the seven proofs are laid over `world` GPUs.  From four GPUs on, the critical path (FinalExp, ~600 ms on one GPU)
+    is sharded (SURVEY 8e "proof-level parallelism on top"); below that whole proofs are assigned longest-first.
+      fe_over = "all":  FinalExp over every GPU, the other six proofs longest-first over the same GPUs on their other
+                        contexts, at the same time (a FinalExp shard of <= 9472 leaves per GPU is latency-bound like them);
+      fe_over = "half": FinalExp over half of the GPUs, the other six proofs share the rest (the round-1 plan).
+    Returns (ranks of the sharded FinalExp proof or [], per-rank lists of whole proofs)."""
     if world < 4:
         return [], full_set_assignment(world)
+    rest_names = [x for x in FULL_SET if x != "final_exp"]
+    if fe_over == "all":
+        return list(range(world)), full_set_assignment_of(rest_names, world)
     k = world // 2
-    rest = full_set_assignment_of([x for x in FULL_SET if x != "final_exp"], world - k)
-    return list(range(k)), [[] for _ in range(k)] + rest
+    return list(range(k)), [[] for _ in range(k)] + full_set_assignment_of(rest_names, world - k)
 
 
 def full_set_assignment_of(names, world):
@@ -328,16 +333,32 @@ def run_full_set(sb, contexts, names, rank, timed, sharded_job=None):
         jobs.append((p, host.data_ptr(), sb.TraceLayout.COLMAJOR_U64, pis))
     per = []
 
+    def batch():
+        for name, (res, ms) in zip(names, prove_batch(contexts, jobs)):
+            if isinstance(res, Exception):
+                raise res
+            per.append((name, ms))
+
     def go():
+        th, err = None, []
+        if jobs and sharded_job is not None:      # this rank's whole proofs run next to its FinalExp shard, on other contexts
+            def guarded():
+                try:
+                    batch()
+                except Exception as e:            # noqa: BLE001
+                    err.append(e)
+            th = threading.Thread(target=guarded)
+            th.start()
         if sharded_job is not None:
             t0 = time.perf_counter()
             sharded_job()
             per.append(("final_exp(sharded)", 1e3 * (time.perf_counter() - t0)))
-        if jobs:
-            for name, (res, ms) in zip(names, prove_batch(contexts, jobs)):
-                if isinstance(res, Exception):
-                    raise res
-                per.append((name, ms))
+        if th is not None:
+            th.join()
+            if err:
+                raise err[0]
+        elif jobs:
+            batch()
     go()                 # warm-up: buffers of every shape allocated, constraint programs bound
     go()                 # (the scheduler may give a context another shape the second time: settle the buffer sizes)
     per.clear()
@@ -367,6 +388,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="sharded legs: NCCL all-to-all after K1 instead of K1 storing into peer memory")
     ap.add_argument("--no-full-set", action="store_true", help="skip the 7-proof BLS set (BASELINE configs[4])")
+    ap.add_argument("--fe-over", default="all", choices=["all", "half"],
+                    help="7-proof set from 4 GPUs on: FinalExp sharded over all GPUs next to the other proofs, or over half of them")
     ap.add_argument("--bundled", action="store_true",
                     help="N=1: also prove the seven proofs of the reference's bundled light_client_update_period_1052/1053 inputs "
                          "(valid traces from the witness generators, ~1 min of host-side trace generation outside the timed region)")
@@ -587,7 +610,7 @@ def main():
         def full_leg():
             if args.no_full_set:
                 return None
-            fe_ranks, per_rank = full_set_plan(world)
+            fe_ranks, per_rank = full_set_plan(world, args.fe_over)
             mine = per_rank[rank]
             sharded_job, sub = None, None
             if fe_ranks:
@@ -601,15 +624,18 @@ def main():
                     slocal = torch.from_numpy(srng.integers(0, 1 << 32, (sg, fi.num_rows), dtype=np.uint64).view(np.int64)).pin_memory()
                     spis = np.random.Generator(np.random.PCG64(0xB2400099)).integers(0, 1 << 32, fi.public_inputs, dtype=np.uint64)
                     sharded_job = lambda: sub.prove(sp, slocal.data_ptr(), spis, on_device=False, fused=not args.no_fused)
-            dt_full, per = run_full_set(sb, [ctx] + more, mine, rank, timed, sharded_job)
+            # the contexts of the whole proofs: not the one the FinalExp shard of this rank is running on
+            dt_full, per = run_full_set(sb, more if sharded_job is not None else [ctx] + more, mine, rank, timed, sharded_job)
             out = {"workload": "2 x PairingPrecomp + 2 x MillerLoop + FP12Mul + FinalExp + ECCAgg (BASELINE configs[4]), synthetic traces, "
                                "end to end from pinned host memory", "gpus": world, "ms": 1e3 * dt_full,
                    "assignment": per_rank, "final_exp_sharded_over_ranks": fe_ranks,
                    "final_exp_k1_stores_into_peer_memory": bool(sub is not None and sub.member and sub.fused_ok and not args.no_fused) if fe_ranks else None,
                    "rank0_proof_ms": {("%s#%d" % (k, i)): round(v, 2) for i, (k, v) in enumerate(per)},
-                   "note": "from 4 GPUs on FinalExp is sharded over half of them and the other six proofs share the rest; otherwise "
-                           "longest-first assignment of whole proofs to GPUs; per GPU the latency-bound proofs (<= 9472 leaves) run up to four in "
-                           "flight first, then the throughput-bound ones one at a time; ms = makespan, max over ranks"}
+                   "plan": args.fe_over if fe_ranks else "whole proofs",
+                   "note": "from 4 GPUs on FinalExp is sharded over the GPUs named above and the other six proofs are assigned longest-first "
+                           "(plan all: to the same GPUs, running next to the FinalExp shards on other contexts; plan half: to the other "
+                           "GPUs); below 4 GPUs whole proofs longest-first; per GPU sb_prove_batch schedules the proofs; ms = makespan, "
+                           "max over ranks"}
             if sub is not None:
                 sub.close()
             return out
