@@ -55,17 +55,30 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
     return (uint64_t(1) << (j.params.log_n + j.params.rate_bits)) > 64ull * (uint64_t)ctx->sm_count;
   };
   const bool mix = !(getenv("SB_SCHED_MIX") && atoi(getenv("SB_SCHED_MIX")) == 0);   // SB_SCHED_MIX=0: never share a device with a big job
+  // SB_SCHED_TRACE=1: one stderr line per job (context, start and end in ms since the call)
+  const bool trace = getenv("SB_SCHED_TRACE") && atoi(getenv("SB_SCHED_TRACE")) != 0;
+  const auto t_call = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
+  int first_turn = 0;      // the first picks go in context order, so that the same job list lands on the same contexts
+                           // from call to call (resident buffers and bound constraint programs are per context)
   auto worker = [&](int c) {
     sb_ctx* ctx = ctxs[c];
     const int d = dev_of(c);
     const bool takes_big = first_ctx[d] == c;
+    bool first = true;
     for (;;) {
       int pick = -1;
       bool big = false;
       {
         std::unique_lock<std::mutex> lk(mu);
+        bool my_turn = first;
+        if (first) {
+          cv.wait(lk, [&] { return first_turn == c; });
+          first = false;
+        }
+        auto release_turn = [&] { if (my_turn) { my_turn = false; first_turn++; cv.notify_all(); } };
         for (;;) {
-          if (remaining == 0) return;
+          if (remaining == 0) { release_turn(); return; }
           DeviceState& st = dev[d];
           bool any_left = false;
           for (int k : order) {
@@ -79,8 +92,10 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
             break;
           }
           if (pick >= 0 || !any_left) break;
+          release_turn();
           cv.wait(lk);
         }
+        release_turn();
         if (pick < 0) return;                                       // nothing left to take (others are finishing)
         taken[pick] = 1;
         DeviceState& st = dev[d];
@@ -91,8 +106,10 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
       }
       sb_job& j = jobs[pick];
       const auto t0 = std::chrono::steady_clock::now();
+      const float ts = since();
       j.rc = sb_prove(ctx, &j.params, j.trace, j.layout, j.public_inputs, &j.proof);
       j.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (trace) fprintf(stderr, "sb_prove_batch: job %d (stark %u) on context %d: %.1f -> %.1f ms\n", pick, j.params.stark_id, c, ts, since());
       {
         std::lock_guard<std::mutex> lk(mu);
         DeviceState& st = dev[d];
