@@ -324,7 +324,9 @@ int sb_group_prove(sb_group* g, const sb_params* p, const void* local_trace, int
 float sb_group_phase_ms(const sb_group* g, const char* phase);
 
 /* The host-side transcript permutation (plonky2 Challenger, run between kernels): variant 0 = portable scalar,
- * 1 = AVX2, 2 = AVX-512; returns 1 if that variant ran, 0 if the CPU lacks the extension.  Parity-test hook. */
+ * 1 = AVX2, 2 = AVX-512, 3 = AVX-512 full rounds + sparse partial rounds, 4 / 5 = AVX-512 IFMA + BMI2 hybrid (words 0..7
+ * in a vector, 8..11 on mulx; look-ahead of one / two partial rounds); the library picks the best one the CPU supports.
+ * Returns 1 if that variant ran, 0 if the CPU lacks the extension.  Parity-test hook. */
 int sb_host_poseidon_permute_variant(uint64_t state[12], int variant);
 
 /* ---- device-resident benchmarking hooks (bench.py `value` leg: inputs already in HBM) ---- */
