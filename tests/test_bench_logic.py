@@ -24,13 +24,21 @@ def test_workload_tables_are_consistent():
 
 
 def test_full_set_plan_shards_final_exp_on_a_whole_box():
-    fe, per = bench.full_set_plan(8)
+    rest = sorted(k for k in bench.FULL_SET if k != "final_exp")
+    # default plan: FinalExp over every GPU, the six other proofs longest-first over the same GPUs (next to the shards)
+    for world in (4, 8):
+        fe, per = bench.full_set_plan(world)
+        assert fe == list(range(world)) and len(per) == world
+        assert sorted(x for r in per for x in r) == rest
+        assert max(sum(bench.FULL_SET_COST[x] for x in r) for r in per) == bench.FULL_SET_COST["miller_loop"]
+    # round-1 plan: FinalExp over half of the GPUs, the others share the rest
+    fe, per = bench.full_set_plan(8, "half")
     assert fe == [0, 1, 2, 3] and per[:4] == [[], [], [], []]
-    assert sorted(x for r in per for x in r) == sorted(k for k in bench.FULL_SET if k != "final_exp")
+    assert sorted(x for r in per for x in r) == rest
     assert max(sum(bench.FULL_SET_COST[x] for x in r) for r in per) == bench.FULL_SET_COST["miller_loop"]
-    fe, per = bench.full_set_plan(4)
+    fe, per = bench.full_set_plan(4, "half")
     assert fe == [0, 1] and per[:2] == [[], []]
-    assert sorted(x for r in per for x in r) == sorted(k for k in bench.FULL_SET if k != "final_exp")
+    assert sorted(x for r in per for x in r) == rest
     fe, per = bench.full_set_plan(2)
     assert fe == [] and per == bench.full_set_assignment(2)
 
