@@ -172,6 +172,14 @@ int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int n_jobs);
  *      sb_prove_fp12_mul: both steps in one call (generate on the host, prove on the ctx's GPU). ---- */
 int sb_witness_fp12_mul(const uint32_t* x, const uint32_t* y, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out);
 int sb_prove_fp12_mul(sb_ctx* ctx, const sb_params* p, const uint32_t* x, const uint32_t* y, sb_proof** out);
+/*      sb_witness_ecc_agg: ECCAggStark::generate_trace (ecc_aggregate.rs:37-82; fill_trace_g1_addition g1.rs:26-255) + the
+ *      public inputs of ec_aggregate_main (aggregate_proof.rs:186-227).  points: 512 affine G1 points, x ++ y as 12
+ *      little-endian u32 limbs each ([512][24]); bits: 512 participation flags (0 / 1).  trace_out: [num_rows][3339]
+ *      uint32_t; public_inputs_out: 12 824 values (points ++ bits ++ aggregate); result_out (may be NULL): the aggregate
+ *      point, 24 limbs.  sb_prove_ecc_agg: both steps in one call. */
+int sb_witness_ecc_agg(const uint32_t* points, const uint8_t* bits, uint32_t num_rows, uint32_t* trace_out,
+                       uint64_t* public_inputs_out, uint32_t* result_out);
+int sb_prove_ecc_agg(sb_ctx* ctx, const sb_params* p, const uint32_t* points, const uint8_t* bits, sb_proof** out);
 const char* sb_witness_last_error(void);
 
 /* ---- proof wire formats: the proof as bytes for a consumer that does not link this library -- the

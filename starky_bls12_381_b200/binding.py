@@ -264,6 +264,32 @@ def witness_fp12_mul(x, y, num_rows=16):
     return trace, pis
 
 
+def g1_limbs(points):
+    """512 affine G1 points [(x, y)] as the [512][24] uint32 limb array of sb_witness_ecc_agg."""
+    out = np.zeros((len(points), 24), np.uint32)
+    for i, (x, y) in enumerate(points):
+        for k in range(12):
+            out[i, k] = (int(x) >> (32 * k)) & 0xFFFFFFFF
+            out[i, 12 + k] = (int(y) >> (32 * k)) & 0xFFFFFFFF
+    return out
+
+
+def witness_ecc_agg(points, bits, num_rows=8192):
+    """sb_witness_ecc_agg: (trace uint32 [num_rows][3339] row-major, public inputs uint64 [12824], aggregate point (x, y))."""
+    pl = g1_limbs(points)
+    bl = np.ascontiguousarray(np.array([1 if b else 0 for b in bits], np.uint8))
+    trace = np.empty((num_rows, 3339), np.uint32)
+    pis = np.empty(12824, np.uint64)
+    res = np.zeros(24, np.uint32)
+    L = lib()
+    L.sb_witness_ecc_agg.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.sb_witness_ecc_agg(_ptr(pl), _ptr(bl), num_rows, _ptr(trace), _ptr(pis), _ptr(res))
+    if rc:
+        raise SbError(rc, L.sb_witness_last_error().decode())
+    val = lambda l: sum(int(v) << (32 * k) for k, v in enumerate(l))
+    return trace, pis, (val(res[:12]), val(res[12:]))
+
+
 def prove_batch(contexts, jobs):
     """sb_prove_batch: jobs = [(Params, trace pointer or array, layout, public inputs)], returns [(Proof or SbError, ms)] in
     job order.  The proofs run on `contexts` with the library's scheduler (internal host threads)."""

@@ -656,6 +656,21 @@ int sb_prove_fp12_mul(sb_ctx* ctx, const sb_params* p, const uint32_t* x, const 
   } catch (const SbError& e) { return sb_fail(ctx, e); }
 }
 
+// ECCAggStark from the 512 points and participation bits (witness.cpp), then the proof
+int sb_prove_ecc_agg(sb_ctx* ctx, const sb_params* p, const uint32_t* points, const uint8_t* bits, sb_proof** out) {
+  if (!ctx || !p || !points || !bits || !out) return SB_EINVAL;
+  try {
+    check_params(p);
+    if (p->stark_id != SB_STARK_ECC_AGG || p->n_cols != 3339 || p->n_public_inputs != 12824)
+      SB_THROW(SB_EINVAL, "sb_prove_ecc_agg needs the ECCAggStark parameters (3339 columns, 12824 public inputs)");
+    const uint32_t rows = 1u << p->log_n;
+    std::vector<uint32_t> trace((size_t)rows * p->n_cols);
+    std::vector<uint64_t> pis(p->n_public_inputs);
+    if (sb_witness_ecc_agg(points, bits, rows, trace.data(), pis.data(), nullptr)) SB_THROW(SB_EINVAL, "%s", sb_witness_last_error());
+    return sb_prove(ctx, p, trace.data(), SB_TRACE_ROWMAJOR_U32, pis.data(), out);
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+
 void sb_proof_free(sb_proof* proof) {
   if (!proof) return;
   if (proof->words) pinned_give(proof->words, 8ull * proof->layout.total_words);

@@ -71,16 +71,52 @@ Big shl_limbs(const Big& a, int k) {
   for (int i = Big::N - k; i < Big::N; i++) if (a.w[i]) throw std::overflow_error("witness: Big shift overflow");
   return r;
 }
-// x = q * m + r, 0 <= r < m (binary long division: the operands are at most 800 bits, the generators divide a few
-// thousand times per trace)
+// x = q * m + r, 0 <= r < m: Knuth's algorithm D on 32-bit limbs (the generators divide ~10^5 times per large trace)
 void divmod(const Big& x, const Big& m, Big& q, Big& r) {
   q = Big(); r = Big();
-  const int t = x.top();
-  for (int bit = 32 * (t + 1) - 1; bit >= 0; bit--) {
-    u32 c = (x.w[bit >> 5] >> (bit & 31)) & 1u;          // r = 2 r + bit
-    for (int i = 0; i < Big::N; i++) { const u32 nc = r.w[i] >> 31; r.w[i] = (r.w[i] << 1) | c; c = nc; }
-    if (cmp(r, m) >= 0) { r = sub(r, m); q.w[bit >> 5] |= 1u << (bit & 31); }
+  const int n = m.top() + 1, tx = x.top() + 1;
+  if (n == 0) throw std::domain_error("witness: division by zero");
+  if (tx < n) { r = x; return; }
+  if (n == 1) {
+    u64 rem = 0;
+    for (int i = tx - 1; i >= 0; i--) { const u64 cur = (rem << 32) | x.w[i]; q.w[i] = (u32)(cur / m.w[0]); rem = cur % m.w[0]; }
+    r.w[0] = (u32)rem;
+    return;
   }
+  const int sh = __builtin_clz(m.w[n - 1]);
+  u32 v[Big::N], u[Big::N + 1];
+  for (int i = n - 1; i > 0; i--) v[i] = sh ? (m.w[i] << sh) | (m.w[i - 1] >> (32 - sh)) : m.w[i];
+  v[0] = m.w[0] << sh;
+  u[tx] = sh ? x.w[tx - 1] >> (32 - sh) : 0;
+  for (int i = tx - 1; i > 0; i--) u[i] = sh ? (x.w[i] << sh) | (x.w[i - 1] >> (32 - sh)) : x.w[i];
+  u[0] = x.w[0] << sh;
+  for (int j = tx - n; j >= 0; j--) {
+    const u64 num = ((u64)u[j + n] << 32) | u[j + n - 1];
+    u64 qh = num / v[n - 1], rh = num % v[n - 1];
+    while (qh >> 32 || qh * v[n - 2] > ((rh << 32) | u[j + n - 2])) {
+      qh--; rh += v[n - 1];
+      if (rh >> 32) break;
+    }
+    int64_t borrow = 0;
+    u64 carry = 0;
+    for (int i = 0; i < n; i++) {
+      const u64 pr = qh * v[i] + carry;
+      carry = pr >> 32;
+      const int64_t t = (int64_t)u[i + j] - (int64_t)(u32)pr + borrow;
+      u[i + j] = (u32)t;
+      borrow = t >> 32;
+    }
+    const int64_t t = (int64_t)u[j + n] - (int64_t)carry + borrow;
+    u[j + n] = (u32)t;
+    if (t < 0) {                                   // qh was one too large: add the divisor back
+      qh--;
+      u64 c = 0;
+      for (int i = 0; i < n; i++) { c += (u64)u[i + j] + v[i]; u[i + j] = (u32)c; c >>= 32; }
+      u[j + n] += (u32)c;
+    }
+    q.w[j] = (u32)qh;
+  }
+  for (int i = 0; i < n; i++) r.w[i] = sh ? (u[i] >> sh) | ((u64)u[i + 1] << (32 - sh)) : u[i];
 }
 
 const u32 P_LIMBS[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
@@ -101,6 +137,15 @@ Fp fp_add(const Fp& x, const Fp& y) { Fp s = add(x, y); return cmp(s, MODP()) >=
 Fp fp_mod(const Big& x) { Big q, r; divmod(x, MODP(), q, r); return r; }
 Fp fp_sub(const Fp& x, const Fp& y) { return fp_mod(sub(add(MODP(), x), y)); }
 Fp fp_mul(const Fp& x, const Fp& y) { return fp_mod(mul(x, y)); }
+Fp fp_inv(const Fp& x) {                                  // x^(p-2)
+  const Big e = sub(MODP(), Big(2));
+  Fp r = Big(1), b = x;
+  for (int bit = 0; bit < 384; bit++) {
+    if ((e.w[bit >> 5] >> (bit & 31)) & 1u) r = fp_mul(r, b);
+    b = fp_mul(b, b);
+  }
+  return r;
+}
 Fp2 fp2_add(const Fp2& x, const Fp2& y) { return {{fp_add(x.c[0], y.c[0]), fp_add(x.c[1], y.c[1])}}; }
 Fp2 fp2_sub(const Fp2& x, const Fp2& y) { return {{fp_sub(x.c[0], y.c[0]), fp_sub(x.c[1], y.c[1])}}; }
 Fp2 fp2_mul(const Fp2& x, const Fp2& y) {
@@ -476,6 +521,49 @@ thread_local std::string g_witness_error;
 
 }  // namespace
 
+// ------------------------------------------------------------------ g1.rs, ecc_aggregate.rs
+struct G1 { Fp x, y; };
+// g1.rs:26-255: chord addition of two affine points, x3 = l^2 - x2 - x1, y3 = l (x1 - x3) - y1, on rows s .. s + 11
+G1 fill_trace_g1_addition(Trace& tr, const G1& p1, const G1& p2, size_t s, size_t col) {
+  const Fp &x1 = p1.x, &y1 = p1.y, &x2 = p2.x, &y2 = p2.y;
+  const Fp lam = fp_mul(fp_sub(y2, y1), fp_inv(fp_sub(x2, x1)));
+  const Fp x3 = fp_sub(fp_sub(fp_mul(lam, lam), x2), x1);
+  const Fp y3 = fp_sub(fp_mul(lam, fp_sub(x1, x3)), y1);
+  const size_t e = s + 11;
+  put_big_rows(tr, s, e, col + g1::G1_POINT_ADDITION_X1, x1, 12); put_big_rows(tr, s, e, col + g1::G1_POINT_ADDITION_Y1, y1, 12);
+  put_big_rows(tr, s, e, col + g1::G1_POINT_ADDITION_X2, x2, 12); put_big_rows(tr, s, e, col + g1::G1_POINT_ADDITION_Y2, y2, 12);
+  put_big_rows(tr, s, e, col + g1::G1_POINT_ADDITION_X3, x3, 12); put_big_rows(tr, s, e, col + g1::G1_POINT_ADDITION_Y3, y3, 12);
+  auto add_rows = [&](const Big& a, const Big& b, size_t c) { fill_trace_addition_fp(tr, a, b, s, c); tr.rep(s, e, c, fp::FP_ADDITION_TOTAL); };
+  auto sub_rows = [&](const Big& a, const Big& b, size_t c) { fill_trace_subtraction_fp(tr, a, b, s, c); tr.rep(s, e, c, fp::FP_SUBTRACTION_TOTAL); };
+  auto mul_red = [&](const Big& a, const Big& b, size_t c) {
+    fill_multiplication_trace_no_mod_reduction(tr, a, b, s, e, c);
+    const Big res = fill_reduction_trace(tr, mul(a, b), s, e, c + fp::FP_MULTIPLICATION_TOTAL_COLUMNS);
+    fill_range_check_trace(tr, res, e, c + fp::FP_MULTIPLICATION_TOTAL_COLUMNS + fp::REDUCTION_TOTAL);
+    return res;
+  };
+  const Big& P = MODP();
+  add_rows(x2, P, col + g1::X2_X1_DIFF);
+  const Big x2_x1 = sub(add(x2, P), x1);
+  sub_rows(add(x2, P), x1, col + g1::X2_X1_DIFF + fp::FP_ADDITION_TOTAL);
+  add_rows(y2, P, col + g1::Y2_Y1_DIFF);
+  const Big y2_y1 = sub(add(y2, P), y1);
+  sub_rows(add(y2, P), y1, col + g1::Y2_Y1_DIFF + fp::FP_ADDITION_TOTAL);
+  const Big x2_x1_sq = mul_red(x2_x1, x2_x1, col + g1::X2_X1_SQ);
+  const Big y2_y1_sq = mul_red(y2_y1, y2_y1, col + g1::Y2_Y1_SQ);
+  add_rows(x1, x2, col + g1::X1_X2_X3_SUM);
+  add_rows(add(x1, x2), x3, col + g1::X1_X2_X3_SUM + fp::FP_ADDITION_TOTAL);
+  const Big lhs = mul_red(add(add(x1, x2), x3), x2_x1_sq, col + g1::X1_X2_X3_X2_X1_SQ);
+  if (cmp(lhs, y2_y1_sq)) throw std::logic_error("witness: g1 addition, x3 relation does not hold");
+  add_rows(y1, y3, col + g1::Y1_Y3);
+  add_rows(x1, P, col + g1::X1_X3);
+  const Big x1_x3 = sub(add(x1, P), x3);
+  sub_rows(add(x1, P), x3, col + g1::X1_X3 + fp::FP_ADDITION_TOTAL);
+  const Big a = mul_red(add(y1, y3), x2_x1, col + g1::Y1_Y3_X2_X1);
+  const Big b = mul_red(y2_y1, x1_x3, col + g1::Y2_Y1_X1_X3);
+  if (cmp(a, b)) throw std::logic_error("witness: g1 addition, y3 relation does not hold");
+  return {x3, y3};
+}
+
 extern "C" {
 
 const char* sb_witness_last_error(void) { return g_witness_error.c_str(); }
@@ -498,6 +586,57 @@ int sb_witness_fp12_mul(const uint32_t* x, const uint32_t* y, uint32_t num_rows,
         public_inputs_out[woff::fp12_mul::PIS_INPUT_Y_OFFSET + 12 * i + k] = Y.c[i].w[k];
         public_inputs_out[woff::fp12_mul::PIS_OUTPUT_OFFSET + 12 * i + k] = Z.c[i].w[k];
       }
+    return SB_OK;
+  } catch (const std::exception& e) {
+    g_witness_error = e.what();
+    return SB_EINVAL;
+  }
+}
+
+// ECCAggStark::generate_trace (ecc_aggregate.rs:37-82) + the public inputs of ec_aggregate_main (aggregate_proof.rs:186-227).
+// points: 512 affine G1 points as x ++ y, 12 little-endian u32 limbs each ([512][24]); bits: 512 participation flags.
+// trace_out: [num_rows][3339] uint32_t row-major; public_inputs_out: 12 824 values (points, bits, aggregate);
+// result_out (optional): the aggregate point, 24 limbs.
+int sb_witness_ecc_agg(const uint32_t* points, const uint8_t* bits, uint32_t num_rows, uint32_t* trace_out,
+                       uint64_t* public_inputs_out, uint32_t* result_out) {
+  if (!points || !bits || !trace_out || !public_inputs_out) return SB_EINVAL;
+  try {
+    namespace E = woff::ecc_aggregate;
+    if ((num_rows & (num_rows - 1)) || (size_t)(E::NUM_POINTS - 1) * 12 >= num_rows)
+      throw std::invalid_argument("witness: stark doesn't have enough rows (power of two > 12 * 511)");
+    Trace tr = {trace_out, num_rows, E::TOTAL_COLUMNS};
+    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    std::vector<G1> pts(E::NUM_POINTS);
+    for (uint32_t i = 0; i < E::NUM_POINTS; i++) {
+      pts[i].x = Big::from_limbs(points + 24 * i, 12);
+      pts[i].y = Big::from_limbs(points + 24 * i + 12, 12);
+    }
+    for (size_t r = 0; r < num_rows; r++) tr.at(r, E::ROW_NUM + r % 12) = 1;
+    for (uint32_t i = 0; i < E::NUM_POINTS; i++) {
+      const size_t row = i >= 2 ? 12ull * (i - 1) : 0;
+      tr.set_rows(row, row + 11, E::PIS_IDX + i, 1);
+    }
+    size_t row = 0;
+    G1 res = fill_trace_g1_addition(tr, pts[0], pts[1], row, E::OP);
+    tr.set_rows(row, row + 11, E::A_IS_INF, bits[0] ? 0 : 1);
+    tr.set_rows(row, row + 11, E::B_IS_INF, bits[1] ? 0 : 1);
+    if (!bits[0]) res = pts[1];
+    else if (!bits[1]) res = pts[0];
+    for (uint32_t i = 2; i < E::NUM_POINTS; i++) {
+      row += 12;
+      const G1 tmp = fill_trace_g1_addition(tr, res, pts[i], row, E::OP);
+      tr.set_rows(row, row + 11, E::B_IS_INF, bits[i] ? 0 : 1);
+      if (bits[i]) res = tmp;
+    }
+    for (uint32_t i = 0; i < E::NUM_POINTS; i++) {
+      for (int k = 0; k < 24; k++) public_inputs_out[E::POINTS + 24 * i + k] = points[24 * i + k];
+      public_inputs_out[E::BITS + i] = bits[i] ? 1 : 0;
+    }
+    for (int k = 0; k < 12; k++) {
+      public_inputs_out[E::RES + k] = res.x.w[k];
+      public_inputs_out[E::RES + 12 + k] = res.y.w[k];
+      if (result_out) { result_out[k] = res.x.w[k]; result_out[12 + k] = res.y.w[k]; }
+    }
     return SB_OK;
   } catch (const std::exception& e) {
     g_witness_error = e.what();

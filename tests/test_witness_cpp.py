@@ -9,7 +9,7 @@ import oracle_lib as O
 import starky_bls12_381_b200 as sb
 from helpers import to_oracle_params
 from starky_bls12_381_b200 import airfiles, witness as W
-from starky_bls12_381_b200.binding import witness_fp12_mul
+from starky_bls12_381_b200.binding import witness_ecc_agg, witness_fp12_mul
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
@@ -40,6 +40,20 @@ def test_every_constraint_vanishes_on_the_cpp_trace():
     rc, words = O.prove(flat, to_oracle_params(p), np.ascontiguousarray(rows.T), pis)     # flags = 0: the quotient must divide
     assert rc == 0, O.err()
     assert O.verify(flat, to_oracle_params(p), words) == 0, O.err()
+
+
+def test_cpp_ecc_agg_trace_equals_the_python_restatement():
+    rng = np.random.default_rng(0xB2007300)
+    pts = [(W.random_fp(rng), W.random_fp(rng)) for _ in range(512)]
+    bits = [bool(b) for b in rng.integers(0, 2, 512)]
+    bits[0], bits[1], bits[2] = False, True, False            # first operand "at infinity", a skipped point
+    want_t, want_p, want_res = W.ecc_aggregate_trace(pts, bits)          # column-major uint64 [3339][8192]
+    got_t, got_p, got_res = witness_ecc_agg(pts, bits)                   # row-major uint32 [8192][3339]
+    assert got_res == want_res
+    assert np.array_equal(got_p, want_p)
+    assert np.array_equal(got_t.astype(np.uint64).T, want_t)
+    with pytest.raises(sb.SbError):
+        witness_ecc_agg(pts, bits, 4096)                      # 511 additions of 12 rows do not fit
 
 
 def test_unreduced_operands_are_rejected():
