@@ -1,0 +1,187 @@
+// K2, third form: the dense MDS layer of the Poseidon leaf sponge on the integer tensor-core path (IMMA).
+// Replaces PoseidonHash::hash_or_noop of every leaf in plonky2's MerkleTree::new (reached from
+// starky::prover::prove, reference call sites /root/reference/src/aggregate_proof.rs:59,105,138,169,212).
+//
+// The dp kernel (leafhash.cuh) spends two thirds of its instructions moving the state between the four threads of a
+// leaf: shared-memory exchange, one barrier per round, 16-bit pair packing, 340 IDP.2A per leaf and round.  Here the
+// exchange IS the matrix instruction.  mma.sync.m16n8k32 (u8 x u8 -> s32) computes D[16 x 8] = A[16 x 32] B[32 x 8] + C
+// with the operands spread over the lanes of a warp in a fixed pattern (lane = 4 g + t):
+//     A: lane (g, t) supplies k = 4t..4t+3 and 16+4t..16+4t+3 of rows g and g+8
+//     D: lane (g, t) receives columns 2t, 2t+1 of rows g and g+8
+// Rows are leaves.  Lane (g, t) owns words 3t..3t+2 of the two leaves of rows g, g+8.  For a pair of byte limbs
+// (2q, 2q+1) the K index is (word, limb class): k = 4t + i is limb 2q of word 3t+i (i = 3: padding, its B rows are
+// zero), k = 16 + 4t + i is limb 2q+1.  Three B tiles j = 0..2 map it to N = (output row 3t'+j, limb class e) at column
+// 2t'+e, so lane (g, t') receives the limb sums of ITS OWN rows 3t'..3t'+2: after the instruction every lane holds the
+// next state of the words it owned before.  No shared-memory exchange, no barrier, one warp per 16 (or 32) leaves.
+//     per 16 leaves and round: 24 PRMT (byte transposes of 3 words x 8 limbs), 12 IMMA, 6 limb recombinations
+// Limb sums are < 264 * 255 < 2^17, exact in s32; the round constants of the next round join the two half sums of
+// the recombination (as the C operand they cost four register moves per instruction).  The S-box of a partial round touches word 0 only, which lives on the t = 0
+// lanes: the leaves of a quad are handed out to its lanes by shuffle so that the x^7 runs once per warp and round.
+#pragma once
+#include "leafhash.cuh"
+
+__device__ __forceinline__ void imma_16832_u8(u32 (&d)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+__device__ __forceinline__ u64 shfl64(u64 v, unsigned src) {
+  const u32 lo = __shfl_sync(0xFFFFFFFFu, (u32)v, src), hi = __shfl_sync(0xFFFFFFFFu, (u32)(v >> 32), src);
+  return ((u64)hi << 32) | lo;
+}
+
+// MT = 16-leaf row tiles per warp (1: 16 leaves, 2: 32 leaves per warp)
+template <int MT>
+__global__ void __launch_bounds__(64) leaf_sponge_mm_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                            uint32_t n_leaves, unsigned log_block,
+                                                            u64* __restrict__ digests,
+                                                            const u64* __restrict__ state_in = nullptr,
+                                                            u64* __restrict__ state_out = nullptr) {
+  constexpr int NL = 2 * MT;                        // leaves per lane
+  __shared__ __align__(16) u64 rcs[31][12][2];      // round constants as (low half, high half), each a u64; row 30 = zeros
+  for (unsigned i = threadIdx.x; i < 31 * 12; i += blockDim.x) {
+    const u64 c = c_poseidon_rc[i];
+    rcs[i / 12][i % 12][0] = c & 0xFFFFFFFFull;
+    rcs[i / 12][i % 12][1] = c >> 32;
+  }
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (16 * MT);
+  if (base >= n_leaves) return;
+
+  uint32_t pos[NL];
+  bool live[NL];
+#pragma unroll
+  for (int L = 0; L < NL; L++) {
+    const uint32_t raw = base + 16 * (L >> 1) + 2 * g + (L & 1);
+    live[L] = raw < n_leaves;
+    pos[L] = live[L] ? raw : n_leaves - 1;
+  }
+  // B tiles: B_j[k = (word 3t+i, class)][n = g -> (row 3 (g >> 1) + j, class g & 1)]
+  u32 bf[3][2];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    u32 v = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const unsigned r = 3 * (g >> 1) + j, c = 3 * t + i;
+      const u32 coef = c_poseidon_circ[(c + 12 - r) % 12] + ((r == 0 && c == 0) ? 8u : 0u);
+      v |= coef << (8 * i);
+    }
+    bf[j][0] = (g & 1) ? 0u : v;
+    bf[j][1] = (g & 1) ? v : 0u;
+  }
+
+  u64 s[NL][3], nx[NL][3];
+#pragma unroll
+  for (int L = 0; L < NL; L++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) { s[L][k] = state_in ? state_in[(size_t)(3 * t + k) * n_leaves + pos[L]] : 0; nx[L][k] = 0; }
+  const uint32_t n_chunks = (leaf_len + 7) / 8;
+  auto fetch = [&](uint32_t chunk) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint32_t w = 3 * t + k, c = chunk * 8 + w;
+      if (w < 8 && c < leaf_len) {
+        const u64* p = cols + (size_t)c * n_leaves;
+#pragma unroll
+        for (int L = 0; L < NL; L++) nx[L][k] = p[pos[L]];
+      }
+    }
+  };
+  fetch(0);
+
+  auto linear_layer = [&](int rd) {
+    const ulonglong2* rcp = reinterpret_cast<const ulonglong2*>(&rcs[rd + 1][3 * t][0]);
+    ulonglong2 rc[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) rc[j] = rcp[j];
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+      u32 A[2][8];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const u64 *w = s[2 * m + h];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          const u32 x0 = (u32)(w[0] >> (32 * half)), x1 = (u32)(w[1] >> (32 * half)), x2 = (u32)(w[2] >> (32 * half));
+          const u32 t0 = __byte_perm(x0, x1, 0x5140), t1 = __byte_perm(x0, x1, 0x7362);
+          A[h][4 * half + 0] = __byte_perm(t0, x2, 0x4410);
+          A[h][4 * half + 1] = __byte_perm(t0, x2, 0x5532);
+          A[h][4 * half + 2] = __byte_perm(t1, x2, 0x6610);
+          A[h][4 * half + 3] = __byte_perm(t1, x2, 0x7732);
+        }
+      }
+      u32 D[3][4][4];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          imma_16832_u8(D[j][q], A[0][2 * q], A[1][2 * q], A[0][2 * q + 1], A[1][2 * q + 1], bf[j][0], bf[j][1]);
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          u32 p[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) p[q] = D[j][q][2 * h] + (D[j][q][2 * h + 1] << 8);
+          // al = p0 + p1 2^16 + low half of the constant, ah likewise: both < 2^41
+          const u64 al = (u64)p[1] * 65536ull + rc[j].x + p[0], ah = (u64)p[3] * 65536ull + rc[j].y + p[2];
+          s[2 * m + h][j] = mds_recombine((u32)al, (u32)(al >> 32), (u32)ah, (u32)(ah >> 32));
+        }
+    }
+  };
+  auto sbox_all = [&]() {
+#pragma unroll
+    for (int L = 0; L < NL; L++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) s[L][k] = poseidon_sbox(s[L][k]);
+  };
+  // word 0 of the quad's NL leaves sits on lane t = 0: lane L of the quad takes leaf L (lanes >= NL redo leaf 0)
+  auto sbox_word0 = [&]() {
+    const unsigned q0 = lane & ~3u;
+    u64 v = s[0][0];
+#pragma unroll
+    for (int L = 1; L < NL; L++) { const u64 x = shfl64(s[L][0], q0); if (t == (unsigned)L) v = x; }
+    const u64 y = poseidon_sbox(v);
+#pragma unroll
+    for (int L = 1; L < NL; L++) { const u64 x = shfl64(y, q0 | L); if (t == 0) s[L][0] = x; }
+    if (t == 0) s[0][0] = y;
+  };
+
+  for (uint32_t m = 0; m < n_chunks; m++) {
+    const unsigned take = min(8u, leaf_len - 8 * m);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (3 * t + k < take) {
+#pragma unroll
+        for (int L = 0; L < NL; L++) s[L][k] = nx[L][k];
+      }
+    if (m + 1 < n_chunks) fetch(m + 1);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const u64 c = rcs[0][3 * t + k][0] | (rcs[0][3 * t + k][1] << 32);
+#pragma unroll
+      for (int L = 0; L < NL; L++) s[L][k] = gl_add_lazy_canon(s[L][k], c);
+    }
+#pragma unroll 1
+    for (int rd = 0; rd < 4; rd++) { sbox_all(); linear_layer(rd); }
+#pragma unroll 1
+    for (int rd = 4; rd < 26; rd++) { sbox_word0(); linear_layer(rd); }
+#pragma unroll 1
+    for (int rd = 26; rd < 30; rd++) { sbox_all(); linear_layer(rd); }
+  }
+#pragma unroll
+  for (int L = 0; L < NL; L++) {
+    if (!live[L]) continue;
+    if (state_out) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) state_out[(size_t)(3 * t + k) * n_leaves + pos[L]] = s[L][k];
+    } else {
+      u64* d = digests + 4ull * leaf_index_of(pos[L], log_block);
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (3 * t + k < 4) d[3 * t + k] = gl_canon(s[L][k]);
+    }
+  }
+}

@@ -13,6 +13,7 @@
 #define SP_TRACE 1
 #endif
 #include "leafhash.cuh"
+#include "leafhash_mm.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -234,7 +235,9 @@ int main(int argc, char** argv) {
     unsigned g32 = (nl + 31) / 32;
     for (int rep = 0; rep < 2; rep++) {
       float ms = time_ms([&] {
-        if (wps == 43) leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
+        if (wps == 201) leaf_sponge_mm_kernel<1><<<g32, 64>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 202) leaf_sponge_mm_kernel<2><<<(nl + 63) / 64, 64>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 43) leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 44) leaf_sponge_dp_kernel<2><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 45) leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 101) leaf_sponge_st_kernel<<<g32, 32>>>(d_cols, ll, nl, 0, d_dig);
@@ -249,6 +252,38 @@ int main(int argc, char** argv) {
       }, 1);
       printf("ws<%d> N=%u C=%u: %.3f ms\n", wps, nl, ll, ms);
     }
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "mm")) {   // dense MDS on IMMA (leafhash_mm.cuh) against the dp / sp kernels
+    struct Shape { const char* name; uint32_t n_leaves, leaf_len; };
+    for (const Shape& sh : {Shape{"ragged", 1000, 77}, Shape{"ragged2", 1013, 131}, Shape{"ML-like", 2048, 8003}, Shape{"PP-like", 4096, 8003},
+                            Shape{"ECC-like", 32768, 3339}, Shape{"FE-like", 32768, 8003}, Shape{"FE 1/2 box", 16384, 8003}}) {
+      const size_t cells = (size_t)sh.n_leaves * sh.leaf_len;
+      u64 *d_cols, *d_dig;
+      CK(cudaMalloc(&d_cols, 8 * cells)); CK(cudaMalloc(&d_dig, 32ull * sh.n_leaves));
+      fill_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_cols, cells);
+      CK(cudaDeviceSynchronize());
+      const double perms = (double)((sh.leaf_len + 7) / 8) * sh.n_leaves;
+      const unsigned g32 = (sh.n_leaves + 31) / 32;
+      std::vector<u64> ref(4ull * sh.n_leaves), got(4ull * sh.n_leaves);
+      printf("%-10s N=%6u C=%6u\n", sh.name, sh.n_leaves, sh.leaf_len);
+      auto run = [&](const char* name, auto launch, bool is_ref) {
+        CK(cudaMemset(d_dig, 0, 32ull * sh.n_leaves));
+        float t = time_ms(launch);
+        CK(cudaMemcpy(is_ref ? ref.data() : got.data(), d_dig, 32ull * sh.n_leaves, cudaMemcpyDeviceToHost));
+        bool ok = is_ref || !memcmp(got.data(), ref.data(), 32ull * sh.n_leaves);
+        printf("    %-46s %9.3f ms  %7.1f Mperm/s  %s\n", name, t, perms / t / 1e3, ok ? "ok" : "MISMATCH");
+      };
+      run("ref (1 thread per leaf)", [&] { ref_leaf_kernel<<<g32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, d_dig); }, true);
+      run("dp<0>", [&] { leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("sp<0>", [&] { leaf_sponge_sp_kernel<0><<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<1> 16 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<1><<<(sh.n_leaves + 31) / 32, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<1> 16 leaves per warp, block 32", [&] { leaf_sponge_mm_kernel<1><<<(sh.n_leaves + 15) / 16, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<2> 32 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<2><<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<2> 32 leaves per warp, block 32", [&] { leaf_sponge_mm_kernel<2><<<(sh.n_leaves + 31) / 32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      cudaFree(d_cols); cudaFree(d_dig);
+    }
+    printf("lab done\n");
     return 0;
   }
   if (argc > 1 && !strcmp(argv[1], "dp")) {   // throughput-bound shapes: which warp owns the partial-round S-box
