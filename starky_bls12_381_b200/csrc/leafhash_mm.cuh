@@ -25,35 +25,62 @@ __device__ __forceinline__ void imma_16832_u8(u32 (&d)[4], u32 a0, u32 a1, u32 a
       : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
+// the same with the accumulator as input: d = a b + d
+__device__ __forceinline__ void imma_16832_u8_acc(u32 (&d)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+static __constant__ u64 c_poseidon_rc_eq[31 * 12] = POSEIDON_RC_EQ;
 __device__ __forceinline__ u64 shfl64(u64 v, unsigned src) {
   const u32 lo = __shfl_sync(0xFFFFFFFFu, (u32)v, src), hi = __shfl_sync(0xFFFFFFFFu, (u32)(v >> 32), src);
   return ((u64)hi << 32) | lo;
 }
 
-// MT = 16-leaf row tiles per warp (1: 16 leaves, 2: 32 leaves per warp)
-template <int MT>
-__global__ void __launch_bounds__(64) leaf_sponge_mm_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+// NL = leaves per lane.  4: two 16-row tiles, 32 leaves per warp; 2: one tile, 16 leaves per warp; 1: half a tile (rows
+// 8..15 unused), 8 leaves per warp -- the latency-bound shapes (MillerLoop 2048, PairingPrecomp 4096 leaves, a FinalExp
+// shard on 8 GPUs), where wall time = chain length x time of one permutation and the fewest instructions per warp win.
+template <int NL>
+__global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                             uint32_t n_leaves, unsigned log_block,
                                                             u64* __restrict__ digests,
                                                             const u64* __restrict__ state_in = nullptr,
                                                             u64* __restrict__ state_out = nullptr) {
-  constexpr int NL = 2 * MT;                        // leaves per lane
-  __shared__ __align__(16) u64 rcs[31][12][2];      // round constants as (low half, high half), each a u64; row 30 = zeros
+  constexpr int MT = NL > 2 ? NL / 2 : 1, H = NL > 1 ? 2 : 1, LPW = 8 * NL;       // row tiles, rows per lane and tile, leaves per warp
+  // Round constants in the equivalent form with one non-zero constant per partial round (poseidon_fast.h, RC_EQ):
+  //   rcs: every round as (low half, high half), each a u64, for the layers that feed a full round; row 30 = zeros
+  //   rcw: the word-0 constants of rounds 5..25 as accumulator images (16-bit chunk q on limb 2q of both rows), [1] for
+  //        the lanes that own word 0 and zeros [0] for the others
+  __shared__ __align__(16) u64 rcs[31][12][2];
+  __shared__ __align__(16) u32 rcw[21][2][4][4];   // [round][owns word 0][instruction][accumulator register]
   for (unsigned i = threadIdx.x; i < 31 * 12; i += blockDim.x) {
-    const u64 c = c_poseidon_rc[i];
+    const u64 c = c_poseidon_rc_eq[i];
     rcs[i / 12][i % 12][0] = c & 0xFFFFFFFFull;
     rcs[i / 12][i % 12][1] = c >> 32;
   }
+  for (unsigned i = threadIdx.x; i < 21 * 4; i += blockDim.x) {
+    const u64 c = c_poseidon_rc_eq[12 * (5 + i / 4)];
+    u32* o = rcw[i / 4][1][i % 4];
+    u32* z = rcw[i / 4][0][i % 4];
+    if (NL == 1) {      // instruction i < 2 holds limbs 4i..4i+3: chunks 2i, 2i+1 on its registers 0 and 2
+      o[0] = (u32)(c >> (32 * (i % 4))) & 0xFFFFu; o[1] = 0; o[2] = (u32)(c >> (32 * (i % 4) + 16)) & 0xFFFFu; o[3] = 0;
+      if (i % 4 >= 2) { o[0] = 0; o[2] = 0; }
+    } else {            // instruction i holds limbs 2i, 2i+1 of rows g and g+8: chunk i on registers 0 and 2
+      const u32 ch = (u32)(c >> (16 * (i % 4))) & 0xFFFFu;
+      o[0] = ch; o[1] = 0; o[2] = ch; o[3] = 0;
+    }
+    z[0] = 0; z[1] = 0; z[2] = 0; z[3] = 0;
+  }
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (16 * MT);
+  const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LPW;
   if (base >= n_leaves) return;
 
   uint32_t pos[NL];
   bool live[NL];
 #pragma unroll
   for (int L = 0; L < NL; L++) {
-    const uint32_t raw = base + 16 * (L >> 1) + 2 * g + (L & 1);
+    const uint32_t raw = NL == 1 ? base + g : base + 16 * (L >> 1) + 2 * g + (L & 1);
     live[L] = raw < n_leaves;
     pos[L] = live[L] ? raw : n_leaves - 1;
   }
@@ -91,6 +118,38 @@ __global__ void __launch_bounds__(64) leaf_sponge_mm_kernel(const u64* __restric
   };
   fetch(0);
 
+  // A operands of row tile m: Q[i] = the four registers of instruction i.
+  //   NL >= 2: i = limb pair q (4 instructions): (limb 2q of row g, of row g+8, limb 2q+1 of row g, of row g+8)
+  //   NL == 1: the rows g+8 carry two more limbs of the SAME leaf, i = limb quad (2 instructions):
+  //            (limb 4i of row g, limb 4i+2 as row g+8, limb 4i+1 of row g, limb 4i+3 as row g+8)  ->  D = limbs 4i..4i+3
+  constexpr int NI = NL == 1 ? 2 : 4;
+  auto pack = [&](int m, u32 (&Q)[NI][4]) {
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+      const u64* w = s[2 * m + h];
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const u32 x0 = (u32)(w[0] >> (32 * half)), x1 = (u32)(w[1] >> (32 * half)), x2 = (u32)(w[2] >> (32 * half));
+        const u32 t0 = __byte_perm(x0, x1, 0x5140), t1 = __byte_perm(x0, x1, 0x7362);
+        const u32 l0 = __byte_perm(t0, x2, 0x4410), l1 = __byte_perm(t0, x2, 0x5532);
+        const u32 l2 = __byte_perm(t1, x2, 0x6610), l3 = __byte_perm(t1, x2, 0x7732);
+        if constexpr (NL == 1) { Q[half][0] = l0; Q[half][2] = l1; Q[half][1] = l2; Q[half][3] = l3; }
+        else { Q[2 * half][h] = l0; Q[2 * half][2 + h] = l1; Q[2 * half + 1][h] = l2; Q[2 * half + 1][2 + h] = l3; }
+      }
+    }
+  };
+  // limb sums (j, i) -> the state word of row h:  16-bit pairs, then the two half sums (+ the constant), then mod p
+  auto recombine = [&](const u32 (&D)[NI][4], int h, u64 cl, u64 ch) -> u64 {
+    u32 p[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if constexpr (NL == 1) p[q] = D[q >> 1][2 * (q & 1)] + (D[q >> 1][2 * (q & 1) + 1] << 8);
+      else p[q] = D[q][2 * h] + (D[q][2 * h + 1] << 8);
+    }
+    const u64 al = (u64)p[1] * 65536ull + cl + p[0], ah = (u64)p[3] * 65536ull + ch + p[2];     // both < 2^41
+    return mds_recombine((u32)al, (u32)(al >> 32), (u32)ah, (u32)(ah >> 32));
+  };
+  // linear layer that feeds a full round (or ends the permutation): every word gets its constant, in the recombination
   auto linear_layer = [&](int rd) {
     const ulonglong2* rcp = reinterpret_cast<const ulonglong2*>(&rcs[rd + 1][3 * t][0]);
     ulonglong2 rc[3];
@@ -98,37 +157,43 @@ __global__ void __launch_bounds__(64) leaf_sponge_mm_kernel(const u64* __restric
     for (int j = 0; j < 3; j++) rc[j] = rcp[j];
 #pragma unroll
     for (int m = 0; m < MT; m++) {
-      u32 A[2][8];
+      u32 Q[NI][4];
+      pack(m, Q);
+      u32 D[3][NI][4];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const u64 *w = s[2 * m + h];
+      for (int j = 0; j < 3; j++)
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          const u32 x0 = (u32)(w[0] >> (32 * half)), x1 = (u32)(w[1] >> (32 * half)), x2 = (u32)(w[2] >> (32 * half));
-          const u32 t0 = __byte_perm(x0, x1, 0x5140), t1 = __byte_perm(x0, x1, 0x7362);
-          A[h][4 * half + 0] = __byte_perm(t0, x2, 0x4410);
-          A[h][4 * half + 1] = __byte_perm(t0, x2, 0x5532);
-          A[h][4 * half + 2] = __byte_perm(t1, x2, 0x6610);
-          A[h][4 * half + 3] = __byte_perm(t1, x2, 0x7732);
-        }
+        for (int i = 0; i < NI; i++) imma_16832_u8(D[j][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[j][0], bf[j][1]);
+#pragma unroll
+      for (int h = 0; h < H; h++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) s[2 * m + h][j] = recombine(D[j], h, rc[j].x, rc[j].y);
+    }
+  };
+  // linear layer that feeds a partial round: only word 0 has a constant; it enters as the accumulator of row 0's
+  // instructions, which are issued first -- the next S-box waits for them alone
+  const unsigned own0 = t == 0 ? 1u : 0u;
+  auto linear_layer_p = [&](int rd) {
+    const uint4* cw = reinterpret_cast<const uint4*>(&rcw[rd - 4][own0][0][0]);
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+      u32 Q[NI][4];
+      pack(m, Q);
+      u32 D[3][NI][4];
+#pragma unroll
+      for (int i = 0; i < NI; i++) {
+        const uint4 c = cw[i];
+        D[0][i][0] = c.x; D[0][i][1] = c.y; D[0][i][2] = c.z; D[0][i][3] = c.w;
+        imma_16832_u8_acc(D[0][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[0][0], bf[0][1]);
       }
-      u32 D[3][4][4];
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int j = 1; j < 3; j++)
 #pragma unroll
-        for (int j = 0; j < 3; j++)
-          imma_16832_u8(D[j][q], A[0][2 * q], A[1][2 * q], A[0][2 * q + 1], A[1][2 * q + 1], bf[j][0], bf[j][1]);
+        for (int i = 0; i < NI; i++) imma_16832_u8(D[j][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[j][0], bf[j][1]);
 #pragma unroll
-      for (int h = 0; h < 2; h++)
+      for (int h = 0; h < H; h++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          u32 p[4];
-#pragma unroll
-          for (int q = 0; q < 4; q++) p[q] = D[j][q][2 * h] + (D[j][q][2 * h + 1] << 8);
-          // al = p0 + p1 2^16 + low half of the constant, ah likewise: both < 2^41
-          const u64 al = (u64)p[1] * 65536ull + rc[j].x + p[0], ah = (u64)p[3] * 65536ull + rc[j].y + p[2];
-          s[2 * m + h][j] = mds_recombine((u32)al, (u32)(al >> 32), (u32)ah, (u32)(ah >> 32));
-        }
+        for (int j = 0; j < 3; j++) s[2 * m + h][j] = recombine(D[j], h, 0, 0);
     }
   };
   auto sbox_all = [&]() {
@@ -167,7 +232,9 @@ __global__ void __launch_bounds__(64) leaf_sponge_mm_kernel(const u64* __restric
 #pragma unroll 1
     for (int rd = 0; rd < 4; rd++) { sbox_all(); linear_layer(rd); }
 #pragma unroll 1
-    for (int rd = 4; rd < 26; rd++) { sbox_word0(); linear_layer(rd); }
+    for (int rd = 4; rd < 25; rd++) { sbox_word0(); linear_layer_p(rd); }
+    sbox_word0();
+    linear_layer(25);
 #pragma unroll 1
     for (int rd = 26; rd < 30; rd++) { sbox_all(); linear_layer(rd); }
   }

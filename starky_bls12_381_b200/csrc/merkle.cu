@@ -56,25 +56,29 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ 
   d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 }
 
-// many-leaf shapes: 32 leaves per warp once that still leaves ~1.5 warps per scheduler, else 16 (measured, lab "mm")
-static int sb_mm_kind(sb_ctx* ctx, uint32_t n_leaves) { return (uint64_t)n_leaves >= 160ull * ctx->sm_count ? 7 : 6; }
+// leaves per warp of the matrix-instruction sponge: 8 up to 64 leaves per SM (latency-bound), 32 once that still leaves
+// ~1.5 warps per scheduler, 16 in between (measured, lab "mm")
+static int sb_mm_kind(sb_ctx* ctx, uint32_t n_leaves) {
+  if ((uint64_t)n_leaves <= 64ull * ctx->sm_count) return 8;
+  return (uint64_t)n_leaves >= 160ull * ctx->sm_count ? 7 : 6;
+}
 
 void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, uint32_t n_leaves, unsigned log_block,
                            u64* d_digests) {
   const uint32_t perms = (leaf_len + 7) / 8;
-  // Kernel choice (leafhash.cuh; measured on B200 with tools/perf/poseidon_lab.cu):
+  // Kernel choice (leafhash.cuh, leafhash_mm.cuh; measured on B200 with tools/perf/poseidon_lab.cu, profiles/r2_poseidon_lab_mm.txt):
   //   short chains (quotient / FRI leaves, <= 2 permutations): one thread per leaf, nothing to split;
-  //   few leaves (<= 2 groups of 32 per SM: PairingPrecomp 4096, MillerLoop 2048): every leaf is in flight at once and
-  //     wall time = chain length x latency of one permutation  ->  one state word per warp, sparse partial rounds with a
-  //     reducer warp (13); the dense-MDS variant with two-barrier partial rounds (12) is kept for comparison;
-  //   many leaves (FinalExp / ECCAgg 32768): throughput-bound on the heavy FMA pipe  ->  the dense MDS layer as an
-  //     integer matrix instruction over the lanes of one warp (leafhash_mm.cuh: 6 = 16 leaves per warp, 7 = 32 leaves
-  //     per warp, faster from ~1.5 warps per scheduler on); round 2's kernels stay selectable: 4 = three words per
-  //     thread, four warps per 32 leaves, dense MDS on dp2a; 3 = the same layout on IMAD.WIDE; 5 = dp2a + sparse rounds.
-  // SB_LEAF_KERNEL=1|3|4|5|6|7|12|13 overrides the choice (profiling, tests).
+  //   everything else: the dense MDS layer as an integer matrix instruction over the lanes of one warp (leafhash_mm.cuh),
+  //     8 = 8 leaves per warp for the latency-bound shapes (PairingPrecomp 4096, MillerLoop 2048 leaves: every leaf is in
+  //         flight at once and wall time = chain length x latency of one permutation),
+  //     6 = 16 and 7 = 32 leaves per warp for the throughput-bound ones (FinalExp / ECCAgg 32768 leaves);
+  //   round 1 / 2 kernels, still selectable: 13 = one state word per warp, sparse partial rounds with a reducer warp (the
+  //     former latency kernel), 12 = its dense two-barrier variant, 4 = three words per thread, four warps per 32 leaves,
+  //     dense MDS on dp2a (the former throughput kernel), 3 = the same on IMAD.WIDE, 5 = dp2a + sparse partial rounds.
+  // SB_LEAF_KERNEL=1|3|4|5|6|7|8|12|13 overrides the choice (profiling, tests).
   int kind = 1;
-  if (leaf_len > 4 && perms > 2) kind = ((uint64_t)n_leaves <= 64ull * ctx->sm_count) ? 13 : sb_mm_kind(ctx, n_leaves);
-  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 6 || v == 7 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
+  if (leaf_len > 4 && perms > 2) kind = sb_mm_kind(ctx, n_leaves);
+  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 6 || v == 7 || v == 8 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
   const uint32_t groups = (n_leaves + 31) / 32;
   if (kind == 13) {
     // SB_SP_VARIANT: lab variants of the sp kernel (leafhash.cuh); 0 = the round-1 kernel
@@ -92,10 +96,12 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
     LAUNCH(ctx, (leaf_sponge_w12_kernel<0, 1>), groups, 384, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 4) {
     LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+  } else if (kind == 8) {
+    LAUNCH(ctx, leaf_sponge_mm_kernel<1>, (n_leaves + 7) / 8, 32, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 6) {
-    LAUNCH(ctx, leaf_sponge_mm_kernel<1>, groups, 64, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+    LAUNCH(ctx, leaf_sponge_mm_kernel<2>, groups, 64, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 7) {
-    LAUNCH(ctx, leaf_sponge_mm_kernel<2>, (n_leaves + 63) / 64, 64, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+    LAUNCH(ctx, leaf_sponge_mm_kernel<4>, (n_leaves + 63) / 64, 64, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 5) {
     LAUNCH(ctx, leaf_sponge_ds_kernel, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 3) {
@@ -109,7 +115,7 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
 // The same sponge fed one slab of columns at a time (capi.cu ingest_and_commit_trace: the trace arrives over PCIe in
 // column slabs and the sponge absorbs columns in order, so slab k is hashed while slab k+1 is copied and extended).
 // d_state = [12][n_leaves] u64 carried between launches; n_cols % 8 == 0 on every launch but the last; the last launch
-// writes the digests.  Only the product kernels (sp: few leaves, mm: many leaves; SB_STREAM_DP=1: round 2's dp) take part.
+// writes the digests.  The matrix-instruction kernels take part (SB_STREAM_OLD=1: round 2's sp / dp kernels).
 bool sb_hash_leaves_streamable(uint32_t leaf_len_total) { return leaf_len_total > 64 && !getenv("SB_LEAF_KERNEL"); }
 void sb_hash_leaves_stream(sb_ctx* ctx, const u64* d_cols, uint32_t n_cols, uint32_t n_leaves, unsigned log_block, u64* d_state,
                            bool first, bool last, u64* d_digests) {
@@ -117,14 +123,19 @@ void sb_hash_leaves_stream(sb_ctx* ctx, const u64* d_cols, uint32_t n_cols, uint
   const uint32_t groups = (n_leaves + 31) / 32;
   const u64* in = first ? nullptr : d_state;
   u64* out = last ? nullptr : d_state;
-  if ((uint64_t)n_leaves <= 64ull * ctx->sm_count)
+  const char* e_old = getenv("SB_STREAM_OLD");                     // round-2 kernels (A/B runs, tests)
+  const int old = e_old ? atoi(e_old) : 0;
+  const int kind = sb_mm_kind(ctx, n_leaves);
+  if (old && kind == 8)
     LAUNCH(ctx, leaf_sponge_sp_kernel<0>, groups, 416, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
-  else if (const char* e = getenv("SB_STREAM_DP"); e && atoi(e))
+  else if (old)
     LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
-  else if (sb_mm_kind(ctx, n_leaves) == 7)
-    LAUNCH(ctx, leaf_sponge_mm_kernel<2>, (n_leaves + 63) / 64, 64, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
+  else if (kind == 8)
+    LAUNCH(ctx, leaf_sponge_mm_kernel<1>, (n_leaves + 7) / 8, 32, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
+  else if (kind == 7)
+    LAUNCH(ctx, leaf_sponge_mm_kernel<4>, (n_leaves + 63) / 64, 64, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else
-    LAUNCH(ctx, leaf_sponge_mm_kernel<1>, groups, 64, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
+    LAUNCH(ctx, leaf_sponge_mm_kernel<2>, groups, 64, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
 }
 
 // one level: out[i] = two_to_one(in[2i], in[2i+1])

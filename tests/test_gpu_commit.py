@@ -54,7 +54,7 @@ def test_hash_leaves_ragged_lengths(ctx, leaf_len):
         assert np.array_equal(got[i], O.hash_or_noop(cols[:, i])), (leaf_len, i)
 
 
-@pytest.mark.parametrize("kernel", [1, 3, 4, 5, 6, 7, 12, 13])
+@pytest.mark.parametrize("kernel", [1, 3, 4, 5, 6, 7, 8, 12, 13])
 @pytest.mark.parametrize("leaf_len,count", [(5, 33), (8, 64), (17, 1000), (24, 32), (135, 100), (1001, 70)])
 def test_hash_leaves_every_kernel_variant(ctx, monkeypatch, kernel, leaf_len, count):
     """The three leaf-sponge kernels (one thread per leaf / 3 words per thread / 1 word per warp) are bit-identical
@@ -91,7 +91,7 @@ def test_lde_commit_matches_oracle(ctx, log_n, n_cols, rate_bits, full):
 
 
 @pytest.mark.parametrize("log_n,n_cols,rate_bits", [(5, 300, 3), (7, 203, 2), (6, 1037, 1), (11, 70, 4), (12, 141, 2)])
-@pytest.mark.parametrize("layout", ["colmajor", "col_ptrs"])
+@pytest.mark.parametrize("layout", ["colmajor", "col_ptrs", "colmajor_old_kernels"])
 def test_streamed_leaf_sponge_matches_oracle(ctx, monkeypatch, log_n, n_cols, rate_bits, layout):
     """The host-trace path hashes the leaves slab by slab behind the copy (capi.cu ingest_and_commit_trace): with small
     slabs every shape here is fed to the sponge in several launches (sp kernel: few leaves, dp kernel: many leaves, a
@@ -102,7 +102,9 @@ def test_streamed_leaf_sponge_matches_oracle(ctx, monkeypatch, log_n, n_cols, ra
     want = O.lde_commit(to_oracle_params(p), trace)
     monkeypatch.setenv("SB_SLAB_BYTES", str(64 << log_n))          # 8 columns per slab
     monkeypatch.setenv("SB_HASH_GROUP_COLS", "64")                 # one sponge launch per 64 columns
-    if layout == "colmajor":
+    if layout == "colmajor_old_kernels":
+        monkeypatch.setenv("SB_STREAM_OLD", "1")                    # round 2's sp / dp kernels carry the same state
+    if layout.startswith("colmajor"):
         got = ctx.lde_commit(p, trace)
     else:
         cols = [np.ascontiguousarray(trace[c]).copy() for c in range(n_cols)]

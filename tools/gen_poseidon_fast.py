@@ -154,6 +154,35 @@ def permute_lookahead(s0, t):
     return s == permute_naive(s0, rc)
 
 
+def eq_constants(rc):
+    """Round constants with the same permutation but only ONE non-zero constant in each partial round (dense-MDS kernels,
+    leafhash_mm.cuh).  x <- M . S0(x + c_r): the word-0 part of c_r is needed before the S-box, the rest commutes with S0
+    and with M -- M . (0, c^_r) joins the constants of the next round.  Rows 4..25 become (k_r, 0, .., 0), row 26 absorbs
+    what is left; rows 0..3 and 27..29 are unchanged; row 30 = zeros ("the round after the last")."""
+    M = mds_matrix()
+    eq = [list(rc[12 * r:12 * r + 12]) for r in range(30)] + [[0] * 12]
+    pend = list(eq[4])
+    for r in range(4, 26):
+        eq[r] = [pend[0]] + [0] * 11
+        pushed = mat_vec(M, [0] + pend[1:])
+        pend = [(a + b) % P for a, b in zip(rc[12 * (r + 1):12 * (r + 2)], pushed)]
+    eq[26] = pend
+    return [v for row in eq for v in row]
+
+
+def permute_eq(s, eq):
+    s = list(s)
+    M = mds_matrix()
+    for r in range(30):
+        s = [(x + eq[12 * r + i]) % P for i, x in enumerate(s)]
+        if r < 4 or r >= 26:
+            s = [sbox(x) for x in s]
+        else:
+            s[0] = sbox(s[0])
+        s = mat_vec(M, s)
+    return s
+
+
 def header(t):
     def arr(name, vals, per=4):
         out = ["#define %s { \\" % name]
@@ -178,6 +207,8 @@ def header(t):
     lines += arr("POSEIDON_FAST_D3", [v for row in t["d3"] for v in row])
     lines += arr("POSEIDON_FAST_K3", t["k3"])
     lines += arr("POSEIDON_FAST_U", t["u"])
+    lines += ["// dense-MDS kernels: the same permutation with one non-zero constant per partial round (31 x 12, row 30 = zeros)."]
+    lines += arr("POSEIDON_RC_EQ", t["rc_eq"])
     return "\n".join(lines) + "\n"
 
 
@@ -191,6 +222,9 @@ if __name__ == "__main__":
     for s in [[0] * 12, list(range(12)), [P - 1] * 12] + [[rnd.randrange(P) for _ in range(12)] for _ in range(20)]:
         assert permute_fast(s, t) == permute_naive(s, t["rc"]), "fast form differs from the naive rounds"
     assert permute_lookahead([rnd.randrange(P) for _ in range(12)], t), "look-ahead schedule differs"
+    t["rc_eq"] = eq_constants(t["rc"])
+    for s in [[0] * 12, [P - 1] * 12] + [[rnd.randrange(P) for _ in range(12)] for _ in range(10)]:
+        assert permute_eq(s, t["rc_eq"]) == permute_naive(s, t["rc"]), "equivalent constants differ from the naive rounds"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for rel in ("oracle/poseidon_fast.h", "starky_bls12_381_b200/csrc/poseidon_fast.h"):
         with open(os.path.join(root, rel), "w") as f:

@@ -235,8 +235,9 @@ int main(int argc, char** argv) {
     unsigned g32 = (nl + 31) / 32;
     for (int rep = 0; rep < 2; rep++) {
       float ms = time_ms([&] {
-        if (wps == 201) leaf_sponge_mm_kernel<1><<<g32, 64>>>(d_cols, ll, nl, 0, d_dig);
-        else if (wps == 202) leaf_sponge_mm_kernel<2><<<(nl + 63) / 64, 64>>>(d_cols, ll, nl, 0, d_dig);
+        if (wps == 201) leaf_sponge_mm_kernel<1><<<(nl + 7) / 8, 32>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 202) leaf_sponge_mm_kernel<2><<<g32, 64>>>(d_cols, ll, nl, 0, d_dig);
+        else if (wps == 204) leaf_sponge_mm_kernel<4><<<(nl + 63) / 64, 64>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 43) leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 44) leaf_sponge_dp_kernel<2><<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
         else if (wps == 45) leaf_sponge_ds_kernel<<<g32, 128>>>(d_cols, ll, nl, 0, d_dig);
@@ -257,7 +258,7 @@ int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "mm")) {   // dense MDS on IMMA (leafhash_mm.cuh) against the dp / sp kernels
     struct Shape { const char* name; uint32_t n_leaves, leaf_len; };
     for (const Shape& sh : {Shape{"ragged", 1000, 77}, Shape{"ragged2", 1013, 131}, Shape{"ML-like", 2048, 8003}, Shape{"PP-like", 4096, 8003},
-                            Shape{"ECC-like", 32768, 3339}, Shape{"FE-like", 32768, 8003}, Shape{"FE 1/2 box", 16384, 8003}}) {
+                            Shape{"ECC-like", 32768, 3339}, Shape{"FE-like", 32768, 8003}, Shape{"FE 1/2 box", 16384, 8003}, Shape{"FE 1/4 box", 8192, 8003}}) {
       const size_t cells = (size_t)sh.n_leaves * sh.leaf_len;
       u64 *d_cols, *d_dig;
       CK(cudaMalloc(&d_cols, 8 * cells)); CK(cudaMalloc(&d_dig, 32ull * sh.n_leaves));
@@ -277,10 +278,9 @@ int main(int argc, char** argv) {
       run("ref (1 thread per leaf)", [&] { ref_leaf_kernel<<<g32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, d_dig); }, true);
       run("dp<0>", [&] { leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       run("sp<0>", [&] { leaf_sponge_sp_kernel<0><<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
-      run("mm<1> 16 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<1><<<(sh.n_leaves + 31) / 32, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
-      run("mm<1> 16 leaves per warp, block 32", [&] { leaf_sponge_mm_kernel<1><<<(sh.n_leaves + 15) / 16, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
-      run("mm<2> 32 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<2><<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
-      run("mm<2> 32 leaves per warp, block 32", [&] { leaf_sponge_mm_kernel<2><<<(sh.n_leaves + 31) / 32, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<1>  8 leaves per warp, block 32", [&] { leaf_sponge_mm_kernel<1><<<(sh.n_leaves + 7) / 8, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<2> 16 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<2><<<(sh.n_leaves + 31) / 32, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<4> 32 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<4><<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       cudaFree(d_cols); cudaFree(d_dig);
     }
     printf("lab done\n");
