@@ -20,18 +20,54 @@
 #pragma once
 #include "leafhash.cuh"
 
+template <int DBG = 0>
 __device__ __forceinline__ void imma_16832_u8(u32 (&d)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1) {
+  if (DBG & 2) { d[0] = a0 ^ b0; d[1] = a1 ^ b1; d[2] = a2 ^ b0; d[3] = a3 ^ b1; return; }
   asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
       : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
 // the same with the accumulator as input: d = a b + d
+template <int DBG = 0>
 __device__ __forceinline__ void imma_16832_u8_acc(u32 (&d)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1) {
+  if (DBG & 2) { d[0] += a0 ^ b0; d[1] += a1 ^ b1; d[2] += a2 ^ b0; d[3] += a3 ^ b1; return; }
   asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 static __constant__ u64 c_poseidon_rc_eq[31 * 12] = POSEIDON_RC_EQ;
+// the Goldilocks fold of gl_mul_lazy with x2 * eps + (x1:x0) as one multiply-add (two instructions move from the ALU to the FMA pipe)
+__device__ __forceinline__ u64 gl_mul_lazy_fma(u64 a, u64 b) {
+  const u64 lo = a * b, hi = __umul64hi(a, b);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 c1, b1;\n\t"
+      "mad.lo.cc.u32 %0, %4, 0xFFFFFFFF, %2;\n\t"
+      "madc.hi.cc.u32 %1, %4, 0xFFFFFFFF, %3;\n\t"
+      "addc.u32 c1, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, %5;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 b1, 0, 0;\n\t"
+      "neg.s32 c1, c1;\n\t"
+      "add.cc.u32 %0, %0, c1;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "sub.cc.u32 %0, %0, b1;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+  return ((u64)r1 << 32) | r0;
+}
+// x^7.  One warp per scheduler (NL == 1): the multiply-add fold is 3 % shorter in latency; with more warps the two
+// forms measure the same (profiles/r2_poseidon_lab_mm.txt)
+template <int NL, int DBG>
+__device__ __forceinline__ u64 mm_sbox(u64 x) {
+  if ((NL == 1) != ((DBG & 16) != 0)) {
+    const u64 x2 = gl_mul_lazy_fma(x, x), x4 = gl_mul_lazy_fma(x2, x2), x3 = gl_mul_lazy_fma(x2, x);
+    return gl_mul_lazy_fma(x3, x4);
+  }
+  return poseidon_sbox(x);
+}
 __device__ __forceinline__ u64 shfl64(u64 v, unsigned src) {
   const u32 lo = __shfl_sync(0xFFFFFFFFu, (u32)v, src), hi = __shfl_sync(0xFFFFFFFFu, (u32)(v >> 32), src);
   return ((u64)hi << 32) | lo;
@@ -40,7 +76,10 @@ __device__ __forceinline__ u64 shfl64(u64 v, unsigned src) {
 // NL = leaves per lane.  4: two 16-row tiles, 32 leaves per warp; 2: one tile, 16 leaves per warp; 1: half a tile (rows
 // 8..15 unused), 8 leaves per warp -- the latency-bound shapes (MillerLoop 2048, PairingPrecomp 4096 leaves, a FinalExp
 // shard on 8 GPUs), where wall time = chain length x time of one permutation and the fewest instructions per warp win.
-template <int NL>
+// DBG (lab only; tools/perf/poseidon_lab mmx).  Timing by elimination, wrong digests: 1 = no S-box in partial rounds,
+// 2 = no matrix instruction, 4 = no recombination, 8 = no S-box in full rounds.  Correct variants: 16 = the other fold in
+// the S-box, 32 = limb pairs as PRMT + IADD3 on the ALU pipe instead of IMAD.
+template <int NL, int DBG = 0>
 __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
                                                             uint32_t n_leaves, unsigned log_block,
                                                             u64* __restrict__ digests,
@@ -129,10 +168,11 @@ __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const
       const u64* w = s[2 * m + h];
 #pragma unroll
       for (int half = 0; half < 2; half++) {
+        // word 0 (the only one behind the S-box of a partial round) enters last: one PRMT between x^7 and the instruction
         const u32 x0 = (u32)(w[0] >> (32 * half)), x1 = (u32)(w[1] >> (32 * half)), x2 = (u32)(w[2] >> (32 * half));
-        const u32 t0 = __byte_perm(x0, x1, 0x5140), t1 = __byte_perm(x0, x1, 0x7362);
-        const u32 l0 = __byte_perm(t0, x2, 0x4410), l1 = __byte_perm(t0, x2, 0x5532);
-        const u32 l2 = __byte_perm(t1, x2, 0x6610), l3 = __byte_perm(t1, x2, 0x7732);
+        const u32 u0 = __byte_perm(x1, x2, 0x5140), u1 = __byte_perm(x1, x2, 0x7362);
+        const u32 l0 = __byte_perm(x0, u0, 0x5540), l1 = __byte_perm(x0, u0, 0x7761);
+        const u32 l2 = __byte_perm(x0, u1, 0x5542), l3 = __byte_perm(x0, u1, 0x7763);
         if constexpr (NL == 1) { Q[half][0] = l0; Q[half][2] = l1; Q[half][1] = l2; Q[half][3] = l3; }
         else { Q[2 * half][h] = l0; Q[2 * half][2 + h] = l1; Q[2 * half + 1][h] = l2; Q[2 * half + 1][2 + h] = l3; }
       }
@@ -143,9 +183,10 @@ __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const
     u32 p[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      if constexpr (NL == 1) p[q] = D[q >> 1][2 * (q & 1)] + (D[q >> 1][2 * (q & 1) + 1] << 8);
-      else p[q] = D[q][2 * h] + (D[q][2 * h + 1] << 8);
+      const u32 de = NL == 1 ? D[q >> 1][2 * (q & 1)] : D[q][2 * h], dod = NL == 1 ? D[q >> 1][2 * (q & 1) + 1] : D[q][2 * h + 1];
+      p[q] = (DBG & 32) ? de + __byte_perm(dod, 0, 0x2104) : de + (dod << 8);
     }
+    if (DBG & 4) return ((u64)(p[0] ^ p[2]) << 32 | (p[1] ^ p[3])) + cl + ch;
     const u64 al = (u64)p[1] * 65536ull + cl + p[0], ah = (u64)p[3] * 65536ull + ch + p[2];     // both < 2^41
     return mds_recombine((u32)al, (u32)(al >> 32), (u32)ah, (u32)(ah >> 32));
   };
@@ -163,7 +204,7 @@ __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const
 #pragma unroll
       for (int j = 0; j < 3; j++)
 #pragma unroll
-        for (int i = 0; i < NI; i++) imma_16832_u8(D[j][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[j][0], bf[j][1]);
+        for (int i = 0; i < NI; i++) imma_16832_u8<DBG>(D[j][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[j][0], bf[j][1]);
 #pragma unroll
       for (int h = 0; h < H; h++)
 #pragma unroll
@@ -173,34 +214,53 @@ __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const
   // linear layer that feeds a partial round: only word 0 has a constant; it enters as the accumulator of row 0's
   // instructions, which are issued first -- the next S-box waits for them alone
   const unsigned own0 = t == 0 ? 1u : 0u;
-  auto linear_layer_p = [&](int rd) {
+  auto issue_p = [&](int m, int rd, u32 (&D)[3][NI][4]) {
     const uint4* cw = reinterpret_cast<const uint4*>(&rcw[rd - 4][own0][0][0]);
+    u32 Q[NI][4];
+    pack(m, Q);
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+      const uint4 c = cw[i];
+      D[0][i][0] = c.x; D[0][i][1] = c.y; D[0][i][2] = c.z; D[0][i][3] = c.w;
+      imma_16832_u8_acc<DBG>(D[0][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[0][0], bf[0][1]);
+    }
+#pragma unroll
+    for (int j = 1; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < NI; i++) imma_16832_u8<DBG>(D[j][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[j][0], bf[j][1]);
+  };
+  auto linear_layer_p = [&](int rd) {
 #pragma unroll
     for (int m = 0; m < MT; m++) {
-      u32 Q[NI][4];
-      pack(m, Q);
       u32 D[3][NI][4];
-#pragma unroll
-      for (int i = 0; i < NI; i++) {
-        const uint4 c = cw[i];
-        D[0][i][0] = c.x; D[0][i][1] = c.y; D[0][i][2] = c.z; D[0][i][3] = c.w;
-        imma_16832_u8_acc(D[0][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[0][0], bf[0][1]);
-      }
-#pragma unroll
-      for (int j = 1; j < 3; j++)
-#pragma unroll
-        for (int i = 0; i < NI; i++) imma_16832_u8(D[j][i], Q[i][0], Q[i][1], Q[i][2], Q[i][3], bf[j][0], bf[j][1]);
+      issue_p(m, rd, D);
 #pragma unroll
       for (int h = 0; h < H; h++)
 #pragma unroll
         for (int j = 0; j < 3; j++) s[2 * m + h][j] = recombine(D[j], h, 0, 0);
     }
   };
+  // the 3 NL S-boxes of a full round.  DBG 64 / 128 / 192 (lab): groups of 3 / 6 / 12 values advance in lock step in
+  // source order (x^2 of every value, then x^4 and x^3, then x^7) instead of one x^7 after the other
   auto sbox_all = [&]() {
+    constexpr int G = (DBG & 192) == 64 ? 3 : (DBG & 192) == 128 ? 6 : (DBG & 192) == 192 ? 12 : 1;
+    if constexpr (G == 1 || (3 * NL) % G != 0) {
 #pragma unroll
-    for (int L = 0; L < NL; L++)
+      for (int L = 0; L < NL; L++)
 #pragma unroll
-      for (int k = 0; k < 3; k++) s[L][k] = poseidon_sbox(s[L][k]);
+        for (int k = 0; k < 3; k++) s[L][k] = (DBG & 8) ? s[L][k] + 3 : mm_sbox<NL, DBG>(s[L][k]);
+    } else {
+#pragma unroll
+      for (int g0 = 0; g0 < 3 * NL; g0 += G) {
+        u64 x2[G], x3[G], x4[G];
+#pragma unroll
+        for (int i = 0; i < G; i++) { const u64 x = s[(g0 + i) / 3][(g0 + i) % 3]; x2[i] = gl_mul_lazy(x, x); }
+#pragma unroll
+        for (int i = 0; i < G; i++) { const u64 x = s[(g0 + i) / 3][(g0 + i) % 3]; x4[i] = gl_mul_lazy(x2[i], x2[i]); x3[i] = gl_mul_lazy(x2[i], x); }
+#pragma unroll
+        for (int i = 0; i < G; i++) s[(g0 + i) / 3][(g0 + i) % 3] = gl_mul_lazy(x3[i], x4[i]);
+      }
+    }
   };
   // word 0 of the quad's NL leaves sits on lane t = 0: lane L of the quad takes leaf L (lanes >= NL redo leaf 0)
   auto sbox_word0 = [&]() {
@@ -208,7 +268,7 @@ __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const
     u64 v = s[0][0];
 #pragma unroll
     for (int L = 1; L < NL; L++) { const u64 x = shfl64(s[L][0], q0); if (t == (unsigned)L) v = x; }
-    const u64 y = poseidon_sbox(v);
+    const u64 y = (DBG & 1) ? v + 3 : mm_sbox<NL, DBG>(v);
 #pragma unroll
     for (int L = 1; L < NL; L++) { const u64 x = shfl64(y, q0 | L); if (t == 0) s[L][0] = x; }
     if (t == 0) s[0][0] = y;

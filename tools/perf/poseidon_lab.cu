@@ -286,6 +286,52 @@ int main(int argc, char** argv) {
     printf("lab done\n");
     return 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "mmx")) {   // where does the time of the matrix-instruction sponge go: timing by elimination (wrong digests)
+    struct Shape { const char* name; uint32_t n_leaves, leaf_len; };
+    for (const Shape& sh : {Shape{"ML-like", 2048, 8003}, Shape{"FE-like", 32768, 8003}}) {
+      const size_t cells = (size_t)sh.n_leaves * sh.leaf_len;
+      u64 *d_cols, *d_dig;
+      CK(cudaMalloc(&d_cols, 8 * cells)); CK(cudaMalloc(&d_dig, 32ull * sh.n_leaves));
+      fill_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_cols, cells);
+      CK(cudaDeviceSynchronize());
+      const unsigned g8 = (sh.n_leaves + 7) / 8, g64 = (sh.n_leaves + 63) / 64;
+      const double chain = (sh.leaf_len + 7) / 8;
+      printf("%-10s N=%6u C=%6u\n", sh.name, sh.n_leaves, sh.leaf_len);
+      auto run = [&](const char* name, auto launch) {
+        float t = time_ms(launch);
+        printf("    %-58s %9.3f ms  %8.0f cycles per permutation\n", name, t, t * 1e-3 / chain * 1.965e9);
+      };
+#define MMX(NLV, DBGV, G, B, label) run(label, [&] { leaf_sponge_mm_kernel<NLV, DBGV><<<G, B>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); })
+      MMX(1, 0, g8, 32, "mm<1> complete");
+      MMX(1, 1, g8, 32, "mm<1> no partial-round S-box");
+      MMX(1, 2, g8, 32, "mm<1> no matrix instruction");
+      MMX(1, 4, g8, 32, "mm<1> no recombination");
+      MMX(1, 8, g8, 32, "mm<1> no full-round S-boxes");
+      MMX(1, 9, g8, 32, "mm<1> no S-box at all");
+      MMX(1, 15, g8, 32, "mm<1> pack + constants + loop only");
+      MMX(4, 0, g64, 64, "mm<4> complete");
+      MMX(4, 1, g64, 64, "mm<4> no partial-round S-box");
+      MMX(4, 2, g64, 64, "mm<4> no matrix instruction");
+      MMX(4, 4, g64, 64, "mm<4> no recombination");
+      MMX(4, 8, g64, 64, "mm<4> no full-round S-boxes");
+      MMX(4, 9, g64, 64, "mm<4> no S-box at all");
+      MMX(4, 64, g64, 64, "mm<4> (correct) full-round S-boxes in lock step, groups of 3");
+      MMX(4, 128, g64, 64, "mm<4> (correct) full-round S-boxes in lock step, groups of 6");
+      MMX(4, 192, g64, 64, "mm<4> (correct) full-round S-boxes in lock step, groups of 12");
+      MMX(2, 0, (sh.n_leaves + 31) / 32, 64, "mm<2> complete");
+      MMX(2, 64, (sh.n_leaves + 31) / 32, 64, "mm<2> (correct) full-round S-boxes in lock step, groups of 3");
+      MMX(2, 128, (sh.n_leaves + 31) / 32, 64, "mm<2> (correct) full-round S-boxes in lock step, groups of 6");
+      MMX(1, 64, g8, 32, "mm<1> (correct) full-round S-boxes in lock step, groups of 3");
+      MMX(4, 16, g64, 64, "mm<4> (correct) fold on the FMA pipe");
+      MMX(4, 32, g64, 64, "mm<4> (correct) limb pairs on the ALU pipe");
+      MMX(4, 48, g64, 64, "mm<4> (correct) both");
+      MMX(1, 16, g8, 32, "mm<1> (correct) fold on the FMA pipe");
+      MMX(1, 32, g8, 32, "mm<1> (correct) limb pairs on the ALU pipe");
+      cudaFree(d_cols); cudaFree(d_dig);
+    }
+    printf("lab done\n");
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "dp")) {   // throughput-bound shapes: which warp owns the partial-round S-box
     struct Shape { const char* name; uint32_t n_leaves, leaf_len; };
     for (const Shape& sh : {Shape{"ECC-like", 32768, 3339}, Shape{"FE-like", 32768, 8003}, Shape{"FE/4", 32768, 18382}, Shape{"FE 1/2 box", 16384, 18382}}) {
