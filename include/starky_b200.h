@@ -180,6 +180,21 @@ int sb_prove_fp12_mul(sb_ctx* ctx, const sb_params* p, const uint32_t* x, const 
 int sb_witness_ecc_agg(const uint32_t* points, const uint8_t* bits, uint32_t num_rows, uint32_t* trace_out,
                        uint64_t* public_inputs_out, uint32_t* result_out);
 int sb_prove_ecc_agg(sb_ctx* ctx, const sb_params* p, const uint32_t* points, const uint8_t* bits, sb_proof** out);
+/*      sb_witness_pairing_precomp: PairingPrecompStark::generate_trace (calc_pairing_precomp.rs:150-366) + the public inputs of
+ *      calc_pairing_precomp_main (aggregate_proof.rs:24-69).  q: the projective G2 point x ++ y ++ z, each an Fp2 of 2 x 12
+ *      little-endian u32 limbs ([3][24]).  trace_out: [num_rows][29376]; public_inputs_out: 4968 values.
+ *      sb_witness_miller_loop: MillerLoopStark::generate_trace (miller_loop.rs:87-160) + miller_loop_main's public inputs
+ *      (aggregate_proof.rs:71-121).  g1: the affine G1 point x ++ y ([24]); q as above.  trace_out: [num_rows][97330];
+ *      public_inputs_out: 5064 values (point, 68 x 3 line coefficients, result).
+ *      sb_witness_final_exp: FinalExponentiateStark::generate_trace (final_exponentiate.rs:137-281) + final_exponentiate_main's
+ *      public inputs (aggregate_proof.rs:153-184).  x: the Fp12 input ([12][12]).  num_rows = 8192; trace_out:
+ *      [8192][73527] (2.4 GB); public_inputs_out: 288 values (x, result).  sb_prove_*: both steps in one call. */
+int sb_witness_pairing_precomp(const uint32_t* q, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out);
+int sb_witness_miller_loop(const uint32_t* g1, const uint32_t* q, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out);
+int sb_witness_final_exp(const uint32_t* x, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out);
+int sb_prove_pairing_precomp(sb_ctx* ctx, const sb_params* p, const uint32_t* q, sb_proof** out);
+int sb_prove_miller_loop(sb_ctx* ctx, const sb_params* p, const uint32_t* g1, const uint32_t* q, sb_proof** out);
+int sb_prove_final_exp(sb_ctx* ctx, const sb_params* p, const uint32_t* x, sb_proof** out);
 const char* sb_witness_last_error(void);
 
 /* ---- proof wire formats: the proof as bytes for a consumer that does not link this library -- the

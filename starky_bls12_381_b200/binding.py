@@ -290,6 +290,39 @@ def witness_ecc_agg(points, bits, num_rows=8192):
     return trace, pis, (val(res[:12]), val(res[12:]))
 
 
+def fp2_limbs(vals):
+    """Fp2 values [(c0, c1), ...] -> uint32 [len][24] little-endian limbs."""
+    return np.array([[(int(c) >> (32 * i)) & 0xFFFFFFFF for c in v for i in range(12)] for v in vals], dtype=np.uint32)
+
+
+def _witness_call(fn_name, args, num_rows, n_cols, n_pis):
+    trace = np.empty((num_rows, n_cols), np.uint32)
+    pis = np.empty(n_pis, np.uint64)
+    L = lib()
+    fn = getattr(L, fn_name)
+    fn.argtypes = [C.c_void_p] * len(args) + [C.c_uint32, C.c_void_p, C.c_void_p]
+    rc = fn(*[_ptr(a) for a in args], num_rows, _ptr(trace), _ptr(pis))
+    if rc:
+        raise SbError(rc, L.sb_witness_last_error().decode())
+    return trace, pis
+
+
+def witness_pairing_precomp(x, y, z, num_rows=1024):
+    """sb_witness_pairing_precomp: (trace uint32 [num_rows][29376] row-major, public inputs uint64 [4968])."""
+    return _witness_call("sb_witness_pairing_precomp", [fp2_limbs([x, y, z])], num_rows, 29376, 4968)
+
+
+def witness_miller_loop(x, y, q, num_rows=1024):
+    """sb_witness_miller_loop: (trace uint32 [num_rows][97330] row-major, public inputs uint64 [5064])."""
+    g1 = np.array([(int(v) >> (32 * i)) & 0xFFFFFFFF for v in (x, y) for i in range(12)], dtype=np.uint32)
+    return _witness_call("sb_witness_miller_loop", [g1, fp2_limbs(list(q))], num_rows, 97330, 5064)
+
+
+def witness_final_exp(x, num_rows=8192):
+    """sb_witness_final_exp: (trace uint32 [8192][73527] row-major, public inputs uint64 [288])."""
+    return _witness_call("sb_witness_final_exp", [fp12_limbs(x)], num_rows, 73527, 288)
+
+
 def prove_batch(contexts, jobs):
     """sb_prove_batch: jobs = [(Params, trace pointer or array, layout, public inputs)], returns [(Proof or SbError, ms)] in
     job order.  The proofs run on `contexts` with the library's scheduler (internal host threads)."""
@@ -415,6 +448,34 @@ class Context:
         out = C.POINTER(_CProof)()
         xl, yl = fp12_limbs(x), fp12_limbs(y)
         self._check(lib().sb_prove_fp12_mul(self._h, C.byref(p), _ptr(xl), _ptr(yl), C.byref(out)))
+        return Proof(out)
+
+    def prove_pairing_precomp(self, p, x, y, z):
+        """sb_prove_pairing_precomp: proof from the projective G2 point (witness generated in C++ on the host)."""
+        out = C.POINTER(_CProof)()
+        L = lib()
+        L.sb_prove_pairing_precomp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        q = fp2_limbs([x, y, z])
+        self._check(L.sb_prove_pairing_precomp(self._h, C.byref(p), _ptr(q), C.byref(out)))
+        return Proof(out)
+
+    def prove_miller_loop(self, p, x, y, q):
+        """sb_prove_miller_loop: proof from the G1 point (x, y) and the projective G2 point q."""
+        out = C.POINTER(_CProof)()
+        L = lib()
+        L.sb_prove_miller_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        g1 = np.array([(int(v) >> (32 * i)) & 0xFFFFFFFF for v in (x, y) for i in range(12)], dtype=np.uint32)
+        ql = fp2_limbs(list(q))
+        self._check(L.sb_prove_miller_loop(self._h, C.byref(p), _ptr(g1), _ptr(ql), C.byref(out)))
+        return Proof(out)
+
+    def prove_final_exp(self, p, x):
+        """sb_prove_final_exp: proof from the Fp12 input."""
+        out = C.POINTER(_CProof)()
+        L = lib()
+        L.sb_prove_final_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        xl = fp12_limbs(x)
+        self._check(L.sb_prove_final_exp(self._h, C.byref(p), _ptr(xl), C.byref(out)))
         return Proof(out)
 
     def synchronize(self):

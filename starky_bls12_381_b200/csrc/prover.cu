@@ -2,6 +2,8 @@
 // (/root/reference/src/aggregate_proof.rs:59,105,138,169,212).  The Fiat-Shamir transcript
 // (plonky2 Challenger, ~10^2 permutations) runs on the host between kernels; only caps, openings, the two combined
 // polynomials and the final proof cross PCIe.
+#include <functional>
+#include <memory>
 #include <string.h>
 
 #include <stdlib.h>
@@ -669,6 +671,39 @@ int sb_prove_ecc_agg(sb_ctx* ctx, const sb_params* p, const uint32_t* points, co
     if (sb_witness_ecc_agg(points, bits, rows, trace.data(), pis.data(), nullptr)) SB_THROW(SB_EINVAL, "%s", sb_witness_last_error());
     return sb_prove(ctx, p, trace.data(), SB_TRACE_ROWMAJOR_U32, pis.data(), out);
   } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+
+
+// the three larger starks from their operands (witness.cpp), then the proof.  The trace is generated into a malloc'd
+// row-major u32 buffer (FinalExp: 2.4 GB) and crosses PCIe once, in slabs, behind the commitment kernels.
+static int prove_from_witness(sb_ctx* ctx, const sb_params* p, uint32_t stark_id, uint32_t n_cols, uint32_t n_pis, const char* what,
+                              const std::function<int(uint32_t rows, uint32_t* trace, uint64_t* pis)>& gen, sb_proof** out) {
+  try {
+    check_params(p);
+    if (p->stark_id != stark_id || p->n_cols != n_cols || p->n_public_inputs != n_pis)
+      SB_THROW(SB_EINVAL, "%s needs that stark's parameters (%u columns, %u public inputs)", what, n_cols, n_pis);
+    const uint32_t rows = 1u << p->log_n;
+    std::unique_ptr<uint32_t, void (*)(void*)> trace((uint32_t*)malloc(4ull * rows * n_cols), free);
+    if (!trace) SB_THROW(SB_EINVAL, "%s: out of host memory for the trace", what);
+    std::vector<uint64_t> pis(n_pis);
+    if (gen(rows, trace.get(), pis.data())) SB_THROW(SB_EINVAL, "%s", sb_witness_last_error());
+    return sb_prove(ctx, p, trace.get(), SB_TRACE_ROWMAJOR_U32, pis.data(), out);
+  } catch (const SbError& e) { return sb_fail(ctx, e); }
+}
+int sb_prove_pairing_precomp(sb_ctx* ctx, const sb_params* p, const uint32_t* q, sb_proof** out) {
+  if (!ctx || !p || !q || !out) return SB_EINVAL;
+  return prove_from_witness(ctx, p, SB_STARK_PAIRING_PRECOMP, 29376, 4968, "sb_prove_pairing_precomp",
+                            [&](uint32_t rows, uint32_t* t, uint64_t* pi) { return sb_witness_pairing_precomp(q, rows, t, pi); }, out);
+}
+int sb_prove_miller_loop(sb_ctx* ctx, const sb_params* p, const uint32_t* g1, const uint32_t* q, sb_proof** out) {
+  if (!ctx || !p || !g1 || !q || !out) return SB_EINVAL;
+  return prove_from_witness(ctx, p, SB_STARK_MILLER_LOOP, 97330, 5064, "sb_prove_miller_loop",
+                            [&](uint32_t rows, uint32_t* t, uint64_t* pi) { return sb_witness_miller_loop(g1, q, rows, t, pi); }, out);
+}
+int sb_prove_final_exp(sb_ctx* ctx, const sb_params* p, const uint32_t* x, sb_proof** out) {
+  if (!ctx || !p || !x || !out) return SB_EINVAL;
+  return prove_from_witness(ctx, p, SB_STARK_FINAL_EXP, 73527, 288, "sb_prove_final_exp",
+                            [&](uint32_t rows, uint32_t* t, uint64_t* pi) { return sb_witness_final_exp(x, rows, t, pi); }, out);
 }
 
 void sb_proof_free(sb_proof* proof) {

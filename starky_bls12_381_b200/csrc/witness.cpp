@@ -3,7 +3,9 @@
 //   fp.rs:185-428   addition / subtraction / multiply_single / reduce_single / range check / 12x12-limb multiplication / reduction
 //   fp2.rs:187-456  Fp2 addition, subtraction, multiplication, +- with reduction, non-residue multiplication
 //   fp6.rs:124-303  Fp6 addition, subtraction, +- with reduction, non-residue multiplication, multiplication
-//   fp12.rs:186-232 Fp12 multiplication;   fp12_mul.rs:44-48 FP12MulStark::generate_trace
+//   fp12.rs:132-426 multiply_by_014, Fp12 multiplication, cyclotomic square / exponentiation, Frobenius map, conjugate
+//   fp12_mul.rs:44-48, ecc_aggregate.rs:37-82, calc_pairing_precomp.rs:150-366, miller_loop.rs:87-160,
+//   final_exponentiate.rs:137-281: generate_trace of the five starks
 // over the BLS12-381 tower of native.rs (quirks kept because they show in the trace: add_fp subtracts p at most once,
 // -x is p - x).  Column offsets come from the reference's constants (witness_offsets.h, generated from
 // witness/offsets.json).  Cells are written as row-major uint32_t -- every cell the reference writes is a u32 limb, a carry
@@ -12,6 +14,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -181,6 +184,143 @@ Fp12 fp12_mul_native(const Fp12& x, const Fp12& y) {    // native.rs:1009-1027
   Fp12 r;
   for (int k = 0; k < 6; k++) { r.c[k] = xx.c[k]; r.c[6 + k] = yy.c[k]; }
   return r;
+}
+
+
+// ---- the rest of native.rs that the three larger starks need ----
+const u64 BLS_X = 15132376222941642752ull;                                                    // native.rs:20-22
+Fp fp_neg(const Fp& x) { return sub(MODP(), x); }                                             // native.rs:417-424: -0 = p
+const Fp& HALF() { static const Fp h = fp_inv(Big(2)); return h; }
+Fp2 fp2_neg(const Fp2& x) { return {{fp_neg(x.c[0]), fp_neg(x.c[1])}}; }
+Fp2 fp2_mul_fp(const Fp2& x, const Fp& k) { return {{fp_mul(x.c[0], k), fp_mul(x.c[1], k)}}; }
+Fp2 fp2_multiply_by_b(const Fp2& x) {
+  const Fp t0 = fp_mul(x.c[0], Big(4)), t1 = fp_mul(x.c[1], Big(4));
+  return {{fp_sub(t0, t1), fp_add(t0, t1)}};
+}
+Fp2 fp2_inv(const Fp2& x) {
+  const Fp f = fp_inv(fp_add(fp_mul(x.c[0], x.c[0]), fp_mul(x.c[1], x.c[1])));
+  return {{fp_mul(f, x.c[0]), fp_mul(f, fp_neg(x.c[1]))}};
+}
+Fp frob_fp(const u32 (*tab)[12], int i) { return Big::from_limbs(tab[i], 12); }
+Fp2 frob_fp2(const u32 (*tab)[12], int i) { return {{frob_fp(tab, 2 * i), frob_fp(tab, 2 * i + 1)}}; }
+Fp2 fp2_frobenius(const Fp2& x, unsigned pw) { return {{x.c[0], fp_mul(x.c[1], frob_fp(woff::FP2_FROB, pw % 2))}}; }   // native.rs:1058-1064
+Fp6 fp6_neg(const Fp6& x) { Fp6 r; for (int i = 0; i < 6; i++) r.c[i] = fp_neg(x.c[i]); return r; }
+Fp6 fp6_multiply_by_01(const Fp6& x, const Fp2& b0, const Fp2& b1) {
+  const Fp2 c0 = part(x, 0), c1 = part(x, 1), c2 = part(x, 2);
+  const Fp2 t0 = fp2_mul(c0, b0), t1 = fp2_mul(c1, b1);
+  const Fp2 xx = fp2_add(fp2_mul_by_nonresidue(fp2_mul(c2, b1)), t0);
+  const Fp2 t6 = fp2_mul(fp2_add(b0, b1), fp2_add(c0, c1));
+  return join(xx, fp2_sub(fp2_sub(t6, t0), t1), fp2_add(fp2_mul(c2, b0), t1));
+}
+Fp6 fp6_multiply_by_1(const Fp6& x, const Fp2& b1) {
+  return join(fp2_mul_by_nonresidue(fp2_mul(part(x, 2), b1)), fp2_mul(part(x, 0), b1), fp2_mul(part(x, 1), b1));
+}
+Fp6 fp6_inv(const Fp6& x) {                                                                   // native.rs:720-734
+  const Fp2 c0 = part(x, 0), c1 = part(x, 1), c2 = part(x, 2);
+  const Fp2 t0 = fp2_sub(fp2_mul(c0, c0), fp2_mul_by_nonresidue(fp2_mul(c2, c1)));
+  const Fp2 t1 = fp2_sub(fp2_mul_by_nonresidue(fp2_mul(c2, c2)), fp2_mul(c0, c1));
+  const Fp2 t2 = fp2_sub(fp2_mul(c1, c1), fp2_mul(c0, c2));
+  const Fp2 t4 = fp2_inv(fp2_add(fp2_mul_by_nonresidue(fp2_add(fp2_mul(c2, t1), fp2_mul(c1, t2))), fp2_mul(c0, t0)));
+  return join(fp2_mul(t4, t0), fp2_mul(t4, t1), fp2_mul(t4, t2));
+}
+Fp6 fp6_frobenius(const Fp6& x, unsigned pw) {                                                // native.rs:1126-1145
+  return join(fp2_frobenius(part(x, 0), pw), fp2_mul(fp2_frobenius(part(x, 1), pw), frob_fp2(woff::FP6_FROB_1, pw % 6)),
+              fp2_mul(fp2_frobenius(part(x, 2), pw), frob_fp2(woff::FP6_FROB_2, pw % 6)));
+}
+Fp12 join12(const Fp6& a, const Fp6& b) { Fp12 r; for (int k = 0; k < 6; k++) { r.c[k] = a.c[k]; r.c[6 + k] = b.c[k]; } return r; }
+Fp12 fp12_one() { Fp12 r; r.c[0] = Big(1); return r; }
+Fp12 fp12_inv(const Fp12& x) {                                                                // native.rs:932-940
+  const Fp6 c0 = half(x, 0), c1 = half(x, 1);
+  const Fp6 t = fp6_inv(fp6_sub(fp6_mul(c0, c0), fp6_mul_by_nonresidue(fp6_mul(c1, c1))));
+  return join12(fp6_mul(c0, t), fp6_neg(fp6_mul(c1, t)));
+}
+Fp12 fp12_multiply_by_014(const Fp12& x, const Fp2& o0, const Fp2& o1, const Fp2& o4) {       // native.rs:1228-1244
+  const Fp6 c0 = half(x, 0), c1 = half(x, 1);
+  const Fp6 t0 = fp6_multiply_by_01(c0, o0, o1), t1 = fp6_multiply_by_1(c1, o4);
+  const Fp6 xx = fp6_add(fp6_mul_by_nonresidue(t1), t0);
+  const Fp6 t5 = fp6_multiply_by_01(fp6_add(c1, c0), o0, fp2_add(o1, o4));
+  return join12(xx, fp6_sub(fp6_sub(t5, t0), t1));
+}
+Fp12 fp12_conjugate(const Fp12& x) { return join12(half(x, 0), fp6_neg(half(x, 1))); }        // native.rs:1246-1252
+Fp12 fp12_frobenius(const Fp12& x, unsigned pw) {                                             // native.rs:1202-1224
+  const Fp6 r0 = fp6_frobenius(half(x, 0), pw), c = fp6_frobenius(half(x, 1), pw);
+  const Fp2 k = frob_fp2(woff::FP12_FROB, pw % 12);
+  return join12(r0, join(fp2_mul(part(c, 0), k), fp2_mul(part(c, 1), k), fp2_mul(part(c, 2), k)));
+}
+Fp2 part12(const Fp12& x, int i) { return {{x.c[2 * i], x.c[2 * i + 1]}}; }
+void fp4_square(const Fp2& a, const Fp2& b, Fp2& o0, Fp2& o1) {                               // native.rs:224-231
+  const Fp2 a2 = fp2_mul(a, a), b2 = fp2_mul(b, b), sm = fp2_add(a, b);
+  o0 = fp2_add(fp2_mul_by_nonresidue(b2), a2);
+  o1 = fp2_sub(fp2_sub(fp2_mul(sm, sm), a2), b2);
+}
+Fp12 fp12_cyclotomic_square(const Fp12& x) {                                                  // native.rs:1254-1298
+  const Fp2 c0c0 = part12(x, 0), c0c1 = part12(x, 1), c0c2 = part12(x, 2), c1c0 = part12(x, 3), c1c1 = part12(x, 4), c1c2 = part12(x, 5);
+  Fp2 t00, t01, t10, t11, t20, t21;
+  fp4_square(c0c0, c1c1, t00, t01); fp4_square(c1c0, c0c2, t10, t11); fp4_square(c0c1, c1c2, t20, t21);
+  const Fp2 t3 = fp2_mul_by_nonresidue(t21);
+  const Fp two = Big(2);
+  const Fp2 c[6] = {fp2_add(fp2_mul_fp(fp2_sub(t00, c0c0), two), t00), fp2_add(fp2_mul_fp(fp2_sub(t10, c0c1), two), t10),
+                    fp2_add(fp2_mul_fp(fp2_sub(t20, c0c2), two), t20), fp2_add(fp2_mul_fp(fp2_add(t3, c1c0), two), t3),
+                    fp2_add(fp2_mul_fp(fp2_add(t01, c1c1), two), t01), fp2_add(fp2_mul_fp(fp2_add(t11, c1c2), two), t11)};
+  Fp12 r;
+  for (int i = 0; i < 6; i++) { r.c[2 * i] = c[i].c[0]; r.c[2 * i + 1] = c[i].c[1]; }
+  return r;
+}
+// calc_precomp_stuff_loop0 / loop1 (native.rs:291-372): the named intermediates of one doubling / one addition step
+struct Loop0 { Fp2 new_rx, new_ry, new_rz, t0, t1, x0, t2, t3, x1, t4, x3, x2, x4, x5, x6, x7, x8, x9, x10, x11, x12, x13; };
+Loop0 calc_precomp_stuff_loop0(const Fp2& rx, const Fp2& ry, const Fp2& rz) {
+  Loop0 v;
+  const Fp three = Big(3), two = Big(2);
+  v.t0 = fp2_mul(ry, ry); v.t1 = fp2_mul(rz, rz); v.x0 = fp2_mul_fp(v.t1, three); v.t2 = fp2_multiply_by_b(v.x0);
+  v.t3 = fp2_mul_fp(v.t2, three); v.x1 = fp2_mul(ry, rz); v.t4 = fp2_mul_fp(v.x1, two); v.x2 = fp2_sub(v.t2, v.t0);
+  v.x3 = fp2_mul(rx, rx); v.x4 = fp2_mul_fp(v.x3, three); v.x5 = fp2_neg(v.t4); v.x6 = fp2_sub(v.t0, v.t3);
+  v.x7 = fp2_mul(rx, ry); v.x8 = fp2_mul(v.x6, v.x7); v.x9 = fp2_add(v.t0, v.t3); v.x10 = fp2_mul_fp(v.x9, HALF());
+  v.x11 = fp2_mul(v.x10, v.x10); v.x12 = fp2_mul(v.t2, v.t2); v.x13 = fp2_mul_fp(v.x12, three);
+  v.new_rx = fp2_mul_fp(v.x8, HALF()); v.new_ry = fp2_sub(v.x11, v.x13); v.new_rz = fp2_mul(v.t0, v.t4);
+  return v;
+}
+struct Loop1 { Fp2 new_rx, new_ry, new_rz, t[19]; };
+Loop1 calc_precomp_stuff_loop1(const Fp2& rx, const Fp2& ry, const Fp2& rz, const Fp2& qx, const Fp2& qy) {
+  Loop1 w;
+  Fp2* t = w.t;
+  t[0] = fp2_mul(qy, rz); t[1] = fp2_sub(ry, t[0]); t[2] = fp2_mul(qx, rz); t[3] = fp2_sub(rx, t[2]); t[4] = fp2_mul(t[1], qx);
+  t[5] = fp2_mul(t[3], qy); t[6] = fp2_sub(t[4], t[5]); t[7] = fp2_neg(t[1]); t[8] = fp2_mul(t[3], t[3]); t[9] = fp2_mul(t[8], t[3]);
+  t[10] = fp2_mul(t[8], rx); t[11] = fp2_mul(t[1], t[1]); t[12] = fp2_mul(t[11], rz); t[13] = fp2_mul_fp(t[10], Big(2));
+  t[14] = fp2_sub(t[9], t[13]); t[15] = fp2_add(t[14], t[12]); t[16] = fp2_sub(t[10], t[15]); t[17] = fp2_mul(t[16], t[1]);
+  t[18] = fp2_mul(t[9], ry);
+  w.new_rx = fp2_mul(t[3], t[15]); w.new_ry = fp2_sub(t[17], t[18]); w.new_rz = fp2_mul(rz, t[9]);
+  return w;
+}
+struct Ell { Fp2 c[3]; };
+std::vector<Ell> pairing_precomp_native(const Fp2& x, const Fp2& y, const Fp2& z) {             // native.rs:1358-1437
+  const Fp2 zi = fp2_inv(z), qx = fp2_mul(x, zi), qy = fp2_mul(y, zi);
+  Fp2 rx = qx, ry = qy, rz = {{Big(1), Big()}};
+  std::vector<Ell> ell;
+  for (int i = 62; i >= 0; i--) {
+    const Loop0 v = calc_precomp_stuff_loop0(rx, ry, rz);
+    ell.push_back({{v.x2, v.x4, v.x5}});
+    rx = v.new_rx; ry = v.new_ry; rz = v.new_rz;
+    if ((BLS_X >> i) & 1) {
+      const Loop1 w = calc_precomp_stuff_loop1(rx, ry, rz, qx, qy);
+      ell.push_back({{w.t[6], w.t[7], w.t[3]}});
+      rx = w.new_rx; ry = w.new_ry; rz = w.new_rz;
+    }
+  }
+  return ell;
+}
+Fp12 miller_loop_native(const Fp& px, const Fp& py, const std::vector<Ell>& pre) {            // native.rs:1440-1466
+  Fp12 f = fp12_one();
+  size_t j = 0;
+  for (int i = 62; i >= 0; i--) {
+    f = fp12_multiply_by_014(f, pre[j].c[0], fp2_mul_fp(pre[j].c[1], px), fp2_mul_fp(pre[j].c[2], py));
+    if ((BLS_X >> i) & 1) {
+      j++;
+      f = fp12_multiply_by_014(f, pre[j].c[0], fp2_mul_fp(pre[j].c[1], px), fp2_mul_fp(pre[j].c[2], py));
+    }
+    if (i != 0) f = fp12_mul_native(f, f);
+    j++;
+  }
+  return fp12_conjugate(f);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -508,6 +648,269 @@ void fill_trace_fp12_multiplication(Trace& tr, const Fp12& x, const Fp12& y, siz
   sub_red6_rows(tr, t6, t1, s, e, col + fp12::FP12_MUL_Y_CALC_OFFSET);
 }
 
+
+// ------------------------------------------------------------------ the gadgets of the three larger starks
+void fill_trace_negate_fp2(Trace& tr, const Fp2& x, size_t row, size_t col) { fill_trace_addition_fp2(tr, x, fp2_neg(x), row, col); }   // fp2.rs:232-243
+void negate_rows(Trace& tr, const Fp2& x, size_t s, size_t e, size_t col) {
+  fill_trace_negate_fp2(tr, x, s, col); tr.rep(s, e, col, fp2::FP2_ADDITION_TOTAL);
+}
+void fill_trace_fp2_fp_mul(Trace& tr, const Fp2& x, const Fp& y, size_t s, size_t e, size_t col) {         // fp2.rs:324-343
+  tr.set_rows(s, e, col + fp2::FP2_FP_MUL_SELECTOR_OFFSET, 1);
+  put_fp2_rows(tr, s, e, col + fp2::FP2_FP_X_INPUT_OFFSET, x);
+  put_big_rows(tr, s, e, col + fp2::FP2_FP_Y_INPUT_OFFSET, y, 12);
+  tr.at(e, col + fp2::FP2_FP_MUL_SELECTOR_OFFSET) = 0;
+  fill_multiplication_trace_no_mod_reduction(tr, x.c[0], y, s, e, col + fp2::X0_Y_MULTIPLICATION_OFFSET);
+  Big rem = fill_reduction_trace(tr, mul(x.c[0], y), s, e, col + fp2::X0_Y_REDUCE_OFFSET);
+  fill_range_check_trace(tr, rem, s, col + fp2::X0_Y_RANGECHECK_OFFSET);
+  fill_multiplication_trace_no_mod_reduction(tr, x.c[1], y, s, e, col + fp2::X1_Y_MULTIPLICATION_OFFSET);
+  rem = fill_reduction_trace(tr, mul(x.c[1], y), s, e, col + fp2::X1_Y_REDUCE_OFFSET);
+  fill_range_check_trace(tr, rem, s, col + fp2::X1_Y_RANGECHECK_OFFSET);
+}
+void fill_multiply_by_b_trace(Trace& tr, const Fp2& x, size_t s, size_t e, size_t col) {                   // fp2.rs:374-410
+  tr.set_rows(s, e, col + fp2::MULTIPLY_B_SELECTOR_OFFSET, 1);
+  put_fp2_rows(tr, s, e, col + fp2::MULTIPLY_B_X_OFFSET, x);
+  tr.at(e, col + fp2::MULTIPLY_B_SELECTOR_OFFSET) = 0;
+  const Big four(4);
+  fill_multiplication_trace_no_mod_reduction(tr, x.c[0], four, s, e, col + fp2::MULTIPLY_B_X0_B_MUL_OFFSET);
+  fill_multiplication_trace_no_mod_reduction(tr, x.c[1], four, s, e, col + fp2::MULTIPLY_B_X1_B_MUL_OFFSET);
+  const Big x0y = mul(x.c[0], four), x1y = mul(x.c[1], four);
+  fill_addition_trace(tr, x0y, MODP2(), s + 11, col + fp2::MULTIPLY_B_ADD_MODSQ_OFFSET);
+  fill_subtraction_trace(tr, add(x0y, MODP2()), x1y, s + 11, col + fp2::MULTIPLY_B_SUB_OFFSET);
+  Big rem = fill_reduction_trace(tr, sub(add(x0y, MODP2()), x1y), s, e, col + fp2::MULTIPLY_B_Z0_REDUCE_OFFSET);
+  fill_range_check_trace(tr, rem, s, col + fp2::MULTIPLY_B_Z0_RANGECHECK_OFFSET);
+  fill_addition_trace(tr, x0y, x1y, s + 11, col + fp2::MULTIPLY_B_ADD_OFFSET);
+  rem = fill_reduction_trace(tr, add(x0y, x1y), s, e, col + fp2::MULTIPLY_B_Z1_REDUCE_OFFSET);
+  fill_range_check_trace(tr, rem, s, col + fp2::MULTIPLY_B_Z1_RANGECHECK_OFFSET);
+}
+void fill_trace_fp4_sq(Trace& tr, const Fp2& x, const Fp2& y, size_t s, size_t e, size_t col) {            // fp2.rs:459-502
+  put_fp2_rows(tr, s, e, col + fp2::FP4_SQ_INPUT_X_OFFSET, x);
+  put_fp2_rows(tr, s, e, col + fp2::FP4_SQ_INPUT_Y_OFFSET, y);
+  tr.set_rows(s, e, col + fp2::FP4_SQ_SELECTOR_OFFSET, 1);
+  tr.at(e, col + fp2::FP4_SQ_SELECTOR_OFFSET) = 0;
+  const Fp2 t0 = fp2_mul(x, x); generate_trace_fp2_mul(tr, x, x, s, e, col + fp2::FP4_SQ_T0_CALC_OFFSET);
+  const Fp2 t1 = fp2_mul(y, y); generate_trace_fp2_mul(tr, y, y, s, e, col + fp2::FP4_SQ_T1_CALC_OFFSET);
+  const Fp2 t2 = fp2_mul_by_nonresidue(t1); nonres_rows(tr, t1, s, e, col + fp2::FP4_SQ_T2_CALC_OFFSET);
+  add_red_rows(tr, t2, t0, s, e, col + fp2::FP4_SQ_X_CALC_OFFSET);
+  const Fp2 t3 = fp2_add(x, y); add_red_rows(tr, x, y, s, e, col + fp2::FP4_SQ_T3_CALC_OFFSET);
+  const Fp2 t4 = fp2_mul(t3, t3); generate_trace_fp2_mul(tr, t3, t3, s, e, col + fp2::FP4_SQ_T4_CALC_OFFSET);
+  const Fp2 t5 = fp2_sub(t4, t0); sub_red_rows(tr, t4, t0, s, e, col + fp2::FP4_SQ_T5_CALC_OFFSET);
+  sub_red_rows(tr, t5, t1, s, e, col + fp2::FP4_SQ_Y_CALC_OFFSET);
+}
+void fill_trace_fp2_forbenius_map(Trace& tr, const Fp2& x, unsigned pw, size_t s, size_t e, size_t col) {  // fp2.rs:505-531
+  const unsigned div = pw / 2, rem = pw % 2;
+  put_fp2_rows(tr, s, e, col + fp2::FP2_FORBENIUS_MAP_INPUT_OFFSET, x);
+  tr.set_rows(s, e, col + fp2::FP2_FORBENIUS_MAP_SELECTOR_OFFSET, 1);
+  tr.set_rows(s, e, col + fp2::FP2_FORBENIUS_MAP_POW_OFFSET, pw);
+  tr.set_rows(s, e, col + fp2::FP2_FORBENIUS_MAP_DIV_OFFSET, div);
+  tr.set_rows(s, e, col + fp2::FP2_FORBENIUS_MAP_REM_OFFSET, rem);
+  tr.at(e, col + fp2::FP2_FORBENIUS_MAP_SELECTOR_OFFSET) = 0;
+  const Fp k = frob_fp(FP2_FROB, rem);
+  fill_multiplication_trace_no_mod_reduction(tr, x.c[1], k, s, e, col + fp2::FP2_FORBENIUS_MAP_T0_CALC_OFFSET);
+  tr.at(s + 11, col + fp2::FP2_FORBENIUS_MAP_MUL_RES_ROW) = 1;
+  const size_t base = col + fp2::FP2_FORBENIUS_MAP_T0_CALC_OFFSET + fp::FP_MULTIPLICATION_TOTAL_COLUMNS;
+  const Big res = fill_reduction_trace(tr, mul(x.c[1], k), s, e, base);
+  fill_range_check_trace(tr, res, s, base + fp::REDUCTION_TOTAL);
+  tr.rep(s, e, base + fp::REDUCTION_TOTAL, fp::RANGE_CHECK_TOTAL);
+}
+void fill_trace_negate_fp6(Trace& tr, const Fp6& x, size_t row, size_t col) { fill_trace_addition_fp6(tr, x, fp6_neg(x), row, col); }   // fp6.rs:186-196
+void negate6_rows(Trace& tr, const Fp6& x, size_t s, size_t e, size_t col) {
+  fill_trace_negate_fp6(tr, x, s, col); tr.rep(s, e, col, fp6::FP6_ADDITION_TOTAL);
+}
+void fill_trace_multiply_by_1(Trace& tr, const Fp6& x, const Fp2& b1, size_t s, size_t e, size_t col) {    // fp6.rs:306-333
+  put_fp6_rows(tr, s, e, col + fp6::MULTIPLY_BY_1_INPUT_OFFSET, x);
+  put_fp2_rows(tr, s, e, col + fp6::MULTIPLY_BY_1_B1_OFFSET, b1);
+  tr.set_rows(s, e, col + fp6::MULTIPLY_BY_1_SELECTOR_OFFSET, 1);
+  tr.at(e, col + fp6::MULTIPLY_BY_1_SELECTOR_OFFSET) = 0;
+  const Fp2 c0 = part(x, 0), c1 = part(x, 1), c2 = part(x, 2);
+  const Fp2 t0 = fp2_mul(c2, b1); generate_trace_fp2_mul(tr, c2, b1, s, e, col + fp6::MULTIPLY_BY_1_T0_CALC_OFFSET);
+  nonres_rows(tr, t0, s, e, col + fp6::MULTIPLY_BY_1_X_CALC_OFFSET);
+  generate_trace_fp2_mul(tr, c0, b1, s, e, col + fp6::MULTIPLY_BY_1_Y_CALC_OFFSET);
+  generate_trace_fp2_mul(tr, c1, b1, s, e, col + fp6::MULTIPLY_BY_1_Z_CALC_OFFSET);
+}
+void fill_trace_multiply_by_01(Trace& tr, const Fp6& x, const Fp2& b0, const Fp2& b1, size_t s, size_t e, size_t col) {   // fp6.rs:336-394
+  put_fp6_rows(tr, s, e, col + fp6::MULTIPLY_BY_01_INPUT_OFFSET, x);
+  put_fp2_rows(tr, s, e, col + fp6::MULTIPLY_BY_01_B0_OFFSET, b0);
+  put_fp2_rows(tr, s, e, col + fp6::MULTIPLY_BY_01_B1_OFFSET, b1);
+  tr.set_rows(s, e, col + fp6::MULTIPLY_BY_01_SELECTOR_OFFSET, 1);
+  tr.at(e, col + fp6::MULTIPLY_BY_01_SELECTOR_OFFSET) = 0;
+  const Fp2 c0 = part(x, 0), c1 = part(x, 1), c2 = part(x, 2);
+  const Fp2 t0 = fp2_mul(c0, b0); generate_trace_fp2_mul(tr, c0, b0, s, e, col + fp6::MULTIPLY_BY_01_T0_CALC_OFFSET);
+  const Fp2 t1 = fp2_mul(c1, b1); generate_trace_fp2_mul(tr, c1, b1, s, e, col + fp6::MULTIPLY_BY_01_T1_CALC_OFFSET);
+  const Fp2 t2 = fp2_mul(c2, b1); generate_trace_fp2_mul(tr, c2, b1, s, e, col + fp6::MULTIPLY_BY_01_T2_CALC_OFFSET);
+  const Fp2 t3 = fp2_mul_by_nonresidue(t2); nonres_rows(tr, t2, s, e, col + fp6::MULTIPLY_BY_01_T3_CALC_OFFSET);
+  add_red_rows(tr, t3, t0, s, e, col + fp6::MULTIPLY_BY_01_X_CALC_OFFSET);
+  const Fp2 t4 = fp2_add(b0, b1); add_red_rows(tr, b0, b1, s, e, col + fp6::MULTIPLY_BY_01_T4_CALC_OFFSET);
+  const Fp2 t5 = fp2_add(c0, c1); add_red_rows(tr, c0, c1, s, e, col + fp6::MULTIPLY_BY_01_T5_CALC_OFFSET);
+  const Fp2 t6 = fp2_mul(t4, t5); generate_trace_fp2_mul(tr, t4, t5, s, e, col + fp6::MULTIPLY_BY_01_T6_CALC_OFFSET);
+  const Fp2 t7 = fp2_sub(t6, t0); sub_red_rows(tr, t6, t0, s, e, col + fp6::MULTIPLY_BY_01_T7_CALC_OFFSET);
+  sub_red_rows(tr, t7, t1, s, e, col + fp6::MULTIPLY_BY_01_Y_CALC_OFFSET);
+  const Fp2 t8 = fp2_mul(c2, b0); generate_trace_fp2_mul(tr, c2, b0, s, e, col + fp6::MULTIPLY_BY_01_T8_CALC_OFFSET);
+  add_red_rows(tr, t8, t1, s, e, col + fp6::MULTIPLY_BY_01_Z_CALC_OFFSET);
+}
+void fill_trace_fp6_forbenius_map(Trace& tr, const Fp6& x, unsigned pw, size_t s, size_t e, size_t col) {  // fp6.rs:397-431
+  const unsigned div = pw / 6, rem = pw % 6;
+  put_fp6_rows(tr, s, e, col + fp6::FP6_FORBENIUS_MAP_INPUT_OFFSET, x);
+  tr.set_rows(s, e, col + fp6::FP6_FORBENIUS_MAP_SELECTOR_OFFSET, 1);
+  tr.set_rows(s, e, col + fp6::FP6_FORBENIUS_MAP_POW_OFFSET, pw);
+  tr.set_rows(s, e, col + fp6::FP6_FORBENIUS_MAP_DIV_OFFSET, div);
+  tr.set_rows(s, e, col + fp6::FP6_FORBENIUS_MAP_REM_OFFSET, rem);
+  tr.set_rows(s, e, col + fp6::FP6_FORBENIUS_MAP_BIT0_OFFSET, rem & 1);
+  tr.set_rows(s, e, col + fp6::FP6_FORBENIUS_MAP_BIT1_OFFSET, (rem >> 1) & 1);
+  tr.set_rows(s, e, col + fp6::FP6_FORBENIUS_MAP_BIT2_OFFSET, rem >> 2);
+  tr.at(e, col + fp6::FP6_FORBENIUS_MAP_SELECTOR_OFFSET) = 0;
+  const Fp2 c0 = part(x, 0), c1 = part(x, 1), c2 = part(x, 2);
+  fill_trace_fp2_forbenius_map(tr, c0, pw, s, e, col + fp6::FP6_FORBENIUS_MAP_X_CALC_OFFSET);
+  const Fp2 t0 = fp2_frobenius(c1, pw);
+  fill_trace_fp2_forbenius_map(tr, c1, pw, s, e, col + fp6::FP6_FORBENIUS_MAP_T0_CALC_OFFSET);
+  generate_trace_fp2_mul(tr, t0, frob_fp2(FP6_FROB_1, rem), s, e, col + fp6::FP6_FORBENIUS_MAP_Y_CALC_OFFSET);
+  const Fp2 t1 = fp2_frobenius(c2, pw);
+  fill_trace_fp2_forbenius_map(tr, c2, pw, s, e, col + fp6::FP6_FORBENIUS_MAP_T1_CALC_OFFSET);
+  generate_trace_fp2_mul(tr, t1, frob_fp2(FP6_FROB_2, rem), s, e, col + fp6::FP6_FORBENIUS_MAP_Z_CALC_OFFSET);
+}
+void put_fp12_rows(Trace& tr, size_t r0, size_t r1, size_t col, const Fp12& x) {
+  for (int i = 0; i < 12; i++) put_big_rows(tr, r0, r1, col + 12 * i, x.c[i], 12);
+}
+void fill_trace_multiply_by_014(Trace& tr, const Fp12& x, const Fp2& o0, const Fp2& o1, const Fp2& o4, size_t s, size_t e, size_t col) {   // fp12.rs:132-183
+  put_fp12_rows(tr, s, e, col + fp12::MULTIPLY_BY_014_INPUT_OFFSET, x);
+  put_fp2_rows(tr, s, e, col + fp12::MULTIPLY_BY_014_O0_OFFSET, o0);
+  put_fp2_rows(tr, s, e, col + fp12::MULTIPLY_BY_014_O1_OFFSET, o1);
+  put_fp2_rows(tr, s, e, col + fp12::MULTIPLY_BY_014_O4_OFFSET, o4);
+  tr.set_rows(s, e, col + fp12::MULTIPLY_BY_014_SELECTOR_OFFSET, 1);
+  tr.at(e, col + fp12::MULTIPLY_BY_014_SELECTOR_OFFSET) = 0;
+  const Fp6 c0 = half(x, 0), c1 = half(x, 1);
+  const Fp6 t0 = fp6_multiply_by_01(c0, o0, o1); fill_trace_multiply_by_01(tr, c0, o0, o1, s, e, col + fp12::MULTIPLY_BY_014_T0_CALC_OFFSET);
+  const Fp6 t1 = fp6_multiply_by_1(c1, o4); fill_trace_multiply_by_1(tr, c1, o4, s, e, col + fp12::MULTIPLY_BY_014_T1_CALC_OFFSET);
+  const Fp6 t2 = fp6_mul_by_nonresidue(t1); nonres6_rows(tr, t1, s, e, col + fp12::MULTIPLY_BY_014_T2_CALC_OFFSET);
+  add_red6_rows(tr, t2, t0, s, e, col + fp12::MULTIPLY_BY_014_X_CALC_OFFSET);
+  const Fp6 t3 = fp6_add(c0, c1); add_red6_rows(tr, c0, c1, s, e, col + fp12::MULTIPLY_BY_014_T3_CALC_OFFSET);
+  const Fp2 t4 = fp2_add(o1, o4); add_red_rows(tr, o1, o4, s, e, col + fp12::MULTIPLY_BY_014_T4_CALC_OFFSET);
+  const Fp6 t5 = fp6_multiply_by_01(t3, o0, t4); fill_trace_multiply_by_01(tr, t3, o0, t4, s, e, col + fp12::MULTIPLY_BY_014_T5_CALC_OFFSET);
+  const Fp6 t6 = fp6_sub(t5, t0); sub_red6_rows(tr, t5, t0, s, e, col + fp12::MULTIPLY_BY_014_T6_CALC_OFFSET);
+  sub_red6_rows(tr, t6, t1, s, e, col + fp12::MULTIPLY_BY_014_Y_CALC_OFFSET);
+}
+void fill_trace_cyclotomic_sq(Trace& tr, const Fp12& x, size_t s, size_t e, size_t col) {                  // fp12.rs:234-332
+  put_fp12_rows(tr, s, e, col + fp12::CYCLOTOMIC_SQ_INPUT_OFFSET, x);
+  tr.set_rows(s, e, col + fp12::CYCLOTOMIC_SQ_SELECTOR_OFFSET, 1);
+  tr.at(e, col + fp12::CYCLOTOMIC_SQ_SELECTOR_OFFSET) = 0;
+  const Fp2 c0c0 = part12(x, 0), c0c1 = part12(x, 1), c0c2 = part12(x, 2), c1c0 = part12(x, 3), c1c1 = part12(x, 4), c1c2 = part12(x, 5);
+  Fp2 t00, t01, t10, t11, t20, t21;
+  fp4_square(c0c0, c1c1, t00, t01); fill_trace_fp4_sq(tr, c0c0, c1c1, s, e, col + fp12::CYCLOTOMIC_SQ_T0_CALC_OFFSET);
+  fp4_square(c1c0, c0c2, t10, t11); fill_trace_fp4_sq(tr, c1c0, c0c2, s, e, col + fp12::CYCLOTOMIC_SQ_T1_CALC_OFFSET);
+  fp4_square(c0c1, c1c2, t20, t21); fill_trace_fp4_sq(tr, c0c1, c1c2, s, e, col + fp12::CYCLOTOMIC_SQ_T2_CALC_OFFSET);
+  const Fp2 t3 = fp2_mul_by_nonresidue(t21); nonres_rows(tr, t21, s, e, col + fp12::CYCLOTOMIC_SQ_T3_CALC_OFFSET);
+  const Fp two = Big(2);
+  auto branch = [&](bool subtract, const Fp2& a, const Fp2& b, u32 o_t, u32 o_2, u32 o_c) {      // t = a -+ b ; t' = 2 t ; c = t' + a
+    Fp2 t;
+    if (subtract) { t = fp2_sub(a, b); sub_red_rows(tr, a, b, s, e, col + o_t); }
+    else { t = fp2_add(a, b); add_red_rows(tr, a, b, s, e, col + o_t); }
+    const Fp2 t_2 = fp2_mul_fp(t, two);
+    fill_trace_fp2_fp_mul(tr, t, two, s, e, col + o_2);
+    add_red_rows(tr, t_2, a, s, e, col + o_c);
+  };
+  branch(true, t00, c0c0, fp12::CYCLOTOMIC_SQ_T4_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_T5_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_C0_CALC_OFFSET);
+  branch(true, t10, c0c1, fp12::CYCLOTOMIC_SQ_T6_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_T7_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_C1_CALC_OFFSET);
+  branch(true, t20, c0c2, fp12::CYCLOTOMIC_SQ_T8_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_T9_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_C2_CALC_OFFSET);
+  branch(false, t3, c1c0, fp12::CYCLOTOMIC_SQ_T10_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_T11_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_C3_CALC_OFFSET);
+  branch(false, t01, c1c1, fp12::CYCLOTOMIC_SQ_T12_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_T13_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_C4_CALC_OFFSET);
+  branch(false, t11, c1c2, fp12::CYCLOTOMIC_SQ_T14_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_T15_CALC_OFFSET, fp12::CYCLOTOMIC_SQ_C5_CALC_OFFSET);
+}
+Fp12 fill_trace_cyclotomic_exp(Trace& tr, const Fp12& x, size_t s, size_t e, size_t col) {                 // fp12.rs:335-375
+  if (e + 1 - s != 70 * 12 + 1) throw std::logic_error("witness: cyclotomic_exp spans 841 rows");
+  put_fp12_rows(tr, s, e, col + fp12::INPUT_OFFSET, x);
+  tr.set_rows(s, e, col + fp12::CYCLOTOMIC_EXP_SELECTOR_OFFSET, 1);
+  tr.at(e, col + fp12::CYCLOTOMIC_EXP_SELECTOR_OFFSET) = 0;
+  tr.at(s, col + fp12::CYCLOTOMIC_EXP_START_ROW) = 1;
+  Fp12 z = fp12_one();
+  int i = 63;
+  bool bitone = false;
+  for (int j = 0; j < 70; j++) {
+    const size_t s_row = s + 12 * j, e_row = s_row + 11;
+    if (bitone) tr.set_rows(s_row, e_row, col + fp12::BIT1_SELECTOR_OFFSET, 1);
+    put_fp12_rows(tr, s_row, e_row, col + fp12::Z_OFFSET, z);
+    tr.at(s_row, col + fp12::FIRST_ROW_SELECTOR_OFFSET) = 1;
+    if (bitone) {
+      fill_trace_fp12_multiplication(tr, z, x, s_row, e_row, col + fp12::Z_MUL_INPUT_OFFSET);
+      z = fp12_mul_native(z, x);
+    } else {
+      fill_trace_cyclotomic_sq(tr, z, s_row, e_row, col + fp12::Z_CYCLOTOMIC_SQ_OFFSET);
+      z = fp12_cyclotomic_square(z);
+    }
+    if (((BLS_X >> i) & 1) && !bitone) bitone = true;
+    else if (j < 69) { i--; bitone = false; }
+  }
+  tr.at(s + 70 * 12, col + fp12::RES_ROW_SELECTOR_OFFSET) = 1;
+  put_fp12_rows(tr, s + 70 * 12, s + 70 * 12, col + fp12::Z_OFFSET, z);
+  return z;
+}
+void fill_trace_fp12_forbenius_map(Trace& tr, const Fp12& x, unsigned pw, size_t s, size_t e, size_t col) {   // fp12.rs:378-411
+  const unsigned div = pw / 12, rem = pw % 12;
+  put_fp12_rows(tr, s, e, col + fp12::FP12_FORBENIUS_MAP_INPUT_OFFSET, x);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_SELECTOR_OFFSET, 1);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_POW_OFFSET, pw);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_DIV_OFFSET, div);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_REM_OFFSET, rem);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_BIT0_OFFSET, rem & 1);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_BIT1_OFFSET, (rem >> 1) & 1);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_BIT2_OFFSET, (rem >> 2) & 1);
+  tr.set_rows(s, e, col + fp12::FP12_FORBENIUS_MAP_BIT3_OFFSET, rem >> 3);
+  tr.at(e, col + fp12::FP12_FORBENIUS_MAP_SELECTOR_OFFSET) = 0;
+  const Fp6 r0 = half(x, 0), r1 = half(x, 1);
+  fill_trace_fp6_forbenius_map(tr, r0, pw, s, e, col + fp12::FP12_FORBENIUS_MAP_R0_CALC_OFFSET);
+  const Fp6 c = fp6_frobenius(r1, pw);
+  fill_trace_fp6_forbenius_map(tr, r1, pw, s, e, col + fp12::FP12_FORBENIUS_MAP_C0C1C2_CALC_OFFSET);
+  const Fp2 k = frob_fp2(FP12_FROB, rem);
+  generate_trace_fp2_mul(tr, part(c, 0), k, s, e, col + fp12::FP12_FORBENIUS_MAP_C0_CALC_OFFSET);
+  generate_trace_fp2_mul(tr, part(c, 1), k, s, e, col + fp12::FP12_FORBENIUS_MAP_C1_CALC_OFFSET);
+  generate_trace_fp2_mul(tr, part(c, 2), k, s, e, col + fp12::FP12_FORBENIUS_MAP_C2_CALC_OFFSET);
+}
+Fp12 fill_trace_fp12_conjugate(Trace& tr, const Fp12& x, size_t row, size_t col) {                         // fp12.rs:414-426
+  put_fp12_rows(tr, row, row, col + fp12::FP12_CONJUGATE_INPUT_OFFSET, x);
+  const Fp12 conj = fp12_conjugate(x);
+  put_fp12_rows(tr, row, row, col + fp12::FP12_CONJUGATE_OUTPUT_OFFSET, conj);
+  fill_trace_addition_fp6(tr, half(x, 1), half(conj, 1), row, col + fp12::FP12_CONJUGATE_ADDITIION_OFFSET);
+  return conj;
+}
+// miller_loop.rs:87-146
+void fill_trace_miller_loop(Trace& tr, const Fp& x, const Fp& y, const std::vector<Ell>& ell, size_t s, size_t e, size_t col) {
+  namespace M = woff::miller_loop;
+  put_big_rows(tr, s, e, col + M::PX_OFFSET, x, 12);
+  put_big_rows(tr, s, e, col + M::PY_OFFSET, y, 12);
+  Fp12 f12 = fp12_one();
+  int i = 62;
+  bool bitone = false;
+  const size_t n_ops = std::min((e + 1 - s) / 12, ell.size());
+  for (size_t j = 0; j < n_ops; j++) {
+    const size_t s_row = s + 12 * j, e_row = s_row + 11;
+    if (j == 0) tr.set_rows(s_row, e_row, col + M::FIRST_BIT_SELECTOR_OFFSET, 1);
+    if (i == 0) tr.set_rows(s_row, e_row, col + M::LAST_BIT_SELECTOR_OFFSET, 1);
+    if (bitone) tr.set_rows(s_row, e_row, col + M::BIT1_SELECTOR_OFFSET, 1);
+    tr.set_rows(s_row, e_row, col + M::ELL_COEFFS_INDEX_OFFEST + j, 1);
+    const Ell& c = ell[j];
+    for (int k = 0; k < 3; k++) put_fp2_rows(tr, s_row, e_row, col + M::ELL_COEFFS_OFFSET + 24 * k, c.c[k]);
+    put_fp12_rows(tr, s_row, e_row, col + M::F12_OFFSET, f12);
+    if (j != 0) tr.at(s_row, col + M::FIRST_ROW_SELECTOR_OFFSET) = 1;
+    fill_trace_fp2_fp_mul(tr, c.c[1], x, s_row, e_row, col + M::O1_CALC_OFFSET);
+    const Fp2 o1 = fp2_mul_fp(c.c[1], x);
+    fill_trace_fp2_fp_mul(tr, c.c[2], y, s_row, e_row, col + M::O4_CALC_OFFSET);
+    const Fp2 o4 = fp2_mul_fp(c.c[2], y);
+    fill_trace_multiply_by_014(tr, f12, c.c[0], o1, o4, s_row, e_row, col + M::F12_MUL_BY_014_OFFSET);
+    f12 = fp12_multiply_by_014(f12, c.c[0], o1, o4);
+    fill_trace_fp12_multiplication(tr, f12, f12, s_row, e_row, col + M::F12_SQ_CALC_OFFSET);
+    const Fp12 f12_sq = fp12_mul_native(f12, f12);
+    if (((BLS_X >> i) & 1) && !bitone) bitone = true;
+    else if (j + 1 < ell.size()) { f12 = f12_sq; i--; bitone = false; }
+  }
+  f12 = fp12_conjugate(f12);
+  put_fp12_rows(tr, s, e, col + M::MILLER_LOOP_RES_OFFSET, f12);
+  negate6_rows(tr, half(f12, 1), s, e, col + M::RES_CONJUGATE_OFFSET);
+}
+Fp2 fp2_from_limbs(const u32* l) {
+  Fp2 r = {{Big::from_limbs(l, 12), Big::from_limbs(l + 12, 12)}};
+  for (int i = 0; i < 2; i++) if (cmp(r.c[i], MODP()) >= 0) throw std::invalid_argument("witness: Fp coefficient is not reduced modulo p");
+  return r;
+}
+void pis_fp2(uint64_t* out, const Fp2& v) { for (int k = 0; k < 12; k++) { out[k] = v.c[0].w[k]; out[12 + k] = v.c[1].w[k]; } }
+
 Fp12 fp12_from_limbs(const u32* l) {
   Fp12 r;
   for (int i = 0; i < 12; i++) {
@@ -637,6 +1040,219 @@ int sb_witness_ecc_agg(const uint32_t* points, const uint8_t* bits, uint32_t num
       public_inputs_out[E::RES + 12 + k] = res.y.w[k];
       if (result_out) { result_out[k] = res.x.w[k]; result_out[12 + k] = res.y.w[k]; }
     }
+    return SB_OK;
+  } catch (const std::exception& e) {
+    g_witness_error = e.what();
+    return SB_EINVAL;
+  }
+}
+
+
+// PairingPrecompStark::generate_trace (calc_pairing_precomp.rs:150-366) + the public inputs of calc_pairing_precomp_main
+// (aggregate_proof.rs:24-69).  q: the projective G2 point x ++ y ++ z, Fp2 each as 2 x 12 little-endian u32 limbs ([3][24]).
+// trace_out: [num_rows][29376] uint32_t row-major; public_inputs_out: 4968 values (x, y, z, 68 x 3 line coefficients).
+int sb_witness_pairing_precomp(const uint32_t* q, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out) {
+  if (!q || !trace_out || !public_inputs_out) return SB_EINVAL;
+  try {
+    namespace A = woff::calc_pairing_precomp;
+    if (num_rows < 16 || (num_rows & (num_rows - 1))) throw std::invalid_argument("witness: num_rows must be a power of two >= 16");
+    const Fp2 x = fp2_from_limbs(q), y = fp2_from_limbs(q + 24), z = fp2_from_limbs(q + 48);
+    Trace tr = {trace_out, num_rows, A::TOTAL_COLUMNS};
+    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    const size_t last = num_rows - 1;
+    const Fp2 z_inv = fp2_inv(z);
+    generate_trace_fp2_mul(tr, z, z_inv, 0, last, A::Z_MULT_Z_INV_OFFSET);
+    generate_trace_fp2_mul(tr, x, z_inv, 0, last, A::X_MULT_Z_INV_OFFSET);
+    generate_trace_fp2_mul(tr, y, z_inv, 0, last, A::Y_MULT_Z_INV_OFFSET);
+    const Fp2 qx = fp2_mul(x, z_inv), qy = fp2_mul(y, z_inv), qz = {{Big(1), Big()}};          // calc_qs (native.rs:277-286)
+    put_fp2_rows(tr, 0, last, A::QX_OFFSET, qx);
+    put_fp2_rows(tr, 0, last, A::QY_OFFSET, qy);
+    put_fp2_rows(tr, 0, last, A::QZ_OFFSET, qz);
+    Fp2 rx = qx, ry = qy, rz = qz;
+    int bit_pos = 62;
+    bool bit1 = false;
+    const size_t num_coeffs = 68;
+    const Fp three = Big(3), two = Big(2);
+    for (size_t n = 0; n < num_rows / 12 + 1; n++) {
+      const size_t s = 12 * n, end_row = 12 * (n + 1), be = std::min(end_row, (size_t)num_rows) - 1;
+      if (n == 0) tr.set_rows(s, be, A::FIRST_LOOP_SELECTOR_OFFSET, 1);
+      put_fp2_rows(tr, s, be, A::RX_OFFSET, rx);
+      put_fp2_rows(tr, s, be, A::RY_OFFSET, ry);
+      put_fp2_rows(tr, s, be, A::RZ_OFFSET, rz);
+      if (bit1) tr.set_rows(s, be, A::BIT1_SELECTOR_OFFSET, 1);
+      if (n < num_coeffs) tr.set_rows(s, be, A::ELL_COEFFS_IDX_OFFSET + n, 1);
+      tr.at(s, A::FIRST_ROW_SELECTOR_OFFSET) = 1;
+      if (end_row > num_rows) break;
+      const size_t e = end_row - 1;
+      if (!bit1) {
+        const Loop0 v = calc_precomp_stuff_loop0(rx, ry, rz);
+        generate_trace_fp2_mul(tr, ry, ry, s, e, A::T0_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, rz, rz, s, e, A::T1_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, v.t1, three, s, e, A::X0_CALC_OFFSET);
+        fill_multiply_by_b_trace(tr, v.x0, s, e, A::T2_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, v.t2, three, s, e, A::T3_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, ry, rz, s, e, A::X1_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, v.x1, two, s, e, A::T4_CALC_OFFSET);
+        sub_red_rows(tr, v.t2, v.t0, s, e, A::X2_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, rx, rx, s, e, A::X3_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, v.x3, three, s, e, A::X4_CALC_OFFSET);
+        negate_rows(tr, v.t4, s, e, A::X5_CALC_OFFSET);
+        sub_red_rows(tr, v.t0, v.t3, s, e, A::X6_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, rx, ry, s, e, A::X7_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, v.x6, v.x7, s, e, A::X8_CALC_OFFSET);
+        add_red_rows(tr, v.t0, v.t3, s, e, A::X9_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, v.x9, HALF(), s, e, A::X10_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, v.x10, v.x10, s, e, A::X11_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, v.t2, v.t2, s, e, A::X12_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, v.x12, three, s, e, A::X13_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, v.x8, HALF(), s, e, A::NEW_RX_OFFSET);
+        sub_red_rows(tr, v.x11, v.x13, s, e, A::NEW_RY_OFFSET);
+        generate_trace_fp2_mul(tr, v.t0, v.t4, s, e, A::NEW_RZ_OFFSET);
+        rx = v.new_rx; ry = v.new_ry; rz = v.new_rz;
+        bit1 = (BLS_X >> bit_pos) & 1;
+        if (!bit1) bit_pos = std::max(bit_pos - 1, 0);
+      } else {
+        const Loop1 w = calc_precomp_stuff_loop1(rx, ry, rz, qx, qy);
+        const Fp2* t = w.t;
+        generate_trace_fp2_mul(tr, qy, rz, s, e, A::BIT1_T0_CALC_OFFSET);
+        sub_red_rows(tr, ry, t[0], s, e, A::BIT1_T1_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, qx, rz, s, e, A::BIT1_T2_CALC_OFFSET);
+        sub_red_rows(tr, rx, t[2], s, e, A::BIT1_T3_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[1], qx, s, e, A::BIT1_T4_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[3], qy, s, e, A::BIT1_T5_CALC_OFFSET);
+        sub_red_rows(tr, t[4], t[5], s, e, A::BIT1_T6_CALC_OFFSET);
+        negate_rows(tr, t[1], s, e, A::BIT1_T7_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[3], t[3], s, e, A::BIT1_T8_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[8], t[3], s, e, A::BIT1_T9_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[8], rx, s, e, A::BIT1_T10_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[1], t[1], s, e, A::BIT1_T11_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[11], rz, s, e, A::BIT1_T12_CALC_OFFSET);
+        fill_trace_fp2_fp_mul(tr, t[10], two, s, e, A::BIT1_T13_CALC_OFFSET);
+        sub_red_rows(tr, t[9], t[13], s, e, A::BIT1_T14_CALC_OFFSET);
+        add_red_rows(tr, t[14], t[12], s, e, A::BIT1_T15_CALC_OFFSET);
+        sub_red_rows(tr, t[10], t[15], s, e, A::BIT1_T16_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[16], t[1], s, e, A::BIT1_T17_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[9], ry, s, e, A::BIT1_T18_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, t[3], t[15], s, e, A::BIT1_RX_CALC_OFFSET);
+        sub_red_rows(tr, t[17], t[18], s, e, A::BIT1_RY_CALC_OFFSET);
+        generate_trace_fp2_mul(tr, rz, t[9], s, e, A::BIT1_RZ_CALC_OFFSET);
+        rx = w.new_rx; ry = w.new_ry; rz = w.new_rz;
+        bit1 = false;
+        bit_pos = std::max(bit_pos - 1, 0);
+      }
+    }
+    pis_fp2(public_inputs_out, x); pis_fp2(public_inputs_out + 24, y); pis_fp2(public_inputs_out + 48, z);
+    const std::vector<Ell> ell = pairing_precomp_native(x, y, z);
+    if (72 + 72 * ell.size() != A::PUBLIC_INPUTS) throw std::logic_error("witness: pairing precomputation, coefficient count");
+    for (size_t i = 0; i < ell.size(); i++)
+      for (int k = 0; k < 3; k++) pis_fp2(public_inputs_out + A::ELL_COEFFS_PUBLIC_INPUTS_OFFSET + 72 * i + 24 * k, ell[i].c[k]);
+    return SB_OK;
+  } catch (const std::exception& e) {
+    g_witness_error = e.what();
+    return SB_EINVAL;
+  }
+}
+
+// MillerLoopStark::generate_trace (miller_loop.rs:157-160, fill_trace_miller_loop :87-146) + the public inputs of
+// miller_loop_main (aggregate_proof.rs:71-121).  p: the G1 point x ++ y ([24] limbs); q: the projective G2 point ([3][24]).
+// trace_out: [num_rows][97330] uint32_t row-major; public_inputs_out: 5064 values (x, y, line coefficients, result).
+int sb_witness_miller_loop(const uint32_t* p, const uint32_t* q, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out) {
+  if (!p || !q || !trace_out || !public_inputs_out) return SB_EINVAL;
+  try {
+    namespace M = woff::miller_loop;
+    if (num_rows < 16 || (num_rows & (num_rows - 1))) throw std::invalid_argument("witness: num_rows must be a power of two >= 16");
+    const Fp x = Big::from_limbs(p, 12), y = Big::from_limbs(p + 12, 12);
+    if (cmp(x, MODP()) >= 0 || cmp(y, MODP()) >= 0) throw std::invalid_argument("witness: Fp coefficient is not reduced modulo p");
+    const Fp2 qx = fp2_from_limbs(q), qy = fp2_from_limbs(q + 24), qz = fp2_from_limbs(q + 48);
+    const std::vector<Ell> ell = pairing_precomp_native(qx, qy, qz);
+    const Fp12 res = miller_loop_native(x, y, ell);
+    Trace tr = {trace_out, num_rows, M::TOTAL_COLUMNS};
+    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    fill_trace_miller_loop(tr, x, y, ell, 0, num_rows - 1, 0);
+    if (24 + 72 * ell.size() + 144 != M::PUBLIC_INPUTS) throw std::logic_error("witness: miller loop, coefficient count");
+    for (int k = 0; k < 12; k++) { public_inputs_out[M::PIS_PX_OFFSET + k] = x.w[k]; public_inputs_out[M::PIS_PY_OFFSET + k] = y.w[k]; }
+    for (size_t i = 0; i < ell.size(); i++)
+      for (int k = 0; k < 3; k++) pis_fp2(public_inputs_out + M::PIS_ELL_COEFFS_OFFSET + 72 * i + 24 * k, ell[i].c[k]);
+    for (int i = 0; i < 12; i++)
+      for (int k = 0; k < 12; k++) public_inputs_out[M::PIS_RES_OFFSET + 12 * i + k] = res.c[i].w[k];
+    return SB_OK;
+  } catch (const std::exception& e) {
+    g_witness_error = e.what();
+    return SB_EINVAL;
+  }
+}
+
+// FinalExponentiateStark::generate_trace (final_exponentiate.rs:137-281) + the public inputs of final_exponentiate_main
+// (aggregate_proof.rs:153-184).  x: the Fp12 input ([12][12] limbs).  trace_out: [8192][73527] uint32_t row-major (2.4 GB);
+// public_inputs_out: 288 values (x, x^((p^12 - 1) / r)).
+int sb_witness_final_exp(const uint32_t* x, uint32_t num_rows, uint32_t* trace_out, uint64_t* public_inputs_out) {
+  if (!x || !trace_out || !public_inputs_out) return SB_EINVAL;
+  try {
+    namespace E = woff::final_exponentiate;
+    if (num_rows != 8192) throw std::invalid_argument("witness: FinalExponentiateStark has 8192 rows (one row selector column per row)");
+    const Fp12 X = fp12_from_limbs(x);
+    Trace tr = {trace_out, num_rows, E::TOTAL_COLUMNS};
+    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    const size_t last = num_rows - 1, OP = E::FINAL_EXP_OP_OFFSET;
+    for (size_t r = 0; r < num_rows; r++) tr.at(r, E::FINAL_EXP_ROW_SELECTORS + r) = 1;
+    put_fp12_rows(tr, 0, last, E::FINAL_EXP_INPUT_OFFSET, X);
+    const u32 ROW[33] = {E::T0_ROW, E::T1_ROW, E::T2_ROW, E::T3_ROW, E::T4_ROW, E::T5_ROW, E::T6_ROW, E::T7_ROW, E::T8_ROW, E::T9_ROW, E::T10_ROW,
+                         E::T11_ROW, E::T12_ROW, E::T13_ROW, E::T14_ROW, E::T15_ROW, E::T16_ROW, E::T17_ROW, E::T18_ROW, E::T19_ROW, E::T20_ROW,
+                         E::T21_ROW, E::T22_ROW, E::T23_ROW, E::T24_ROW, E::T25_ROW, E::T26_ROW, E::T27_ROW, E::T28_ROW, E::T29_ROW, E::T30_ROW,
+                         E::T31_ROW, E::TOTAL_ROW};
+    const u32 OFF[32] = {E::FINAL_EXP_T0_OFFSET, E::FINAL_EXP_T1_OFFSET, E::FINAL_EXP_T2_OFFSET, E::FINAL_EXP_T3_OFFSET, E::FINAL_EXP_T4_OFFSET,
+                         E::FINAL_EXP_T5_OFFSET, E::FINAL_EXP_T6_OFFSET, E::FINAL_EXP_T7_OFFSET, E::FINAL_EXP_T8_OFFSET, E::FINAL_EXP_T9_OFFSET,
+                         E::FINAL_EXP_T10_OFFSET, E::FINAL_EXP_T11_OFFSET, E::FINAL_EXP_T12_OFFSET, E::FINAL_EXP_T13_OFFSET, E::FINAL_EXP_T14_OFFSET,
+                         E::FINAL_EXP_T15_OFFSET, E::FINAL_EXP_T16_OFFSET, E::FINAL_EXP_T17_OFFSET, E::FINAL_EXP_T18_OFFSET, E::FINAL_EXP_T19_OFFSET,
+                         E::FINAL_EXP_T20_OFFSET, E::FINAL_EXP_T21_OFFSET, E::FINAL_EXP_T22_OFFSET, E::FINAL_EXP_T23_OFFSET, E::FINAL_EXP_T24_OFFSET,
+                         E::FINAL_EXP_T25_OFFSET, E::FINAL_EXP_T26_OFFSET, E::FINAL_EXP_T27_OFFSET, E::FINAL_EXP_T28_OFFSET, E::FINAL_EXP_T29_OFFSET,
+                         E::FINAL_EXP_T30_OFFSET, E::FINAL_EXP_T31_OFFSET};
+    Fp12 t[32];
+    auto out = [&](int k, const Fp12& v) { put_fp12_rows(tr, 0, last, OFF[k], v); t[k] = v; };
+    auto frob = [&](int k, const Fp12& v, unsigned pw) {                        // fill_trace_forbenius
+      const size_t s = ROW[k], e = ROW[k + 1] - 1;
+      tr.set_rows(s, e, E::FINAL_EXP_FORBENIUS_MAP_SELECTOR, 1);
+      fill_trace_fp12_forbenius_map(tr, v, pw, s, e, OP);
+      out(k, fp12_frobenius(v, pw));
+    };
+    auto mulop = [&](int k, const Fp12& a, const Fp12& b) {                     // fill_trace_mul
+      const size_t s = ROW[k], e = ROW[k + 1] - 1;
+      tr.set_rows(s, e, E::FINAL_EXP_MUL_SELECTOR, 1);
+      fill_trace_fp12_multiplication(tr, a, b, s, e, OP);
+      out(k, fp12_mul_native(a, b));
+    };
+    auto divop = [&](int k, const Fp12& a, const Fp12& b) {                     // fill_trace_div: res = a / b, the trace proves res * b
+      const size_t s = ROW[k], e = ROW[k + 1] - 1;
+      const Fp12 res = fp12_mul_native(a, fp12_inv(b));
+      tr.set_rows(s, e, E::FINAL_EXP_MUL_SELECTOR, 1);
+      fill_trace_fp12_multiplication(tr, res, b, s, e, OP);
+      out(k, res);
+    };
+    auto cexp = [&](int k, const Fp12& v) {                                     // fill_trace_cyc_exp
+      const size_t s = ROW[k], e = ROW[k + 1] - 1;
+      tr.set_rows(s, e, E::FINAL_EXP_CYCLOTOMIC_EXP_SELECTOR, 1);
+      out(k, fill_trace_cyclotomic_exp(tr, v, s, e, OP));
+    };
+    auto conj = [&](int k, const Fp12& v) {                                     // fill_trace_conjugate
+      tr.at(ROW[k], E::FINAL_EXP_CONJUGATE_SELECTOR) = 1;
+      out(k, fill_trace_fp12_conjugate(tr, v, ROW[k], OP));
+    };
+    auto csq = [&](int k, const Fp12& v) {                                      // fill_trace_cyc_sq
+      const size_t s = ROW[k], e = ROW[k + 1] - 1;
+      tr.set_rows(s, e, E::FINAL_EXP_CYCLOTOMIC_SQ_SELECTOR, 1);
+      fill_trace_cyclotomic_sq(tr, v, s, e, OP);
+      out(k, fp12_cyclotomic_square(v));
+    };
+    frob(0, X, 6); divop(1, t[0], X); frob(2, t[1], 2); mulop(3, t[2], t[1]); cexp(4, t[3]); conj(5, t[4]); csq(6, t[3]); conj(7, t[6]);
+    mulop(8, t[7], t[5]); cexp(9, t[8]); conj(10, t[9]); cexp(11, t[10]); conj(12, t[11]); cexp(13, t[12]); conj(14, t[13]); csq(15, t[5]);
+    mulop(16, t[14], t[15]); cexp(17, t[16]); conj(18, t[17]); mulop(19, t[5], t[12]); frob(20, t[19], 2); mulop(21, t[10], t[3]);
+    frob(22, t[21], 3); conj(23, t[3]); mulop(24, t[16], t[23]); frob(25, t[24], 1); conj(26, t[8]); mulop(27, t[18], t[26]);
+    mulop(28, t[27], t[3]); mulop(29, t[20], t[22]); mulop(30, t[29], t[25]); mulop(31, t[30], t[28]);
+    for (int i = 0; i < 12; i++)
+      for (int k = 0; k < 12; k++) {
+        public_inputs_out[E::PIS_INPUT_OFFSET + 12 * i + k] = X.c[i].w[k];
+        public_inputs_out[E::PIS_OUTPUT_OFFSET + 12 * i + k] = t[31].c[i].w[k];
+      }
     return SB_OK;
   } catch (const std::exception& e) {
     g_witness_error = e.what();

@@ -9,7 +9,8 @@ import oracle_lib as O
 import starky_bls12_381_b200 as sb
 from helpers import to_oracle_params
 from starky_bls12_381_b200 import airfiles, witness as W
-from starky_bls12_381_b200.binding import witness_ecc_agg, witness_fp12_mul
+from starky_bls12_381_b200.binding import (witness_ecc_agg, witness_final_exp, witness_fp12_mul, witness_miller_loop,
+                                           witness_pairing_precomp)
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
@@ -56,6 +57,46 @@ def test_cpp_ecc_agg_trace_equals_the_python_restatement():
         witness_ecc_agg(pts, bits, 4096)                      # 511 additions of 12 rows do not fit
 
 
+def _rand_fp2(rng):
+    return (W.random_fp(rng), W.random_fp(rng))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_cpp_pairing_precomp_trace_equals_the_python_restatement(seed):
+    rng = np.random.default_rng(0xB2007400 + seed)
+    x, y, z = _rand_fp2(rng), _rand_fp2(rng), _rand_fp2(rng)
+    if seed == 2:
+        z = (1, 0)                                            # an affine point handed over as projective
+    want_t, want_p = W.pairing_precomp_trace(x, y, z, 1024)  # column-major uint64 [29376][1024]
+    got_t, got_p = witness_pairing_precomp(x, y, z, 1024)    # row-major uint32 [1024][29376]
+    assert np.array_equal(got_p, want_p)
+    assert np.array_equal(got_t.astype(np.uint64).T, want_t)
+
+
+def test_cpp_miller_loop_trace_equals_the_python_restatement():
+    rng = np.random.default_rng(0xB2007500)
+    px, py = W.random_fp(rng), W.random_fp(rng)
+    q = (_rand_fp2(rng), _rand_fp2(rng), _rand_fp2(rng))
+    want_t, want_p = W.miller_loop_trace(px, py, q, 1024)    # column-major uint64 [97330][1024]
+    got_t, got_p = witness_miller_loop(px, py, q, 1024)      # row-major uint32 [1024][97330]
+    assert np.array_equal(got_p, want_p)
+    assert np.array_equal(got_t.astype(np.uint64).T, want_t)
+    with pytest.raises(sb.SbError):
+        witness_miller_loop(W.N.P, py, q, 1024)               # unreduced coordinate
+
+
+def test_cpp_final_exp_trace_equals_the_python_restatement():
+    rng = np.random.default_rng(0xB2007600)
+    x = W.random_fp12(rng)
+    got_t, got_p = witness_final_exp(x)                       # row-major uint32 [8192][73527] (2.4 GB)
+    want_t, want_p = W.final_exp_trace(x)                     # column-major uint64 [73527][8192]
+    assert np.array_equal(got_p, want_p)
+    for c0 in range(0, want_t.shape[0], 4096):                # compare in column blocks: no second 4.8 GB copy
+        assert np.array_equal(got_t[:, c0:c0 + 4096].astype(np.uint64).T, want_t[c0:c0 + 4096]), c0
+    with pytest.raises(sb.SbError):
+        witness_final_exp(x, 4096)                            # one row-selector column per row: 8192 rows only
+
+
 def test_unreduced_operands_are_rejected():
     bad = (W.N.P,) + (0,) * 11
     with pytest.raises(sb.SbError):
@@ -78,3 +119,42 @@ def test_gpu_proof_from_operands_equals_the_proof_of_the_python_trace():
         ctx.close()
     assert np.array_equal(got.words, want.words)
     assert O.verify(airfiles.air_path("fp12_mul", "air"), to_oracle_params(p), got.words) == 0, O.err()
+
+
+@pytest.mark.gpu
+def test_gpu_proofs_from_operands_of_the_larger_starks():
+    """sb_prove_pairing_precomp / sb_prove_miller_loop (operands in, proof out; the trace is generated in C++ as row-major
+    u32) give the proof of the Python restatement's trace word for word, and the oracle's verifier accepts it."""
+    rng = np.random.default_rng(0xB2007700)
+    x, y, z = _rand_fp2(rng), _rand_fp2(rng), _rand_fp2(rng)
+    px, py = W.random_fp(rng), W.random_fp(rng)
+    ctx = sb.Context(0)
+    try:
+        p = sb.standard_params(sb.StarkId.PAIRING_PRECOMP, 10)
+        trace, pis = W.pairing_precomp_trace(x, y, z, 1024)
+        want, got = ctx.prove(p, trace, pis), ctx.prove_pairing_precomp(p, x, y, z)
+        assert np.array_equal(got.words, want.words)
+        assert O.verify(airfiles.air_path("pairing_precomp", "air"), to_oracle_params(p), got.words) == 0, O.err()
+        p = sb.standard_params(sb.StarkId.MILLER_LOOP, 10)
+        trace, pis = W.miller_loop_trace(px, py, (x, y, z), 1024)
+        want, got = ctx.prove(p, trace, pis), ctx.prove_miller_loop(p, px, py, (x, y, z))
+        assert np.array_equal(got.words, want.words)
+        assert O.verify(airfiles.air_path("miller_loop", "air"), to_oracle_params(p), got.words) == 0, O.err()
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_final_exp_proof_from_its_operand_verifies():
+    rng = np.random.default_rng(0xB2007800)
+    x = W.random_fp12(rng)
+    p = sb.standard_params(sb.StarkId.FINAL_EXP, 13)
+    ctx = sb.Context(0)
+    try:
+        got = ctx.prove_final_exp(p, x)
+    finally:
+        ctx.close()
+    assert O.verify(airfiles.air_path("final_exp", "air"), to_oracle_params(p), got.words) == 0, O.err()
+    want_out = W.N.fp12_final_exponentiate(x)
+    pis = got.field("off_public_inputs", 288)
+    assert [int(v) for v in pis[144:288]] == [l for c in want_out for l in W.N.limbs(c)]
