@@ -96,6 +96,13 @@ extern "C" {
                           public_inputs: *const u64, flags: u32, out: *mut *mut sb_proof) -> c_int;
     // the seven proofs of one BLS verification (aggregate_proof.rs:279-370) through one call
     pub fn sb_prove_batch(ctxs: *const *mut sb_ctx, n_ctx: c_int, jobs: *mut sb_job, n_jobs: c_int) -> c_int;
+    // generate_trace in C++ + prove, from the operands of the *_main functions (aggregate_proof.rs:24-227); limbs are the
+    // reference's Fp = [u32; 12], little-endian
+    pub fn sb_prove_fp12_mul(ctx: *mut sb_ctx, p: *const sb_params, x: *const u32, y: *const u32, out: *mut *mut sb_proof) -> c_int;
+    pub fn sb_prove_ecc_agg(ctx: *mut sb_ctx, p: *const sb_params, points: *const u32, bits: *const u8, out: *mut *mut sb_proof) -> c_int;
+    pub fn sb_prove_pairing_precomp(ctx: *mut sb_ctx, p: *const sb_params, q: *const u32, out: *mut *mut sb_proof) -> c_int;
+    pub fn sb_prove_miller_loop(ctx: *mut sb_ctx, p: *const sb_params, g1: *const u32, q: *const u32, out: *mut *mut sb_proof) -> c_int;
+    pub fn sb_prove_final_exp(ctx: *mut sb_ctx, p: *const sb_params, x: *const u32, out: *mut *mut sb_proof) -> c_int;
 }
 
 #[repr(C)]

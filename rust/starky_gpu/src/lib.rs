@@ -128,6 +128,41 @@ pub fn prove_from_rows<S: GpuStark, const COLUMNS: usize>(
     Ok(proof)
 }
 
+/// The operands of one `*_main` function of aggregate_proof.rs, as the reference's limb arrays (`Fp = [u32; 12]`): the
+/// library generates the trace in C++ (csrc/witness.cpp, the restated `generate_trace`) and proves it, so neither
+/// `generate_trace` nor `trace_rows_to_poly_values` runs on the Rust side and the trace crosses PCIe once, as u32.
+pub enum Operands<'a> {
+    /// `fp12_mul_main(x, y)` (aggregate_proof.rs:122-151)
+    Fp12Mul { x: &'a [[u32; 12]; 12], y: &'a [[u32; 12]; 12] },
+    /// `calc_pairing_precomp_main(x, y, z)` (aggregate_proof.rs:24-69): Fp2 = [[u32; 12]; 2]
+    PairingPrecomp { q: &'a [[[u32; 12]; 2]; 3] },
+    /// `miller_loop_main(x, y, q)` (aggregate_proof.rs:71-121)
+    MillerLoop { g1: &'a [[u32; 12]; 2], q: &'a [[[u32; 12]; 2]; 3] },
+    /// `final_exponentiate_main(x)` (aggregate_proof.rs:153-184)
+    FinalExp { x: &'a [[u32; 12]; 12] },
+    /// `ec_aggregate_main(points, bits)` (aggregate_proof.rs:186-227): 512 affine G1 points and participation flags
+    EccAgg { points: &'a [[[u32; 12]; 2]; 512], bits: &'a [u8; 512] },
+}
+
+/// `generate_trace` + `prove` inside the library.  `p` = `params_for(&stark, &config, S::PUBLIC_INPUTS)`.
+#[cfg(feature = "gpu")]
+pub fn prove_from_operands(gpu: &mut GpuProver, p: &ffi::sb_params, ops: Operands) -> Result<StarkProofWithPublicInputs<F, C, D>> {
+    let mut out = std::ptr::null_mut();
+    let rc = unsafe {
+        match ops {
+            Operands::Fp12Mul { x, y } => ffi::sb_prove_fp12_mul(gpu.ctx, p, x.as_ptr() as *const u32, y.as_ptr() as *const u32, &mut out),
+            Operands::PairingPrecomp { q } => ffi::sb_prove_pairing_precomp(gpu.ctx, p, q.as_ptr() as *const u32, &mut out),
+            Operands::MillerLoop { g1, q } => ffi::sb_prove_miller_loop(gpu.ctx, p, g1.as_ptr() as *const u32, q.as_ptr() as *const u32, &mut out),
+            Operands::FinalExp { x } => ffi::sb_prove_final_exp(gpu.ctx, p, x.as_ptr() as *const u32, &mut out),
+            Operands::EccAgg { points, bits } => ffi::sb_prove_ecc_agg(gpu.ctx, p, points.as_ptr() as *const u32, bits.as_ptr(), &mut out),
+        }
+    };
+    if rc != ffi::SB_OK { return Err(anyhow!("{}", gpu.last_error())); }
+    let proof = unsafe { unpack(&*out) };
+    unsafe { ffi::sb_proof_free(out) };
+    Ok(proof)
+}
+
 #[cfg(feature = "gpu")]
 unsafe fn unpack(pr: &ffi::sb_proof) -> StarkProofWithPublicInputs<F, C, D> {
     unpack_words(&pr.layout, std::slice::from_raw_parts(pr.words, pr.layout.total_words as usize))

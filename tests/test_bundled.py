@@ -55,6 +55,18 @@ def test_bundled_fp12_mul_job_proves_and_verifies_in_the_oracle(inputs):
     assert O.verify(flat, to_oracle_params(p), words) == 0, O.err()
 
 
+def test_bundled_native_jobs_equal_the_python_jobs_on_the_small_starks(inputs):
+    """bundled.jobs_native (C++ witness generators, row-major u32) against bundled.jobs (Python restatement, column-major u64)
+    on the reference's own inputs: FP12Mul and both PairingPrecomp jobs (the others are compared in test_witness_cpp.py)."""
+    import numpy as np
+    want = bundled.jobs(inputs, {"fp12_mul", "pairing_precomp"})
+    got = bundled.jobs_native(inputs, {"fp12_mul", "pairing_precomp"})
+    assert [j[0] for j in got] == [j[0] for j in want] == ["pairing_precomp", "pairing_precomp", "fp12_mul"]
+    for (_, wt, wp), (_, gt, gp) in zip(want, got):
+        assert np.array_equal(gp, wp)
+        assert np.array_equal(gt.astype(np.uint64).T, wt)
+
+
 @pytest.mark.gpu
 @pytest.mark.slow
 def test_gpu_proves_the_seven_bundled_proofs(inputs):
