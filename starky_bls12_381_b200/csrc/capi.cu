@@ -226,6 +226,34 @@ void ingest_and_commit_trace(sb_ctx* ctx, const sb_params* p, const void* trace,
   if (!pipelined) {
     const u64* d_values = ingest_trace(ctx, p, trace, layout);
     if (h2d_done) CUDA_CHECK(cudaEventRecord(h2d_done, ctx->stream));
+    // The other layouts (row-major rows, device-resident columns) inside sb_prove_batch (SB_YIELD_SLABS, set by the
+    // scheduler): K1 and K2 alternate over column groups as in the pipelined path below -- the same work in more launches,
+    // but a throughput-bound proof then yields the SMs at every launch boundary instead of holding them with one
+    // 350 ms leaf-sponge launch, and the latency-bound proofs next to it keep running.
+    const size_t group = 2048;
+    if (ctx->yield_slabs && C > 2 * group && sb_hash_leaves_streamable((uint32_t)C) && !getenv("SB_NO_STREAM_HASH")) {
+      ctx->coeffs.ensure(8 * n * C);
+      ctx->lde.ensure(8 * N * C);
+      ctx->tree.ensure(32 * 2 * N);
+      ctx->sponge.ensure(8ull * 12 * N);
+      stage_begin(ctx, "lde");
+      stage_begin(ctx, "leaf_hash");                                   // (the two stage timers overlap in this path)
+      for (size_t c0 = 0; c0 < C; c0 += group) {
+        const size_t cnt = std::min(group, C - c0);
+        const bool last = c0 + cnt == C;
+        sb_lde_trace(ctx, d_values + c0 * n, ctx->coeffs.as<u64>() + c0 * n, ctx->lde.as<u64>() + c0 * N, (uint32_t)cnt, p->log_n, p->rate_bits);
+        if (last) stage_end(ctx, "lde");
+        sb_hash_leaves_stream(ctx, ctx->lde.as<u64>() + c0 * N, (uint32_t)cnt, (uint32_t)N, p->log_n, ctx->sponge.as<u64>(), c0 == 0, last,
+                              ctx->tree.as<u64>());
+      }
+      stage_end(ctx, "leaf_hash");
+      stage_begin(ctx, "merkle");
+      sb_merkle_levels(ctx, ctx->tree.as<u64>(), (uint32_t)N, p->cap_height);
+      stage_end(ctx, "merkle");
+      ctx->cur = *p;
+      ctx->have_lde = true;
+      return;
+    }
     commit_trace(ctx, p, d_values);
     return;
   }

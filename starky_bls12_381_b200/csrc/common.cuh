@@ -73,6 +73,7 @@ struct sb_ctx {
   // resident state of the current proof
   sb_params cur = {};
   bool have_trace = false, have_lde = false;
+  bool yield_slabs = false;   // set by sb_prove_batch: commit traces of every layout group by group (capi.cu)
   DevBuf trace;        // [C][n] u64 column-major values
   DevBuf staging;      // raw host layout before transposition
   DevBuf coeffs;       // [C][n] coefficients, bit-reversed coefficient order

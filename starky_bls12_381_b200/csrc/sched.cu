@@ -9,13 +9,14 @@
 //     per MillerLoop proof, 4: 78 ms).
 //   * many-leaf proofs (FinalExp, ECCAgg: 32768 leaves) fill the GPU on their own.  With a device-resident trace their leaf
 //     sponge is ONE launch whose blocks hold every SM for the whole chain, and a latency-bound chain next to it starves
-//     (MillerLoop 225 -> 937 ms): such a job runs alone on its device.  With a host trace the sponge follows the column
-//     slabs (capi.cu: one launch per >= 2048 columns, ~12 ms), the small jobs' blocks get in at every launch boundary and
-//     fill the issue slots the dp kernel leaves (it is heavy-pipe bound at 64 % issue): the full BLS set on one GPU,
-//     918 -> 806 ms, FinalExp 608 -> 773 ms with both MillerLoops, both PairingPrecomps and FP12Mul inside it.
+//     (MillerLoop 225 -> 937 ms).  Inside a batch the commitment therefore goes column group by column group for every
+//     trace layout (capi.cu: one K1 + one K2 launch per >= 2048 columns, ~12 ms; for the host column layouts the groups
+//     follow the PCIe slabs anyway): the small jobs' blocks get in at every launch boundary and fill the issue slots the
+//     leaf sponge leaves (< 50 % issue) -- the full BLS set on one GPU 918 -> 806 ms in round 2, 700 ms with this round's
+//     leaf sponge.  SB_SCHED_MIX=0 restores "a throughput-bound job runs alone on its device".
 // Rule per device: a throughput-bound job always runs on the device's first context, so that its tens of GB of buffers
-// exist once, and one at a time; latency-bound jobs share a device up to the number of contexts it has, next to a
-// throughput-bound job only if that one streams its trace from the host.  Jobs are taken in decreasing estimated cost.
+// exist once, and one at a time; latency-bound jobs share a device up to the number of contexts it has, also next to a
+// throughput-bound job.  Jobs are taken in decreasing estimated cost.
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -85,7 +86,7 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
             if (taken[k]) continue;
             any_left = true;
             const bool b = is_big(jobs[k], ctx);
-            const bool streamed = mix && (jobs[k].layout == SB_TRACE_COLMAJOR_U64 || jobs[k].layout == SB_TRACE_COLS_U64_PTRS);
+            const bool streamed = mix;      // every layout commits its trace group by group inside a batch (ctx->yield_slabs)
             if (st.running_big && (b || !st.big_is_streamed)) break;   // the device belongs to a throughput-bound job
             if (b && (!takes_big || (st.running_few > 0 && !streamed))) continue;  // needs its device's first context (and an idle device unless it streams); a smaller job may still fit
             pick = k; big = b;
@@ -101,13 +102,15 @@ extern "C" int sb_prove_batch(sb_ctx* const* ctxs, int n_ctx, sb_job* jobs, int 
         DeviceState& st = dev[d];
         if (big) {
           st.running_big = true;
-          st.big_is_streamed = mix && (jobs[pick].layout == SB_TRACE_COLMAJOR_U64 || jobs[pick].layout == SB_TRACE_COLS_U64_PTRS);
+          st.big_is_streamed = mix;
         } else st.running_few++;
       }
       sb_job& j = jobs[pick];
       const auto t0 = std::chrono::steady_clock::now();
       const float ts = since();
+      ctx->yield_slabs = mix;
       j.rc = sb_prove(ctx, &j.params, j.trace, j.layout, j.public_inputs, &j.proof);
+      ctx->yield_slabs = false;
       j.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (trace) fprintf(stderr, "sb_prove_batch: job %d (stark %u) on context %d: %.1f -> %.1f ms\n", pick, j.params.stark_id, c, ts, since());
       {

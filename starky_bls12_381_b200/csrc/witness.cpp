@@ -15,7 +15,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -904,6 +907,14 @@ void fill_trace_miller_loop(Trace& tr, const Fp& x, const Fp& y, const std::vect
   put_fp12_rows(tr, s, e, col + M::MILLER_LOOP_RES_OFFSET, f12);
   negate6_rows(tr, half(f12, 1), s, e, col + M::RES_CONJUGATE_OFFSET);
 }
+Fp12 fp12_cyclotomic_exponent(const Fp12& x) {                                               // native.rs:1300-1309
+  Fp12 z = fp12_one();
+  for (int i = 63; i >= 0; i--) {
+    z = fp12_cyclotomic_square(z);
+    if ((BLS_X >> i) & 1) z = fp12_mul_native(z, x);
+  }
+  return z;
+}
 Fp2 fp2_from_limbs(const u32* l) {
   Fp2 r = {{Big::from_limbs(l, 12), Big::from_limbs(l + 12, 12)}};
   for (int i = 0; i < 2; i++) if (cmp(r.c[i], MODP()) >= 0) throw std::invalid_argument("witness: Fp coefficient is not reduced modulo p");
@@ -1207,47 +1218,85 @@ int sb_witness_final_exp(const uint32_t* x, uint32_t num_rows, uint32_t* trace_o
                          E::FINAL_EXP_T20_OFFSET, E::FINAL_EXP_T21_OFFSET, E::FINAL_EXP_T22_OFFSET, E::FINAL_EXP_T23_OFFSET, E::FINAL_EXP_T24_OFFSET,
                          E::FINAL_EXP_T25_OFFSET, E::FINAL_EXP_T26_OFFSET, E::FINAL_EXP_T27_OFFSET, E::FINAL_EXP_T28_OFFSET, E::FINAL_EXP_T29_OFFSET,
                          E::FINAL_EXP_T30_OFFSET, E::FINAL_EXP_T31_OFFSET};
+    // The 32 steps of native.rs:1311-1345.  Their values first (a few ms), then the trace blocks: step k fills rows
+    // ROW[k] .. ROW[k+1]-1 of the operation columns and its own result columns, so the steps are filled by independent
+    // host threads (the five cyclotomic exponentiations, 841 rows each, are most of the 2.4 GB).
+    enum Kind { FROB, MUL, DIV, CEXP, CONJ, CSQ };
+    struct Step { Kind kind; int a, b; unsigned pw; };                          // operands: index into t, -1 = the input x
+    static const Step STEPS[32] = {
+        {FROB, -1, 0, 6}, {DIV, 0, -1, 0}, {FROB, 1, 0, 2}, {MUL, 2, 1, 0}, {CEXP, 3, 0, 0}, {CONJ, 4, 0, 0}, {CSQ, 3, 0, 0}, {CONJ, 6, 0, 0},
+        {MUL, 7, 5, 0}, {CEXP, 8, 0, 0}, {CONJ, 9, 0, 0}, {CEXP, 10, 0, 0}, {CONJ, 11, 0, 0}, {CEXP, 12, 0, 0}, {CONJ, 13, 0, 0}, {CSQ, 5, 0, 0},
+        {MUL, 14, 15, 0}, {CEXP, 16, 0, 0}, {CONJ, 17, 0, 0}, {MUL, 5, 12, 0}, {FROB, 19, 0, 2}, {MUL, 10, 3, 0}, {FROB, 21, 0, 3}, {CONJ, 3, 0, 0},
+        {MUL, 16, 23, 0}, {FROB, 24, 0, 1}, {CONJ, 8, 0, 0}, {MUL, 18, 26, 0}, {MUL, 27, 3, 0}, {MUL, 20, 22, 0}, {MUL, 29, 25, 0}, {MUL, 30, 28, 0}};
     Fp12 t[32];
-    auto out = [&](int k, const Fp12& v) { put_fp12_rows(tr, 0, last, OFF[k], v); t[k] = v; };
-    auto frob = [&](int k, const Fp12& v, unsigned pw) {                        // fill_trace_forbenius
+    auto val = [&](int i) -> const Fp12& { return i < 0 ? X : t[i]; };
+    for (int k = 0; k < 32; k++) {
+      const Step& st = STEPS[k];
+      const Fp12& a = val(st.a);
+      switch (st.kind) {
+        case FROB: t[k] = fp12_frobenius(a, st.pw); break;
+        case MUL: t[k] = fp12_mul_native(a, val(st.b)); break;
+        case DIV: t[k] = fp12_mul_native(a, fp12_inv(val(st.b))); break;       // the trace proves t[k] * b = a
+        case CEXP: t[k] = fp12_cyclotomic_exponent(a); break;
+        case CONJ: t[k] = fp12_conjugate(a); break;
+        case CSQ: t[k] = fp12_cyclotomic_square(a); break;
+      }
+    }
+    auto fill_step = [&](int k) {
+      const Step& st = STEPS[k];
+      const Fp12& a = val(st.a);
       const size_t s = ROW[k], e = ROW[k + 1] - 1;
-      tr.set_rows(s, e, E::FINAL_EXP_FORBENIUS_MAP_SELECTOR, 1);
-      fill_trace_fp12_forbenius_map(tr, v, pw, s, e, OP);
-      out(k, fp12_frobenius(v, pw));
+      switch (st.kind) {
+        case FROB:                                                               // fill_trace_forbenius
+          tr.set_rows(s, e, E::FINAL_EXP_FORBENIUS_MAP_SELECTOR, 1);
+          fill_trace_fp12_forbenius_map(tr, a, st.pw, s, e, OP);
+          break;
+        case MUL:                                                                // fill_trace_mul
+          tr.set_rows(s, e, E::FINAL_EXP_MUL_SELECTOR, 1);
+          fill_trace_fp12_multiplication(tr, a, val(st.b), s, e, OP);
+          break;
+        case DIV:                                                                // fill_trace_div
+          tr.set_rows(s, e, E::FINAL_EXP_MUL_SELECTOR, 1);
+          fill_trace_fp12_multiplication(tr, t[k], val(st.b), s, e, OP);
+          break;
+        case CEXP: {                                                             // fill_trace_cyc_exp
+          tr.set_rows(s, e, E::FINAL_EXP_CYCLOTOMIC_EXP_SELECTOR, 1);
+          const Fp12 z = fill_trace_cyclotomic_exp(tr, a, s, e, OP);
+          for (int i = 0; i < 12; i++) if (cmp(z.c[i], t[k].c[i])) throw std::logic_error("witness: cyclotomic exponentiation, trace and value differ");
+          break;
+        }
+        case CONJ:                                                               // fill_trace_conjugate
+          tr.at(s, E::FINAL_EXP_CONJUGATE_SELECTOR) = 1;
+          fill_trace_fp12_conjugate(tr, a, s, OP);
+          break;
+        case CSQ:                                                                // fill_trace_cyc_sq
+          tr.set_rows(s, e, E::FINAL_EXP_CYCLOTOMIC_SQ_SELECTOR, 1);
+          fill_trace_cyclotomic_sq(tr, a, s, e, OP);
+          break;
+      }
+      put_fp12_rows(tr, 0, last, OFF[k], t[k]);
     };
-    auto mulop = [&](int k, const Fp12& a, const Fp12& b) {                     // fill_trace_mul
-      const size_t s = ROW[k], e = ROW[k + 1] - 1;
-      tr.set_rows(s, e, E::FINAL_EXP_MUL_SELECTOR, 1);
-      fill_trace_fp12_multiplication(tr, a, b, s, e, OP);
-      out(k, fp12_mul_native(a, b));
-    };
-    auto divop = [&](int k, const Fp12& a, const Fp12& b) {                     // fill_trace_div: res = a / b, the trace proves res * b
-      const size_t s = ROW[k], e = ROW[k + 1] - 1;
-      const Fp12 res = fp12_mul_native(a, fp12_inv(b));
-      tr.set_rows(s, e, E::FINAL_EXP_MUL_SELECTOR, 1);
-      fill_trace_fp12_multiplication(tr, res, b, s, e, OP);
-      out(k, res);
-    };
-    auto cexp = [&](int k, const Fp12& v) {                                     // fill_trace_cyc_exp
-      const size_t s = ROW[k], e = ROW[k + 1] - 1;
-      tr.set_rows(s, e, E::FINAL_EXP_CYCLOTOMIC_EXP_SELECTOR, 1);
-      out(k, fill_trace_cyclotomic_exp(tr, v, s, e, OP));
-    };
-    auto conj = [&](int k, const Fp12& v) {                                     // fill_trace_conjugate
-      tr.at(ROW[k], E::FINAL_EXP_CONJUGATE_SELECTOR) = 1;
-      out(k, fill_trace_fp12_conjugate(tr, v, ROW[k], OP));
-    };
-    auto csq = [&](int k, const Fp12& v) {                                      // fill_trace_cyc_sq
-      const size_t s = ROW[k], e = ROW[k + 1] - 1;
-      tr.set_rows(s, e, E::FINAL_EXP_CYCLOTOMIC_SQ_SELECTOR, 1);
-      fill_trace_cyclotomic_sq(tr, v, s, e, OP);
-      out(k, fp12_cyclotomic_square(v));
-    };
-    frob(0, X, 6); divop(1, t[0], X); frob(2, t[1], 2); mulop(3, t[2], t[1]); cexp(4, t[3]); conj(5, t[4]); csq(6, t[3]); conj(7, t[6]);
-    mulop(8, t[7], t[5]); cexp(9, t[8]); conj(10, t[9]); cexp(11, t[10]); conj(12, t[11]); cexp(13, t[12]); conj(14, t[13]); csq(15, t[5]);
-    mulop(16, t[14], t[15]); cexp(17, t[16]); conj(18, t[17]); mulop(19, t[5], t[12]); frob(20, t[19], 2); mulop(21, t[10], t[3]);
-    frob(22, t[21], 3); conj(23, t[3]); mulop(24, t[16], t[23]); frob(25, t[24], 1); conj(26, t[8]); mulop(27, t[18], t[26]);
-    mulop(28, t[27], t[3]); mulop(29, t[20], t[22]); mulop(30, t[29], t[25]); mulop(31, t[30], t[28]);
+    {
+      // longest first: the five exponentiations, then everything else, over up to 8 threads
+      std::vector<int> order;
+      for (int k = 0; k < 32; k++) if (STEPS[k].kind == CEXP) order.push_back(k);
+      for (int k = 0; k < 32; k++) if (STEPS[k].kind != CEXP) order.push_back(k);
+      std::atomic<size_t> next{0};
+      std::mutex err_mu;
+      std::string err;
+      const unsigned hw = std::thread::hardware_concurrency();
+      const unsigned workers = std::max(1u, std::min(8u, hw ? hw : 1u));
+      std::vector<std::thread> th;
+      for (unsigned w = 0; w < workers; w++)
+        th.emplace_back([&] {
+          for (size_t i; (i = next.fetch_add(1)) < order.size();) {
+            try { fill_step(order[i]); }
+            catch (const std::exception& ex) { std::lock_guard<std::mutex> g(err_mu); if (err.empty()) err = ex.what(); }
+          }
+        });
+      for (auto& x : th) x.join();
+      if (!err.empty()) throw std::runtime_error(err);
+    }
     for (int i = 0; i < 12; i++)
       for (int k = 0; k < 12; k++) {
         public_inputs_out[E::PIS_INPUT_OFFSET + 12 * i + k] = X.c[i].w[k];

@@ -164,6 +164,12 @@ def test_prove_batch_schedules_the_seven_proofs_and_returns_them_in_job_order():
             for (res, ms), w in zip(got[:-1], want):
                 assert np.array_equal(res.words, w) and ms > 0
             assert isinstance(got[-1][0], sb.SbError) and got[-1][0].code == -1
+        # inside a batch every layout commits its trace column group by column group (capi.cu, ctx->yield_slabs): the same
+        # jobs as row-major u32 rows (what the C++ witness generators write) give the same proofs
+        rows = [(p, np.ascontiguousarray(t.T).astype(np.uint32), sb.TraceLayout.ROWMAJOR_U32, pis) for p, t, _, pis in jobs[:-1]]
+        got = prove_batch(ctxs, rows)
+        for (res, ms), w in zip(got, want):
+            assert np.array_equal(res.words, w)
     finally:
         one.close()
         for c in ctxs:
