@@ -211,7 +211,7 @@ def roofline_for(stark, info, kern, ms_step, imad, hbm_peak, peak_src):
     t_hash = (kern["leaf_hash"] + kern["merkle"]) * 1e-3
     t_lde, t_q = kern["lde"] * 1e-3, kern["quotient"] * 1e-3
     lde_bytes = 8.0 * C * (n + n + N)           # trace read + coefficients kept + LDE written
-    k2 = "leaf_sponge_sp_kernel" if N <= 64 * 148 else "leaf_sponge_mm_kernel"
+    k2 = "leaf_sponge_mm_kernel" if N <= 64 * 148 else "leaf_sponge_mm_het_kernel"
     return {
         # dominant kernel of the step: the Poseidon leaf sponge (integer-pipe bound)
         "kernel": k2 + "+merkle_level_kernel", "bound": "imad",

@@ -79,40 +79,45 @@ __device__ __forceinline__ u64 shfl64(u64 v, unsigned src) {
 // DBG (lab only; tools/perf/poseidon_lab mmx).  Timing by elimination, wrong digests: 1 = no S-box in partial rounds,
 // 2 = no matrix instruction, 4 = no recombination, 8 = no S-box in full rounds.  Correct variants: 16 = the other fold in
 // the S-box, 32 = limb pairs as PRMT + IADD3 on the ALU pipe instead of IMAD.
-template <int NL, int DBG = 0>
-__global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
-                                                            uint32_t n_leaves, unsigned log_block,
-                                                            u64* __restrict__ digests,
-                                                            const u64* __restrict__ state_in = nullptr,
-                                                            u64* __restrict__ state_out = nullptr) {
-  constexpr int MT = NL > 2 ? NL / 2 : 1, H = NL > 1 ? 2 : 1, LPW = 8 * NL;       // row tiles, rows per lane and tile, leaves per warp
-  // Round constants in the equivalent form with one non-zero constant per partial round (poseidon_fast.h, RC_EQ):
-  //   rcs: every round as (low half, high half), each a u64, for the layers that feed a full round; row 30 = zeros
-  //   rcw: the word-0 constants of rounds 5..25 as accumulator images (16-bit chunk q on limb 2q of both rows), [1] for
-  //        the lanes that own word 0 and zeros [0] for the others
-  __shared__ __align__(16) u64 rcs[31][12][2];
-  __shared__ __align__(16) u32 rcw[21][2][4][4];   // [round][owns word 0][instruction][accumulator register]
+// Round constants in the equivalent form with one non-zero constant per partial round (poseidon_fast.h, RC_EQ):
+//   rcs: every round as (low half, high half), each a u64, for the layers that feed a full round; row 30 = zeros
+//   rcw: the word-0 constants of rounds 5..25 as accumulator images (16-bit chunks on the even limbs), [1] for the lanes
+//        that own word 0 and zeros [0] for the others; the image depends on the tile layout (NL == 1 or not)
+struct __align__(16) MmTables {
+  u64 rcs[31][12][2];
+  u32 rcw[21][2][4][4];   // [round][owns word 0][instruction][accumulator register]
+};
+template <int NL>
+__device__ __forceinline__ void mm_fill_tables(MmTables& T) {      // by the whole block; the caller synchronises
   for (unsigned i = threadIdx.x; i < 31 * 12; i += blockDim.x) {
     const u64 c = c_poseidon_rc_eq[i];
-    rcs[i / 12][i % 12][0] = c & 0xFFFFFFFFull;
-    rcs[i / 12][i % 12][1] = c >> 32;
+    T.rcs[i / 12][i % 12][0] = c & 0xFFFFFFFFull;
+    T.rcs[i / 12][i % 12][1] = c >> 32;
   }
   for (unsigned i = threadIdx.x; i < 21 * 4; i += blockDim.x) {
     const u64 c = c_poseidon_rc_eq[12 * (5 + i / 4)];
-    u32* o = rcw[i / 4][1][i % 4];
-    u32* z = rcw[i / 4][0][i % 4];
-    if (NL == 1) {      // instruction i < 2 holds limbs 4i..4i+3: chunks 2i, 2i+1 on its registers 0 and 2
-      o[0] = (u32)(c >> (32 * (i % 4))) & 0xFFFFu; o[1] = 0; o[2] = (u32)(c >> (32 * (i % 4) + 16)) & 0xFFFFu; o[3] = 0;
-      if (i % 4 >= 2) { o[0] = 0; o[2] = 0; }
-    } else {            // instruction i holds limbs 2i, 2i+1 of rows g and g+8: chunk i on registers 0 and 2
-      const u32 ch = (u32)(c >> (16 * (i % 4))) & 0xFFFFu;
+    const unsigned q = i % 4;
+    u32* o = T.rcw[i / 4][1][q];
+    u32* z = T.rcw[i / 4][0][q];
+    if (NL == 1) {      // instruction q < 2 holds limbs 4q..4q+3: chunks 2q, 2q+1 on its registers 0 and 2
+      o[0] = q < 2 ? (u32)(c >> (32 * q)) & 0xFFFFu : 0u; o[1] = 0; o[2] = q < 2 ? (u32)(c >> (32 * q + 16)) & 0xFFFFu : 0u; o[3] = 0;
+    } else {            // instruction q holds limbs 2q, 2q+1 of rows g and g+8: chunk q on registers 0 and 2
+      const u32 ch = (u32)(c >> (16 * q)) & 0xFFFFu;
       o[0] = ch; o[1] = 0; o[2] = ch; o[3] = 0;
     }
     z[0] = 0; z[1] = 0; z[2] = 0; z[3] = 0;
   }
-  __syncthreads();
+}
+
+// the sponge of the 8 NL leaves base .. base + 8 NL - 1, by one warp
+template <int NL, int DBG>
+__device__ __forceinline__ void mm_sponge_warp(const MmTables& T, uint32_t base, const u64* __restrict__ cols, uint32_t leaf_len,
+                                               uint32_t n_leaves, unsigned log_block, u64* __restrict__ digests,
+                                               const u64* __restrict__ state_in, u64* __restrict__ state_out) {
+  constexpr int MT = NL > 2 ? NL / 2 : 1, H = NL > 1 ? 2 : 1;       // row tiles, rows per lane and tile
+  const auto& rcs = T.rcs;
+  const auto& rcw = T.rcw;
   const unsigned lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LPW;
   if (base >= n_leaves) return;
 
   uint32_t pos[NL];
@@ -311,4 +316,44 @@ __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const
         if (3 * t + k < 4) d[3 * t + k] = gl_canon(s[L][k]);
     }
   }
+}
+
+template <int NL, int DBG = 0>
+__global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                            uint32_t n_leaves, unsigned log_block,
+                                                            u64* __restrict__ digests,
+                                                            const u64* __restrict__ state_in = nullptr,
+                                                            u64* __restrict__ state_out = nullptr) {
+  __shared__ MmTables T;
+  mm_fill_tables<NL>(T);
+  __syncthreads();
+  const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (8 * NL);
+  mm_sponge_warp<NL, DBG>(T, base, cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
+}
+
+// Throughput-bound shapes (32 768 leaves on 148 SMs = 55.35 leaves per scheduler): with one kind of warp the schedulers end
+// up with 48 or 64 leaves and the kernel lasts as long as the fuller ones (13.5 % of the machine idle).  Here one block per
+// SM gives EVERY scheduler (warp index mod 4) the same mix: N4 32-leaf warps, N2 16-leaf warps and N1 8-leaf warps -- the
+// product uses (0, 3, 1) = 56 leaves per scheduler.  Launch with 128 (N4 + N2 + N1) threads and enough dynamic shared
+// memory that two blocks do not share an SM (merkle.cu).
+template <int N4, int N2, int N1>
+struct MmHet {
+  static constexpr uint32_t PER_SCHED = 32 * N4 + 16 * N2 + 8 * N1, LEAVES = 4 * PER_SCHED, THREADS = 128 * (N4 + N2 + N1);
+};
+template <int N4, int N2, int N1, int DBG = 0>
+__global__ void __launch_bounds__(128 * (N4 + N2 + N1)) leaf_sponge_mm_het_kernel(const u64* __restrict__ cols, uint32_t leaf_len,
+                                                                  uint32_t n_leaves, unsigned log_block, u64* __restrict__ digests,
+                                                                  const u64* __restrict__ state_in = nullptr,
+                                                                  u64* __restrict__ state_out = nullptr) {
+  using H = MmHet<N4, N2, N1>;
+  __shared__ MmTables T2, T1;
+  mm_fill_tables<2>(T2);                                       // (the 32- and 16-leaf warps share the accumulator images)
+  mm_fill_tables<1>(T1);
+  __syncthreads();
+  const unsigned w = threadIdx.x >> 5, sched = w & 3;
+  const int slot = (int)(w >> 2);
+  const uint32_t b0 = blockIdx.x * H::LEAVES + sched * H::PER_SCHED;
+  if (slot < N4) mm_sponge_warp<4, DBG>(T2, b0 + 32 * slot, cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
+  else if (slot < N4 + N2) mm_sponge_warp<2, DBG>(T2, b0 + 32 * N4 + 16 * (slot - N4), cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
+  else mm_sponge_warp<1, DBG>(T1, b0 + 32 * N4 + 16 * N2 + 8 * (slot - N4 - N2), cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
 }

@@ -58,9 +58,21 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ 
 
 // leaves per warp of the matrix-instruction sponge: 8 up to 64 leaves per SM (latency-bound), 32 once that still leaves
 // ~1.5 warps per scheduler, 16 in between (measured, lab "mm")
+// 9 = one block per SM that gives every scheduler three 16-leaf warps and one 8-leaf warp (leaf_sponge_mm_het_kernel), when
+// the leaves fill that shape to more than 6/7 (FinalExp / ECCAgg: 32768 leaves on 148 SMs, 33152 places)
+typedef MmHet<0, 3, 1> HetShape;
 static int sb_mm_kind(sb_ctx* ctx, uint32_t n_leaves) {
   if ((uint64_t)n_leaves <= 64ull * ctx->sm_count) return 8;
+  const uint64_t places = (uint64_t)HetShape::LEAVES * ctx->sm_count;
+  if (n_leaves <= places && 7ull * n_leaves > 6 * places) return 9;
   return (uint64_t)n_leaves >= 160ull * ctx->sm_count ? 7 : 6;
+}
+static void launch_mm_het(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, uint32_t n_leaves, unsigned log_block, u64* d_digests,
+                          const u64* in, u64* out) {
+  // 120 KB of (unused) dynamic shared memory: two blocks never share an SM.  Per device: function attributes are per context.
+  CUDA_CHECK(cudaFuncSetAttribute(leaf_sponge_mm_het_kernel<0, 3, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 << 10));
+  LAUNCH(ctx, (leaf_sponge_mm_het_kernel<0, 3, 1, 0>), (n_leaves + HetShape::LEAVES - 1) / HetShape::LEAVES, HetShape::THREADS, 120 << 10,
+         d_cols, leaf_len, n_leaves, log_block, d_digests, in, out);
 }
 
 void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, uint32_t n_leaves, unsigned log_block,
@@ -71,14 +83,15 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
   //   everything else: the dense MDS layer as an integer matrix instruction over the lanes of one warp (leafhash_mm.cuh),
   //     8 = 8 leaves per warp for the latency-bound shapes (PairingPrecomp 4096, MillerLoop 2048 leaves: every leaf is in
   //         flight at once and wall time = chain length x latency of one permutation),
-  //     6 = 16 and 7 = 32 leaves per warp for the throughput-bound ones (FinalExp / ECCAgg 32768 leaves);
+  //     6 = 16 and 7 = 32 leaves per warp for the throughput-bound ones, 9 = one block per SM with the same mix of 16- and
+  //         8-leaf warps on every scheduler when the leaves fill that shape (FinalExp / ECCAgg: 32768 leaves on 148 SMs);
   //   round 1 / 2 kernels, still selectable: 13 = one state word per warp, sparse partial rounds with a reducer warp (the
   //     former latency kernel), 12 = its dense two-barrier variant, 4 = three words per thread, four warps per 32 leaves,
   //     dense MDS on dp2a (the former throughput kernel), 3 = the same on IMAD.WIDE, 5 = dp2a + sparse partial rounds.
-  // SB_LEAF_KERNEL=1|3|4|5|6|7|8|12|13 overrides the choice (profiling, tests).
+  // SB_LEAF_KERNEL=1|3|4|5|6|7|8|9|12|13 overrides the choice (profiling, tests).
   int kind = 1;
   if (leaf_len > 4 && perms > 2) kind = sb_mm_kind(ctx, n_leaves);
-  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 6 || v == 7 || v == 8 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
+  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 6 || v == 7 || v == 8 || v == 9 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
   const uint32_t groups = (n_leaves + 31) / 32;
   if (kind == 13) {
     // SB_SP_VARIANT: lab variants of the sp kernel (leafhash.cuh); 0 = the round-1 kernel
@@ -96,6 +109,8 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
     LAUNCH(ctx, (leaf_sponge_w12_kernel<0, 1>), groups, 384, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 4) {
     LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
+  } else if (kind == 9) {
+    launch_mm_het(ctx, d_cols, leaf_len, n_leaves, log_block, d_digests, nullptr, nullptr);
   } else if (kind == 8) {
     LAUNCH(ctx, leaf_sponge_mm_kernel<1>, (n_leaves + 7) / 8, 32, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 6) {
@@ -130,6 +145,8 @@ void sb_hash_leaves_stream(sb_ctx* ctx, const u64* d_cols, uint32_t n_cols, uint
     LAUNCH(ctx, leaf_sponge_sp_kernel<0>, groups, 416, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else if (old)
     LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
+  else if (kind == 9)
+    launch_mm_het(ctx, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else if (kind == 8)
     LAUNCH(ctx, leaf_sponge_mm_kernel<1>, (n_leaves + 7) / 8, 32, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else if (kind == 7)

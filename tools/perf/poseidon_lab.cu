@@ -281,6 +281,14 @@ int main(int argc, char** argv) {
       run("mm<1>  8 leaves per warp, block 32", [&] { leaf_sponge_mm_kernel<1><<<(sh.n_leaves + 7) / 8, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       run("mm<2> 16 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<2><<<(sh.n_leaves + 31) / 32, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       run("mm<4> 32 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<4><<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+#define HET(N4, N2, N1, label) do { using Hh = MmHet<N4, N2, N1>; \
+      CK(cudaFuncSetAttribute(leaf_sponge_mm_het_kernel<N4, N2, N1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 << 10)); \
+      run(label, [&] { leaf_sponge_mm_het_kernel<N4, N2, N1, 0><<<(sh.n_leaves + Hh::LEAVES - 1) / Hh::LEAVES, Hh::THREADS, 120 << 10>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false); } while (0)
+      HET(0, 3, 1, "mm het: 3 x 16 + 8 leaves per scheduler");
+      HET(1, 1, 1, "mm het: 32 + 16 + 8 leaves per scheduler");
+      HET(1, 0, 3, "mm het: 32 + 3 x 8 leaves per scheduler");
+      HET(0, 2, 3, "mm het: 2 x 16 + 3 x 8 leaves per scheduler");
+      HET(0, 0, 7, "mm het: 7 x 8 leaves per scheduler");
       cudaFree(d_cols); cudaFree(d_dig);
     }
     printf("lab done\n");
