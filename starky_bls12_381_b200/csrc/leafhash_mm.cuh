@@ -352,8 +352,12 @@ __global__ void __launch_bounds__(128 * (N4 + N2 + N1)) leaf_sponge_mm_het_kerne
   __syncthreads();
   const unsigned w = threadIdx.x >> 5, sched = w & 3;
   const int slot = (int)(w >> 2);
-  const uint32_t b0 = blockIdx.x * H::LEAVES + sched * H::PER_SCHED;
-  if (slot < N4) mm_sponge_warp<4, DBG>(T2, b0 + 32 * slot, cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
-  else if (slot < N4 + N2) mm_sponge_warp<2, DBG>(T2, b0 + 32 * N4 + 16 * (slot - N4), cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
-  else mm_sponge_warp<1, DBG>(T1, b0 + 32 * N4 + 16 * N2 + 8 * (slot - N4 - N2), cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
+  // leaves of the block: first the 32-leaf warps' (slot-major, scheduler-minor), then the 16-leaf warps', then the 8-leaf
+  // warps' -- every warp reads whole 128-byte lines of a column (64 bytes for the 8-leaf warps)
+  const uint32_t b0 = blockIdx.x * H::LEAVES;
+  if (slot < N4) mm_sponge_warp<4, DBG>(T2, b0 + 32 * (4 * slot + sched), cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
+  else if (slot < N4 + N2)
+    mm_sponge_warp<2, DBG>(T2, b0 + 128 * N4 + 16 * (4 * (slot - N4) + sched), cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
+  else
+    mm_sponge_warp<1, DBG>(T1, b0 + 128 * N4 + 64 * N2 + 8 * (4 * (slot - N4 - N2) + sched), cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
 }
