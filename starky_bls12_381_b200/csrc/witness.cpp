@@ -931,6 +931,16 @@ Fp12 fp12_from_limbs(const u32* l) {
   return r;
 }
 
+// a fresh trace buffer is gigabytes of first-touch page faults: zero it from several threads (FinalExp 2.4 GB: 1.9 -> 0.1 s)
+void zero_trace(void* p, size_t bytes) {
+  if (bytes < (64u << 20)) { memset(p, 0, bytes); return; }
+  const size_t parts = 8, step = (bytes / parts + 4095) & ~size_t(4095);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < parts; i++)
+    th.emplace_back([=] { const size_t a = std::min(bytes, i * step), b = std::min(bytes, (i + 1) * step); memset((char*)p + a, 0, b - a); });
+  for (auto& x : th) x.join();
+}
+
 thread_local std::string g_witness_error;
 
 }  // namespace
@@ -991,7 +1001,7 @@ int sb_witness_fp12_mul(const uint32_t* x, const uint32_t* y, uint32_t num_rows,
     if (num_rows < 12 || (num_rows & (num_rows - 1))) throw std::invalid_argument("witness: num_rows must be a power of two >= 16");
     const Fp12 X = fp12_from_limbs(x), Y = fp12_from_limbs(y);
     Trace tr = {trace_out, num_rows, woff::fp12_mul::TOTAL_COLUMNS};
-    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    zero_trace(trace_out, 4ull * num_rows * tr.cols);
     fill_trace_fp12_multiplication(tr, X, Y, 0, 11, 0);
     const Fp12 Z = fp12_mul_native(X, Y);
     for (int i = 0; i < 12; i++)
@@ -1019,7 +1029,7 @@ int sb_witness_ecc_agg(const uint32_t* points, const uint8_t* bits, uint32_t num
     if ((num_rows & (num_rows - 1)) || (size_t)(E::NUM_POINTS - 1) * 12 >= num_rows)
       throw std::invalid_argument("witness: stark doesn't have enough rows (power of two > 12 * 511)");
     Trace tr = {trace_out, num_rows, E::TOTAL_COLUMNS};
-    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    zero_trace(trace_out, 4ull * num_rows * tr.cols);
     std::vector<G1> pts(E::NUM_POINTS);
     for (uint32_t i = 0; i < E::NUM_POINTS; i++) {
       pts[i].x = Big::from_limbs(points + 24 * i, 12);
@@ -1069,7 +1079,7 @@ int sb_witness_pairing_precomp(const uint32_t* q, uint32_t num_rows, uint32_t* t
     if (num_rows < 16 || (num_rows & (num_rows - 1))) throw std::invalid_argument("witness: num_rows must be a power of two >= 16");
     const Fp2 x = fp2_from_limbs(q), y = fp2_from_limbs(q + 24), z = fp2_from_limbs(q + 48);
     Trace tr = {trace_out, num_rows, A::TOTAL_COLUMNS};
-    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    zero_trace(trace_out, 4ull * num_rows * tr.cols);
     const size_t last = num_rows - 1;
     const Fp2 z_inv = fp2_inv(z);
     generate_trace_fp2_mul(tr, z, z_inv, 0, last, A::Z_MULT_Z_INV_OFFSET);
@@ -1178,7 +1188,7 @@ int sb_witness_miller_loop(const uint32_t* p, const uint32_t* q, uint32_t num_ro
     const std::vector<Ell> ell = pairing_precomp_native(qx, qy, qz);
     const Fp12 res = miller_loop_native(x, y, ell);
     Trace tr = {trace_out, num_rows, M::TOTAL_COLUMNS};
-    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    zero_trace(trace_out, 4ull * num_rows * tr.cols);
     fill_trace_miller_loop(tr, x, y, ell, 0, num_rows - 1, 0);
     if (24 + 72 * ell.size() + 144 != M::PUBLIC_INPUTS) throw std::logic_error("witness: miller loop, coefficient count");
     for (int k = 0; k < 12; k++) { public_inputs_out[M::PIS_PX_OFFSET + k] = x.w[k]; public_inputs_out[M::PIS_PY_OFFSET + k] = y.w[k]; }
@@ -1203,7 +1213,7 @@ int sb_witness_final_exp(const uint32_t* x, uint32_t num_rows, uint32_t* trace_o
     if (num_rows != 8192) throw std::invalid_argument("witness: FinalExponentiateStark has 8192 rows (one row selector column per row)");
     const Fp12 X = fp12_from_limbs(x);
     Trace tr = {trace_out, num_rows, E::TOTAL_COLUMNS};
-    memset(trace_out, 0, 4ull * num_rows * tr.cols);
+    zero_trace(trace_out, 4ull * num_rows * tr.cols);
     const size_t last = num_rows - 1, OP = E::FINAL_EXP_OP_OFFSET;
     for (size_t r = 0; r < num_rows; r++) tr.at(r, E::FINAL_EXP_ROW_SELECTORS + r) = 1;
     put_fp12_rows(tr, 0, last, E::FINAL_EXP_INPUT_OFFSET, X);
