@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "250",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", os.environ.get("SB_BENCH_SMI_MS", "250"),
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -254,24 +254,27 @@ def measure_stark(ctx, sb, stark, steps, warmup, timed, seed, pageable_leg=True)
     ctx.trace_upload(p, host_ptr)
     resident = lambda: ctx.prove(p, None, pis, sb.TraceLayout.DEVICE_COLMAJOR_U64)
     e2e_fn = lambda: ctx.prove(p, host_ptr, pis, sb.TraceLayout.COLMAJOR_U64)
-    for _ in range(warmup):
-        resident()
+    # warm-up through the same loop as the timed steps: there the previous proof is still alive while the next one is made,
+    # so the library's pool of pinned proof buffers needs two of them (a first cudaMallocHost of 52 MB inside the timed
+    # region cost 40-80 ms of one step)
+    timed(resident, warmup)
     l0 = ctx.kernel_launches()
     dt, proofs = timed(resident, steps)
+    step_ms = list(getattr(timed, "step_ms", []))
     launches = ctx.kernel_launches() - l0
     stage_of = [pr if isinstance(pr, dict) else pr.timings for pr in proofs]
     stage = {k: float(np.mean([t[k] for t in stage_of])) for k in stage_of[0]}
     kern = {k: ctx.stage_ms(k) for k in ("lde", "leaf_hash", "merkle", "quotient")}
-    e2e_fn()
+    timed(e2e_fn, 2)
     dt_e2e, _ = timed(e2e_fn, steps)
-    out = {"ms": 1e3 * dt / steps, "ms_e2e": 1e3 * dt_e2e / steps, "stage_ms": stage, "kernel_ms": kern, "launches": int(launches),
+    out = {"ms": 1e3 * dt / steps, "ms_e2e": 1e3 * dt_e2e / steps, "step_ms": step_ms, "stage_ms": stage, "kernel_ms": kern, "launches": int(launches),
            "h2d_bytes": 8 * info.columns * info.num_rows + 8 * info.public_inputs,
            "d2h_bytes": int(proofs[-1].layout.total_words) * 8,
            "leaf_hash_mperm_s": (-(-info.columns // 8) * (info.num_rows << info.rate_bits)) / (kern["leaf_hash"] * 1e-3) / 1e6}
     if pageable_leg:
         cols, ptrs = pageable_columns(trace)
         pg = lambda: ctx.prove(p, ctypes.addressof(ptrs), pis, sb.TraceLayout.COLS_U64_PTRS)
-        pg()
+        timed(pg, 2)
         k = max(1, min(steps, 3))
         dt_pg, _ = timed(pg, k)
         out["ms_e2e_pageable_cols"] = 1e3 * dt_pg / k
@@ -424,8 +427,11 @@ def main():
         barrier()
         t0 = time.perf_counter()
         out = []
+        timed.step_ms = []
         for _ in range(steps):
+            ts = time.perf_counter()
             res = fn()
+            timed.step_ms.append(round(1e3 * (time.perf_counter() - ts), 2))     # (every fn here returns after its proof is complete)
             if out and hasattr(out[-1], "timings"):
                 out[-1] = out[-1].timings        # keep the stage timings, release the proof: its pinned buffer goes back to
             out.append(res)                       # the library's pool, as it does in a caller that consumes each proof
@@ -466,7 +472,7 @@ def main():
                                           "reference's Vec<PolynomialValues<F>>): gathered into pinned staging slabs inside the call" % C},
             "gpu_launches": m["launches"], "clocks": clocks,
             "roofline": roofline_for(args.stark, info, m["kernel_ms"], m["ms"], imad, hbm_peak, peak_src),
-            "cpu_baseline": cpu, "stage_ms": m["stage_ms"], "kernel_ms": m["kernel_ms"], "leaf_hash_mperm_s": m["leaf_hash_mperm_s"],
+            "cpu_baseline": cpu, "step_ms": m["step_ms"], "stage_ms": m["stage_ms"], "kernel_ms": m["kernel_ms"], "leaf_hash_mperm_s": m["leaf_hash_mperm_s"],
         }
         also = {}
         for name in also_names:
@@ -498,13 +504,12 @@ def main():
         fused = not args.no_fused
         res_fn = lambda: group.prove(p, local_dev.data_ptr(), pis, on_device=True, fused=fused)
         e2e_fn = lambda: group.prove(p, local_host.data_ptr(), pis, on_device=False, fused=fused)
-        for _ in range(args.warmup):
-            res_fn()
+        timed(res_fn, args.warmup)          # warm-up in the pattern of the timed loop (two proof buffers alive, see measure_stark)
         l0 = ctx.kernel_launches()
         dt, proofs = timed(res_fn, args.steps)
         launches = ctx.kernel_launches() - l0
         kern = {k: ctx.stage_ms(k) for k in ("lde", "leaf_hash", "merkle", "quotient")}
-        e2e_fn()
+        timed(e2e_fn, 2)
         dt_e2e, _ = timed(e2e_fn, args.steps)
         same = multi.same_on_every_rank(proofs[-1].words)
         clocks = sampler.stop() if rank == 0 else None
@@ -556,12 +561,12 @@ def main():
                     adev = ahost.cuda()
                     apis = np.random.Generator(np.random.PCG64(0xB2100000 + ai.stark_id)).integers(0, 1 << 32, ai.public_inputs, dtype=np.uint64)
                     fn = lambda: group.prove(ap_, adev.data_ptr(), apis, on_device=True, fused=fused)
-                    fn()
+                    timed(fn, 2)
                     k = max(1, min(args.steps, 3))
                     adt, aproofs = timed(fn, k)
                     akern = {kk: ctx.stage_ms(kk) for kk in ("lde", "leaf_hash", "merkle", "quotient")}
                     fe2e = lambda: group.prove(ap_, ahost.data_ptr(), apis, on_device=False, fused=fused)
-                    fe2e()
+                    timed(fe2e, 2)
                     adt2, _ = timed(fe2e, k)
                     return {"workload": WORKLOADS[name], "value": 1e3 * adt / k, "unit": "ms", "ranks": world,
                             "e2e": {"value": 1e3 * adt2 / k, "unit": "ms", "h2d_bytes_per_step": 8 * ag * ai.num_rows, "d2h_bytes_per_step": int(aproofs[-1].layout.total_words) * 8},
