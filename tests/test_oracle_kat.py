@@ -32,6 +32,28 @@ def test_round_constants_recipe():
         assert open(os.path.join(O.ROOT, rel)).read() == gen.header(rc)
 
 
+def test_fast_and_equivalent_round_constant_tables():
+    """poseidon_fast.h (sparse partial rounds for the round-1 kernels and the host transcript; POSEIDON_RC_EQ: the same
+    permutation with ONE non-zero constant per partial round, used by the matrix-instruction leaf sponge) is the output of
+    tools/gen_poseidon_fast.py, and both forms give the oracle's permutation."""
+    import importlib.util, os, sys
+    sys.path.insert(0, os.path.join(O.ROOT, "tools"))
+    spec = importlib.util.spec_from_file_location("genfast", os.path.join(O.ROOT, "tools", "gen_poseidon_fast.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    t = gen.derive()
+    t["rc_eq"] = gen.eq_constants(t["rc"])
+    for rel in ("oracle/poseidon_fast.h", "starky_bls12_381_b200/csrc/poseidon_fast.h"):
+        assert open(os.path.join(O.ROOT, rel)).read() == gen.header(t)
+    eq = t["rc_eq"]
+    assert len(eq) == 31 * 12 and eq[:48] == t["rc"][:48] and eq[27 * 12:30 * 12] == t["rc"][27 * 12:] and not any(eq[360:])
+    for r in range(4, 26):
+        assert not any(eq[12 * r + 1:12 * r + 12])                     # partial rounds: word 0 only
+    rng = np.random.default_rng(5)
+    for s in ([0] * 12, [P - 1] * 12, [int(x) % P for x in rng.integers(0, 1 << 64, 12, dtype=np.uint64)]):
+        want = [int(x) for x in O.permute(s)]
+        assert gen.permute_eq(s, eq) == want and gen.permute_fast(s, t) == want
+
+
 def test_goldilocks_facts():
     L = O.lib()
     assert pow(7, (P - 1) >> 32, P) == 1753635133440165772
