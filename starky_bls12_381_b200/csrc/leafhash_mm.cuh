@@ -78,7 +78,7 @@ __device__ __forceinline__ u64 shfl64(u64 v, unsigned src) {
 // shard on 8 GPUs), where wall time = chain length x time of one permutation and the fewest instructions per warp win.
 // DBG (lab only; tools/perf/poseidon_lab mmx).  Timing by elimination, wrong digests: 1 = no S-box in partial rounds,
 // 2 = no matrix instruction, 4 = no recombination, 8 = no S-box in full rounds.  Correct variants: 16 = the other fold in
-// the S-box, 32 = limb pairs as PRMT + IADD3 on the ALU pipe instead of IMAD.
+// the S-box, 32 = limb pairs as PRMT + IADD3 on the ALU pipe instead of IMAD.  256 (NL == 1, product): helper lanes.
 // Round constants in the equivalent form with one non-zero constant per partial round (poseidon_fast.h, RC_EQ):
 //   rcs: every round as (low half, high half), each a u64, for the layers that feed a full round; row 30 = zeros
 //   rcw: the word-0 constants of rounds 5..25 as accumulator images (16-bit chunks on the even limbs), [1] for the lanes
@@ -124,7 +124,8 @@ __device__ __forceinline__ void mm_sponge_warp(const MmTables& T, uint32_t base,
   bool live[NL];
 #pragma unroll
   for (int L = 0; L < NL; L++) {
-    const uint32_t raw = NL == 1 ? base + g : base + 16 * (L >> 1) + 2 * g + (L & 1);
+    // (helper-lane form, DBG & 256: four leaves per warp on quads 0..3; the lanes of quads 4..7 own nothing)
+    const uint32_t raw = NL == 1 ? (((DBG & 256) && g >= 4) ? n_leaves : base + g) : base + 16 * (L >> 1) + 2 * g + (L & 1);
     live[L] = raw < n_leaves;
     pos[L] = live[L] ? raw : n_leaves - 1;
   }
@@ -249,7 +250,17 @@ __device__ __forceinline__ void mm_sponge_warp(const MmTables& T, uint32_t base,
   // source order (x^2 of every value, then x^4 and x^3, then x^7) instead of one x^7 after the other
   auto sbox_all = [&]() {
     constexpr int G = (DBG & 192) == 64 ? 3 : (DBG & 192) == 128 ? 6 : (DBG & 192) == 192 ? 12 : 1;
-    if constexpr (G == 1 || (3 * NL) % G != 0) {
+    if constexpr (NL == 1 && (DBG & 256) != 0) {
+      // Helper lanes (the shapes with so few leaves that half of every warp can stay empty: MillerLoop 2048, FP12Mul 32):
+      // a lone warp issues one instruction every ~2 cycles, so a full round costs its instruction count -- lane + 16
+      // takes the third x^7 of lane's leaf and the warp executes two S-boxes instead of three.
+      const bool helper = lane >= 16;
+      const u64 w2 = shfl64(s[0][2], lane & 15);
+      u64 a = helper ? w2 : s[0][0], b = s[0][1];
+      a = mm_sbox<NL, DBG>(a); b = mm_sbox<NL, DBG>(b);
+      const u64 back = shfl64(a, lane | 16);
+      if (!helper) { s[0][0] = a; s[0][1] = b; s[0][2] = back; }
+    } else if constexpr (G == 1 || (3 * NL) % G != 0) {
 #pragma unroll
       for (int L = 0; L < NL; L++)
 #pragma unroll
@@ -327,7 +338,8 @@ __global__ void __launch_bounds__(NL == 1 ? 32 : 64) leaf_sponge_mm_kernel(const
   __shared__ MmTables T;
   mm_fill_tables<NL>(T);
   __syncthreads();
-  const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (8 * NL);
+  constexpr uint32_t LPW = (NL == 1 && (DBG & 256)) ? 4 : 8 * NL;          // leaves per warp
+  const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LPW;
   mm_sponge_warp<NL, DBG>(T, base, cols, leaf_len, n_leaves, log_block, digests, state_in, state_out);
 }
 

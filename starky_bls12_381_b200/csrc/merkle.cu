@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ 
 // 9 = one block per SM that gives every scheduler three 16-leaf warps and one 8-leaf warp (leaf_sponge_mm_het_kernel), when
 // the leaves fill that shape to more than 6/7 (FinalExp / ECCAgg: 32768 leaves on 148 SMs, 33152 places)
 typedef MmHet<0, 3, 1> HetShape;
+// 10 = the 8-leaf form with helper lanes (four leaves per warp, the other half of the warp takes a third of the full-round
+// S-boxes) while that still leaves at most one warp per scheduler (MillerLoop 2048, FP12Mul 32 leaves)
 static int sb_mm_kind(sb_ctx* ctx, uint32_t n_leaves) {
+  if ((uint64_t)n_leaves <= 16ull * ctx->sm_count) return 10;
   if ((uint64_t)n_leaves <= 64ull * ctx->sm_count) return 8;
   const uint64_t places = (uint64_t)HetShape::LEAVES * ctx->sm_count;
   if (n_leaves <= places && 7ull * n_leaves > 6 * places) return 9;
@@ -82,16 +85,17 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
   //   short chains (quotient / FRI leaves, <= 2 permutations): one thread per leaf, nothing to split;
   //   everything else: the dense MDS layer as an integer matrix instruction over the lanes of one warp (leafhash_mm.cuh),
   //     8 = 8 leaves per warp for the latency-bound shapes (PairingPrecomp 4096, MillerLoop 2048 leaves: every leaf is in
-  //         flight at once and wall time = chain length x latency of one permutation),
+  //         flight at once and wall time = chain length x latency of one permutation), 10 = the same with 4 leaves per
+  //         warp and helper lanes when there are at most 4 x 4 leaves per SM (MillerLoop, FP12Mul),
   //     6 = 16 and 7 = 32 leaves per warp for the throughput-bound ones, 9 = one block per SM with the same mix of 16- and
   //         8-leaf warps on every scheduler when the leaves fill that shape (FinalExp / ECCAgg: 32768 leaves on 148 SMs);
   //   round 1 / 2 kernels, still selectable: 13 = one state word per warp, sparse partial rounds with a reducer warp (the
   //     former latency kernel), 12 = its dense two-barrier variant, 4 = three words per thread, four warps per 32 leaves,
   //     dense MDS on dp2a (the former throughput kernel), 3 = the same on IMAD.WIDE, 5 = dp2a + sparse partial rounds.
-  // SB_LEAF_KERNEL=1|3|4|5|6|7|8|9|12|13 overrides the choice (profiling, tests).
+  // SB_LEAF_KERNEL=1|3|4|5|6|7|8|9|10|12|13 overrides the choice (profiling, tests).
   int kind = 1;
   if (leaf_len > 4 && perms > 2) kind = sb_mm_kind(ctx, n_leaves);
-  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 6 || v == 7 || v == 8 || v == 9 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
+  if (const char* e = getenv("SB_LEAF_KERNEL")) { int v = atoi(e); if (v == 1 || ((v == 3 || v == 4 || v == 5 || v == 6 || v == 7 || v == 8 || v == 9 || v == 10 || v == 12 || v == 13) && leaf_len > 4)) kind = v; }
   const uint32_t groups = (n_leaves + 31) / 32;
   if (kind == 13) {
     // SB_SP_VARIANT: lab variants of the sp kernel (leafhash.cuh); 0 = the round-1 kernel
@@ -111,6 +115,8 @@ void sb_hash_leaves_device(sb_ctx* ctx, const u64* d_cols, uint32_t leaf_len, ui
     LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 9) {
     launch_mm_het(ctx, d_cols, leaf_len, n_leaves, log_block, d_digests, nullptr, nullptr);
+  } else if (kind == 10) {
+    LAUNCH(ctx, (leaf_sponge_mm_kernel<1, 256>), (n_leaves + 3) / 4, 32, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 8) {
     LAUNCH(ctx, leaf_sponge_mm_kernel<1>, (n_leaves + 7) / 8, 32, 0, d_cols, leaf_len, n_leaves, log_block, d_digests);
   } else if (kind == 6) {
@@ -141,12 +147,14 @@ void sb_hash_leaves_stream(sb_ctx* ctx, const u64* d_cols, uint32_t n_cols, uint
   const char* e_old = getenv("SB_STREAM_OLD");                     // round-2 kernels (A/B runs, tests)
   const int old = e_old ? atoi(e_old) : 0;
   const int kind = sb_mm_kind(ctx, n_leaves);
-  if (old && kind == 8)
+  if (old && (kind == 8 || kind == 10))
     LAUNCH(ctx, leaf_sponge_sp_kernel<0>, groups, 416, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else if (old)
     LAUNCH(ctx, leaf_sponge_dp_kernel<0>, groups, 128, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else if (kind == 9)
     launch_mm_het(ctx, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
+  else if (kind == 10)
+    LAUNCH(ctx, (leaf_sponge_mm_kernel<1, 256>), (n_leaves + 3) / 4, 32, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else if (kind == 8)
     LAUNCH(ctx, leaf_sponge_mm_kernel<1>, (n_leaves + 7) / 8, 32, 0, d_cols, n_cols, n_leaves, log_block, d_digests, in, out);
   else if (kind == 7)

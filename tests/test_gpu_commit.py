@@ -54,7 +54,7 @@ def test_hash_leaves_ragged_lengths(ctx, leaf_len):
         assert np.array_equal(got[i], O.hash_or_noop(cols[:, i])), (leaf_len, i)
 
 
-@pytest.mark.parametrize("kernel", [1, 3, 4, 5, 6, 7, 8, 9, 12, 13])
+@pytest.mark.parametrize("kernel", [1, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13])
 @pytest.mark.parametrize("leaf_len,count", [(5, 33), (8, 64), (17, 1000), (24, 32), (135, 100), (1001, 70)])
 def test_hash_leaves_every_kernel_variant(ctx, monkeypatch, kernel, leaf_len, count):
     """The three leaf-sponge kernels (one thread per leaf / 3 words per thread / 1 word per warp) are bit-identical

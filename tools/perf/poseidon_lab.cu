@@ -279,6 +279,7 @@ int main(int argc, char** argv) {
       run("dp<0>", [&] { leaf_sponge_dp_kernel<0><<<g32, 128>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       run("sp<0>", [&] { leaf_sponge_sp_kernel<0><<<g32, 416>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       run("mm<1>  8 leaves per warp, block 32", [&] { leaf_sponge_mm_kernel<1><<<(sh.n_leaves + 7) / 8, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
+      run("mm<1> 4 leaves per warp + helper lanes", [&] { leaf_sponge_mm_kernel<1, 256><<<(sh.n_leaves + 3) / 4, 32>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       run("mm<2> 16 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<2><<<(sh.n_leaves + 31) / 32, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
       run("mm<4> 32 leaves per warp, block 64", [&] { leaf_sponge_mm_kernel<4><<<(sh.n_leaves + 63) / 64, 64>>>(d_cols, sh.leaf_len, sh.n_leaves, 0, d_dig); }, false);
 #define HET(N4, N2, N1, label) do { using Hh = MmHet<N4, N2, N1>; \
