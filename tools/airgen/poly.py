@@ -44,10 +44,12 @@ class Expander:
             return []
         return [nid]
 
-    def size(self, nid, memo={}):
-        key = (id(self.dag), nid)
-        if key in memo: return memo[key]
+    def size(self, nid):
+        # memo per instance: a process-wide table keyed by id(dag) handed the sizes of a collected DAG to a new one that
+        # was allocated at the same address (a test that extracts several programs in one process failed once in a while)
+        memo = self.__dict__.setdefault("_size_memo", {})
+        if nid in memo: return memo[nid]
         op, a, b = self.dag.nodes[nid]
         s = 1 if op in (CONST, LOCAL, NEXT, PI) else 1 + self.size(a) + self.size(b)
-        memo[key] = s
+        memo[nid] = s
         return s
