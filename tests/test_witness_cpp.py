@@ -112,6 +112,22 @@ def test_cpp_final_exp_trace_equals_the_python_restatement():
         witness_final_exp(x, 4096)                            # one row-selector column per row: 8192 rows only
 
 
+def test_api_generate_trace_rows_is_the_row_major_form_of_generate_trace():
+    """api.XStark.generate_trace_rows (C++ generators, the reference's Vec<[F; COLUMNS]> as uint32 rows) against
+    generate_trace (Python restatement, trace_rows_to_poly_values order) on the two small starks."""
+    rng = np.random.default_rng(0xB2007900)
+    st = sb.FP12MulStark.new(16)
+    x, y = W.random_fp12(rng), W.random_fp12(rng)
+    (cols, pis), (rows, pis2) = st.generate_trace(x, y), st.generate_trace_rows(x, y)
+    assert rows.dtype == np.uint32 and rows.shape == (16, st.info.columns)
+    assert np.array_equal(rows.astype(np.uint64).T, cols) and np.array_equal(pis, pis2)
+    st = sb.PairingPrecompStark.new(1024)
+    q = [_rand_fp2(rng) for _ in range(3)]
+    (cols, pis), (rows, pis2) = st.generate_trace(*q), st.generate_trace_rows(*q)
+    assert rows.shape == (1024, st.info.columns)
+    assert np.array_equal(rows.astype(np.uint64).T, cols) and np.array_equal(pis, pis2)
+
+
 def test_unreduced_operands_are_rejected():
     bad = (W.N.P,) + (0,) * 11
     with pytest.raises(sb.SbError):
