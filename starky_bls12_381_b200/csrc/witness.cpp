@@ -874,35 +874,63 @@ Fp12 fill_trace_fp12_conjugate(Trace& tr, const Fp12& x, size_t row, size_t col)
   return conj;
 }
 // miller_loop.rs:87-146
+// run `work(i)` for i in [0, n) on up to 8 host threads (the blocks of a trace are disjoint row ranges); the first
+// exception is rethrown on the calling thread
+template <class F> void parallel_blocks(size_t n, F&& work) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t workers = std::min<size_t>(n, std::max(1u, std::min(8u, hw ? hw : 1u)));
+  if (workers <= 1) { for (size_t i = 0; i < n; i++) work(i); return; }
+  std::atomic<size_t> next{0};
+  std::mutex err_mu;
+  std::string err;
+  std::vector<std::thread> th;
+  for (size_t w = 0; w < workers; w++)
+    th.emplace_back([&] {
+      for (size_t i; (i = next.fetch_add(1)) < n;) {
+        try { work(i); }
+        catch (const std::exception& ex) { std::lock_guard<std::mutex> g(err_mu); if (err.empty()) err = ex.what(); }
+      }
+    });
+  for (auto& x : th) x.join();
+  if (!err.empty()) throw std::runtime_error(err);
+}
 void fill_trace_miller_loop(Trace& tr, const Fp& x, const Fp& y, const std::vector<Ell>& ell, size_t s, size_t e, size_t col) {
   namespace M = woff::miller_loop;
   put_big_rows(tr, s, e, col + M::PX_OFFSET, x, 12);
   put_big_rows(tr, s, e, col + M::PY_OFFSET, y, 12);
+  // the accumulator chain first (values only: ~10 ms), then the 12-row blocks on several threads
+  struct Block { Fp12 f12; bool first_bit, last_bit, bitone; };
+  const size_t n_ops = std::min((e + 1 - s) / 12, ell.size());
+  std::vector<Block> blocks(n_ops);
   Fp12 f12 = fp12_one();
   int i = 62;
   bool bitone = false;
-  const size_t n_ops = std::min((e + 1 - s) / 12, ell.size());
   for (size_t j = 0; j < n_ops; j++) {
+    blocks[j] = {f12, j == 0, i == 0, bitone};
+    const Ell& c = ell[j];
+    f12 = fp12_multiply_by_014(f12, c.c[0], fp2_mul_fp(c.c[1], x), fp2_mul_fp(c.c[2], y));
+    if (((BLS_X >> i) & 1) && !bitone) bitone = true;
+    else if (j + 1 < ell.size()) { f12 = fp12_mul_native(f12, f12); i--; bitone = false; }
+  }
+  parallel_blocks(n_ops, [&](size_t j) {
+    const Block& b = blocks[j];
     const size_t s_row = s + 12 * j, e_row = s_row + 11;
-    if (j == 0) tr.set_rows(s_row, e_row, col + M::FIRST_BIT_SELECTOR_OFFSET, 1);
-    if (i == 0) tr.set_rows(s_row, e_row, col + M::LAST_BIT_SELECTOR_OFFSET, 1);
-    if (bitone) tr.set_rows(s_row, e_row, col + M::BIT1_SELECTOR_OFFSET, 1);
+    if (b.first_bit) tr.set_rows(s_row, e_row, col + M::FIRST_BIT_SELECTOR_OFFSET, 1);
+    if (b.last_bit) tr.set_rows(s_row, e_row, col + M::LAST_BIT_SELECTOR_OFFSET, 1);
+    if (b.bitone) tr.set_rows(s_row, e_row, col + M::BIT1_SELECTOR_OFFSET, 1);
     tr.set_rows(s_row, e_row, col + M::ELL_COEFFS_INDEX_OFFEST + j, 1);
     const Ell& c = ell[j];
     for (int k = 0; k < 3; k++) put_fp2_rows(tr, s_row, e_row, col + M::ELL_COEFFS_OFFSET + 24 * k, c.c[k]);
-    put_fp12_rows(tr, s_row, e_row, col + M::F12_OFFSET, f12);
+    put_fp12_rows(tr, s_row, e_row, col + M::F12_OFFSET, b.f12);
     if (j != 0) tr.at(s_row, col + M::FIRST_ROW_SELECTOR_OFFSET) = 1;
     fill_trace_fp2_fp_mul(tr, c.c[1], x, s_row, e_row, col + M::O1_CALC_OFFSET);
     const Fp2 o1 = fp2_mul_fp(c.c[1], x);
     fill_trace_fp2_fp_mul(tr, c.c[2], y, s_row, e_row, col + M::O4_CALC_OFFSET);
     const Fp2 o4 = fp2_mul_fp(c.c[2], y);
-    fill_trace_multiply_by_014(tr, f12, c.c[0], o1, o4, s_row, e_row, col + M::F12_MUL_BY_014_OFFSET);
-    f12 = fp12_multiply_by_014(f12, c.c[0], o1, o4);
-    fill_trace_fp12_multiplication(tr, f12, f12, s_row, e_row, col + M::F12_SQ_CALC_OFFSET);
-    const Fp12 f12_sq = fp12_mul_native(f12, f12);
-    if (((BLS_X >> i) & 1) && !bitone) bitone = true;
-    else if (j + 1 < ell.size()) { f12 = f12_sq; i--; bitone = false; }
-  }
+    fill_trace_multiply_by_014(tr, b.f12, c.c[0], o1, o4, s_row, e_row, col + M::F12_MUL_BY_014_OFFSET);
+    const Fp12 g = fp12_multiply_by_014(b.f12, c.c[0], o1, o4);
+    fill_trace_fp12_multiplication(tr, g, g, s_row, e_row, col + M::F12_SQ_CALC_OFFSET);
+  });
   f12 = fp12_conjugate(f12);
   put_fp12_rows(tr, s, e, col + M::MILLER_LOOP_RES_OFFSET, f12);
   negate6_rows(tr, half(f12, 1), s, e, col + M::RES_CONJUGATE_OFFSET);
@@ -1287,25 +1315,11 @@ int sb_witness_final_exp(const uint32_t* x, uint32_t num_rows, uint32_t* trace_o
       put_fp12_rows(tr, 0, last, OFF[k], t[k]);
     };
     {
-      // longest first: the five exponentiations, then everything else, over up to 8 threads
+      // longest first: the five exponentiations, then everything else
       std::vector<int> order;
       for (int k = 0; k < 32; k++) if (STEPS[k].kind == CEXP) order.push_back(k);
       for (int k = 0; k < 32; k++) if (STEPS[k].kind != CEXP) order.push_back(k);
-      std::atomic<size_t> next{0};
-      std::mutex err_mu;
-      std::string err;
-      const unsigned hw = std::thread::hardware_concurrency();
-      const unsigned workers = std::max(1u, std::min(8u, hw ? hw : 1u));
-      std::vector<std::thread> th;
-      for (unsigned w = 0; w < workers; w++)
-        th.emplace_back([&] {
-          for (size_t i; (i = next.fetch_add(1)) < order.size();) {
-            try { fill_step(order[i]); }
-            catch (const std::exception& ex) { std::lock_guard<std::mutex> g(err_mu); if (err.empty()) err = ex.what(); }
-          }
-        });
-      for (auto& x : th) x.join();
-      if (!err.empty()) throw std::runtime_error(err);
+      parallel_blocks(order.size(), [&](size_t i) { fill_step(order[i]); });
     }
     for (int i = 0; i < 12; i++)
       for (int k = 0; k < 12; k++) {
